@@ -1,0 +1,594 @@
+// ref_harness.cpp -- C entry points around the UNMODIFIED reference sources (/root/reference/source).
+//
+// TEST INFRASTRUCTURE (oracle/): only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+// --impl reference legs may load the library built from this file.  It is built by oracle/Makefile
+// into oracle/_ref/libref_cb.so, straight from the sources where they lie under /root/reference
+// (never copied), with:   g++ -O2 -std=c++17 -ffp-contract=off -include ref_shim.h -I$(REF)/source
+//
+// What is the reference's and what is ours:
+//   * every geometric / shading / sampling / photon / kd-tree routine called below is the
+//     reference's own code, reached by `#include "Main.cpp"` (main renamed, `private` opened);
+//   * the only logic re-stated here is glue the reference keeps inside monolithic loops, so that a
+//     random stream can be selected per unit of work:
+//       - the pixel loop of Renderer::render           (Renderer.cpp:219-260)
+//       - the emission loop of PhotonMap::PhotonMap    (PhotonMap.h:19-44)
+//       - the composite of Renderer::render            (Renderer.cpp:262-265)
+//     Each is a handful of lines and cites the lines it follows.
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <exception>
+#include <fstream>
+#include <functional>
+#include <iostream>
+#include <limits>
+#include <random>
+#include <sstream>
+#include <stdexcept>
+#include <string>
+#include <unordered_map>
+#include <vector>
+#include <array>
+#include <assert.h>
+#include <math.h>
+
+#include "rng_contract.h"
+
+#define private public
+#define protected public
+#define main ref_main
+#include "Main.cpp"  // the reference program, found through -I/root/reference/source
+#undef main
+#undef private
+#undef protected
+
+#ifndef RT_ORACLE_SHARED_RNG
+#error "build with -include ref_shim.h (shared-RNG oracle)"
+#endif
+
+// ---------------------------------------------------------------- the engine behind `gen`
+static uint64_t g_key = 0;
+static uint32_t g_ctr = 0;
+static uint64_t g_words_drawn = 0;
+std::cb_engine::result_type std::cb_engine::operator()() {
+  ++g_words_drawn;
+  return rto_word(g_key, g_ctr++);
+}
+static inline void set_stream(uint64_t seed, uint64_t domain, uint64_t index) {
+  g_key = rto_stream_key(seed, domain, index);
+  g_ctr = 0;
+}
+
+namespace {
+struct RefScene {
+  Scene scene;
+  int w, h;
+};
+struct RefPhotonMap {
+  std::vector<Particle> list;
+  kdtree* tree = nullptr;
+  int depth_hist[20] = {0};
+  ~RefPhotonMap() { delete tree; }
+};
+struct Quiet {  // the reference prints banners/progress to cout; silence it while we are inside
+  std::streambuf* old;
+  std::ostringstream sink;
+  Quiet() : old(std::cout.rdbuf(sink.rdbuf())) {}
+  ~Quiet() { std::cout.rdbuf(old); }
+};
+}  // namespace
+
+extern "C" {
+
+// Build the reference's scene exactly as Main.cpp:165-208 does.  `custom_off` (nullable) replaces
+// ../meshes/cube_tri.off as mesh_cube (cfg 1/2); everything else is stock.
+void* ref_scene_create(const char* meshdir, const char* custom_off, int w, int h) {
+  Quiet q;
+  RefScene* rs = new RefScene();
+  rs->w = w;
+  rs->h = h;
+  Scene& scene = rs->scene;
+  Camera camera(Vec3f(0.3f, 0.6f, 2.3f), Vec3f(), Vec3f(0.f, 1.f, 0.f), 60.f, float(size_t(w)) / size_t(h));
+  scene.camera() = camera;
+  initLightSources(scene);
+  Mesh mesh_walls, mesh_cube, mesh_cube2, mesh_left_wall, mesh_right_wall;
+  initLightMaterials(mesh_walls, mesh_cube, mesh_cube2, mesh_left_wall, mesh_right_wall);
+  try {
+    std::string dir(meshdir);
+    mesh_cube.loadOFF(custom_off && custom_off[0] ? std::string(custom_off) : dir + "/cube_tri.off");
+    mesh_cube2.loadOFF(dir + "/cube_tri2.off");
+  } catch (const std::exception& e) {
+    std::cerr << e.what() << std::endl;
+    delete rs;
+    return nullptr;
+  }
+  float box_size = 1.51f, ceiling = 1.5f;
+  createCornellBox(box_size, ceiling, mesh_walls, mesh_right_wall, mesh_left_wall);
+  rotationY(mesh_cube, M_PI / 4.5f);
+  rotationY(mesh_cube2, -M_PI / 4.5f);
+  scene.meshes().push_back(mesh_walls);
+  scene.meshes().push_back(mesh_left_wall);
+  scene.meshes().push_back(mesh_right_wall);
+  scene.meshes().push_back(mesh_cube);
+  scene.meshes().push_back(mesh_cube2);
+  return rs;
+}
+
+// Build a reference Scene from flat arrays (used to hand the synthetic subdivided mesh and other
+// generated scenes to the reference code).  Light bases are recomputed by the reference's own
+// LightSource constructor from (position, direction = position + normal); the caller checks they
+// reproduce.  Camera: the reference's own constructor from the stock look-at (Main.cpp:169-170).
+void* ref_scene_from_flat(int V, int T, int M, int L, const float* pos, const float* nrm, const int32_t* tri,
+                          const int32_t* mesh_tri_off, const int32_t* mesh_vtx_off, const float* mats,
+                          const float* lights_pos_color_dir_int_side /* 11 per light */, int w, int h) {
+  (void)V; (void)T;
+  RefScene* rs = new RefScene();
+  rs->w = w;
+  rs->h = h;
+  Scene& scene = rs->scene;
+  Camera camera(Vec3f(0.3f, 0.6f, 2.3f), Vec3f(), Vec3f(0.f, 1.f, 0.f), 60.f, float(size_t(w)) / size_t(h));
+  scene.camera() = camera;
+  for (int l = 0; l < L; l++) {
+    const float* p = lights_pos_color_dir_int_side + 11 * l;
+    scene.lightsources().push_back(
+        LightSource(Vec3f(p[0], p[1], p[2]), Vec3f(p[3], p[4], p[5]), Vec3f(p[6], p[7], p[8]), p[9], p[10]));
+  }
+  for (int m = 0; m < M; m++) {
+    Mesh mesh;
+    int v0 = mesh_vtx_off[m], v1 = mesh_vtx_off[m + 1];
+    for (int v = v0; v < v1; v++) {
+      mesh.vertexPositions().push_back(Vec3f(pos[3 * v], pos[3 * v + 1], pos[3 * v + 2]));
+      mesh.vertexNormals().push_back(Vec3f(nrm[3 * v], nrm[3 * v + 1], nrm[3 * v + 2]));
+    }
+    for (int t = mesh_tri_off[m]; t < mesh_tri_off[m + 1]; t++)
+      mesh.indexedTriangles().push_back(Vec3i(tri[3 * t] - v0, tri[3 * t + 1] - v0, tri[3 * t + 2] - v0));
+    const float* a = mats + 8 * m;
+    mesh.material() = Material(a[0], a[1], Vec3f(a[2], a[3], a[4]), Vec3f(a[5], a[6], a[7]));
+    scene.meshes().push_back(mesh);
+  }
+  return rs;
+}
+
+void ref_scene_destroy(void* s) { delete static_cast<RefScene*>(s); }
+
+void ref_scene_counts(void* s, int32_t out[4]) {
+  const Scene& scene = static_cast<RefScene*>(s)->scene;
+  int V = 0, T = 0;
+  for (const Mesh& m : scene.meshes()) {
+    V += (int)m.vertexPositions().size();
+    T += (int)m.indexedTriangles().size();
+  }
+  out[0] = V;
+  out[1] = T;
+  out[2] = (int)scene.meshes().size();
+  out[3] = (int)scene.lightsources().size();
+}
+
+// Flat dump of what crosses the Renderer::render seam.
+// mats: 8 floats/mesh {kd, alpha, albedo[3], F0[3]};
+// lights: 21 floats/light {position, color, normal, vertical, horizontal, intensity, side, ac, al, aq, factor};
+// lights_ctor: 11 floats/light {position, color, direction, intensity, side} (constructor arguments);
+// cam: 12 floats {position, lowerLeft, horizontal, vertical}.
+void ref_scene_flatten(void* s, float* pos, float* nrm, int32_t* tri, int32_t* mesh_tri_off, int32_t* mesh_vtx_off,
+                       float* mats, float* lights, float* lights_ctor, float* cam) {
+  Scene& scene = static_cast<RefScene*>(s)->scene;
+  int vbase = 0, tbase = 0, mi = 0;
+  for (Mesh& m : scene.meshes()) {
+    mesh_tri_off[mi] = tbase;
+    mesh_vtx_off[mi] = vbase;
+    const auto& P = m.vertexPositions();
+    const auto& N = m.vertexNormals();
+    const auto& T = m.indexedTriangles();
+    for (size_t i = 0; i < P.size(); i++)
+      for (int c = 0; c < 3; c++) {
+        pos[3 * (vbase + i) + c] = P[i][c];
+        nrm[3 * (vbase + i) + c] = N[i][c];
+      }
+    for (size_t i = 0; i < T.size(); i++)
+      for (int c = 0; c < 3; c++) tri[3 * (tbase + i) + c] = T[i][c] + vbase;
+    Material& mat = m.material();
+    float* a = mats + 8 * mi;
+    a[0] = mat.m_kd;
+    a[1] = mat.m_alpha;
+    for (int c = 0; c < 3; c++) {
+      a[2 + c] = mat.m_albedo[c];
+      a[5 + c] = mat.m_F0[c];
+    }
+    vbase += (int)P.size();
+    tbase += (int)T.size();
+    mi++;
+  }
+  mesh_tri_off[mi] = tbase;
+  mesh_vtx_off[mi] = vbase;
+  int li = 0;
+  for (LightSource& l : scene.lightsources()) {
+    float* a = lights + 21 * li;
+    float* b = lights_ctor + 11 * li;
+    for (int c = 0; c < 3; c++) {
+      a[c] = l.m_position[c];
+      a[3 + c] = l.m_color[c];
+      a[6 + c] = l.m_normal[c];
+      a[9 + c] = l.m_vertical[c];
+      a[12 + c] = l.m_horizontal[c];
+      b[c] = l.m_position[c];
+      b[3 + c] = l.m_color[c];
+      b[6 + c] = l.m_direction[c];
+    }
+    a[15] = l.m_intensity;
+    a[16] = l.m_sideLength;
+    a[17] = l.ac;
+    a[18] = l.al;
+    a[19] = l.aq;
+    a[20] = l.m_factor;
+    b[9] = l.m_intensity;
+    b[10] = l.m_sideLength;
+    li++;
+  }
+  Camera& c = scene.camera();
+  for (int k = 0; k < 3; k++) {
+    cam[k] = c.m_position[k];
+    cam[3 + k] = c.m_lowerLeftCorner[k];
+    cam[6 + k] = c.m_horizontal[k];
+    cam[9 + k] = c.m_vertical[k];
+  }
+}
+
+// Mesh::loadOFF (Mesh.h:57-90) on an arbitrary file: positions, normals, local triangles.
+// Call with null outputs to get the counts.  Returns 0, or 1 when the loader throws.
+int ref_load_off(const char* path, int32_t* counts /*V,T*/, float* pos, float* nrm, int32_t* tri) {
+  Mesh m;
+  try {
+    m.loadOFF(path);
+  } catch (const std::exception& e) {
+    return 1;
+  }
+  counts[0] = (int)m.vertexPositions().size();
+  counts[1] = (int)m.indexedTriangles().size();
+  if (pos)
+    for (int i = 0; i < counts[0]; i++)
+      for (int c = 0; c < 3; c++) {
+        pos[3 * i + c] = m.vertexPositions()[i][c];
+        nrm[3 * i + c] = m.vertexNormals()[i][c];
+      }
+  if (tri)
+    for (int i = 0; i < counts[1]; i++)
+      for (int c = 0; c < 3; c++) tri[3 * i + c] = m.indexedTriangles()[i][c];
+  return 0;
+}
+
+// RayTracer::rayTrace (RayTracer.h:27-53) on a batch.  rays: 6 floats (origin, direction).
+// tri3 holds the reference's returned Vec3i (MESH-LOCAL vertex indices); outputs of a miss are left 0.
+void ref_trace(void* s, const float* rays, int64_t n, int32_t* hit, int32_t* mesh, int32_t* tri3, float* uvd) {
+  const Scene& scene = static_cast<RefScene*>(s)->scene;
+  RayTracer rt;
+  for (int64_t i = 0; i < n; i++) {
+    Ray ray(Vec3f(rays[6 * i], rays[6 * i + 1], rays[6 * i + 2]),
+            Vec3f(rays[6 * i + 3], rays[6 * i + 4], rays[6 * i + 5]));
+    size_t mi = 0;
+    Vec3i t(0, 0, 0);
+    float u = 0, v = 0, d = 0;
+    bool found = rt.rayTrace(ray, scene, mi, t, u, v, d);
+    hit[i] = found ? 1 : 0;
+    mesh[i] = found ? (int32_t)mi : 0;
+    for (int c = 0; c < 3; c++) tri3[3 * i + c] = found ? t[c] : 0;
+    uvd[3 * i] = found ? u : 0.f;
+    uvd[3 * i + 1] = found ? v : 0.f;
+    uvd[3 * i + 2] = found ? d : 0.f;
+  }
+}
+
+// Ray::triangleIntersect (Ray.cpp:9-24) on a batch: in 15 floats (o, d, p0, p1, p2); out flag + u,v,t
+// (u,v,t are written by the reference before its range tests, so they are returned for misses too).
+void ref_triangle_intersect(const float* in, int64_t n, int32_t* flag, float* uvt) {
+  for (int64_t i = 0; i < n; i++) {
+    const float* a = in + 15 * i;
+    Ray ray(Vec3f(a[0], a[1], a[2]), Vec3f(a[3], a[4], a[5]));
+    float u = 0, v = 0, t = 0;
+    bool r = ray.triangleIntersect(Vec3f(a[6], a[7], a[8]), Vec3f(a[9], a[10], a[11]), Vec3f(a[12], a[13], a[14]),
+                                   u, v, t);
+    flag[i] = r;
+    uvt[3 * i] = u;
+    uvt[3 * i + 1] = v;
+    uvt[3 * i + 2] = t;
+  }
+}
+
+// Material::evaluateColorResponse (Material.h:25-36).  in: 9 floats (normal, wi, wo) per item.
+void ref_bsdf(const float* mat8, const float* in, int64_t n, float* out) {
+  Material m(mat8[0], mat8[1], Vec3f(mat8[2], mat8[3], mat8[4]), Vec3f(mat8[5], mat8[6], mat8[7]));
+  for (int64_t i = 0; i < n; i++) {
+    const float* a = in + 9 * i;
+    Vec3f r = m.evaluateColorResponse(Vec3f(a[0], a[1], a[2]), Vec3f(a[3], a[4], a[5]), Vec3f(a[6], a[7], a[8]));
+    for (int c = 0; c < 3; c++) out[3 * i + c] = r[c];
+  }
+}
+
+// LightSource::evaluateLight (LightSource.h:56-59) at points.
+void ref_light_eval(void* s, int light, const float* pts, int64_t n, float* out) {
+  LightSource l = static_cast<RefScene*>(s)->scene.lightsources()[light];
+  for (int64_t i = 0; i < n; i++) {
+    Vec3f r = l.evaluateLight(Vec3f(pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]));
+    for (int c = 0; c < 3; c++) out[3 * i + c] = r[c];
+  }
+}
+
+// LightSource::randAreaPosition (LightSource.h:46-49): n positions, item i drawn from stream
+// (seed, domain, index0+i) starting at word 0.
+void ref_light_sample(void* s, int light, uint64_t seed, uint64_t domain, uint64_t index0, int64_t n, float* out) {
+  LightSource l = static_cast<RefScene*>(s)->scene.lightsources()[light];
+  for (int64_t i = 0; i < n; i++) {
+    set_stream(seed, domain, index0 + i);
+    Vec3f r = l.randAreaPosition();
+    for (int c = 0; c < 3; c++) out[3 * i + c] = r[c];
+  }
+}
+
+// RayTracer::jitterSample (RayTracer.h:109-117) for sample index i of N, from stream word 0.
+void ref_jitter(uint64_t seed, uint64_t domain, uint64_t index0, int64_t n, int sample, int nsamples, float* out2) {
+  RayTracer rt;
+  for (int64_t i = 0; i < n; i++) {
+    set_stream(seed, domain, index0 + i);
+    Vec3f r = rt.jitterSample(sample, nsamples);
+    out2[2 * i] = r[0];
+    out2[2 * i + 1] = r[1];
+  }
+}
+
+// RayTracer::hsphereUniformSample (RayTracer.h:95-107) around normals (3 floats each), from word 0.
+void ref_hsphere(uint64_t seed, uint64_t domain, uint64_t index0, int64_t n, const float* normals, float* out3) {
+  RayTracer rt;
+  for (int64_t i = 0; i < n; i++) {
+    set_stream(seed, domain, index0 + i);
+    Vec3f r = rt.hsphereUniformSample(Vec3f(normals[3 * i], normals[3 * i + 1], normals[3 * i + 2]), M_PI / 2.f);
+    for (int c = 0; c < 3; c++) out3[3 * i + c] = r[c];
+  }
+}
+
+// Raw words and libstdc++ distribution draws from one stream (pins the word -> uniform arithmetic).
+void ref_rng_words(uint64_t seed, uint64_t domain, uint64_t index, int n, uint32_t* out) {
+  set_stream(seed, domain, index);
+  for (int i = 0; i < n; i++) out[i] = gen();
+}
+void ref_rng_uniform_float(uint64_t seed, uint64_t domain, uint64_t index, int n, float a, float b, float* out) {
+  set_stream(seed, domain, index);
+  std::uniform_real_distribution<float> dis(a, b);
+  for (int i = 0; i < n; i++) out[i] = dis(gen);
+}
+void ref_rng_uniform_double(uint64_t seed, uint64_t domain, uint64_t index, int n, double a, double b, double* out) {
+  set_stream(seed, domain, index);
+  std::uniform_real_distribution<> dis(a, b);
+  for (int i = 0; i < n; i++) out[i] = dis(gen);
+}
+
+// Camera::rayAt (Camera.h:27-30) through the pixel-centre formula of Renderer.cpp:233-234 with a
+// given jitter: in 2 floats (shiftX, shiftY) per item for pixel (x,y); out 6 floats.
+void ref_camera_rays(void* s, const int32_t* xy, const float* shift, int64_t n, float* rays) {
+  RefScene* rs = static_cast<RefScene*>(s);
+  const Camera& camera = rs->scene.camera();
+  size_t w = rs->w, h = rs->h;
+  for (int64_t i = 0; i < n; i++) {
+    int x = xy[2 * i], y = xy[2 * i + 1];
+    float shiftX = shift[2 * i], shiftY = shift[2 * i + 1];
+    Ray ray = camera.rayAt((x + shiftX) / (float)w, 1.f - (y + shiftY) / (float)h);
+    for (int c = 0; c < 3; c++) {
+      rays[6 * i + c] = ray.origin()[c];
+      rays[6 * i + 3 + c] = ray.direction()[c];
+    }
+  }
+}
+
+// ---------------------------------------------------------------- photon map + kd-tree
+// The emission loop of PhotonMap::PhotonMap (PhotonMap.h:19-44) with one random stream per path:
+// path p of light l uses stream (seed, PHOTON, l*perLight + p).  calculatePhotonPath is the
+// reference's own (PhotonMap.h:92-155).
+void* ref_photon_map_create(void* s, int numPhotons, uint64_t seed, int first_path, int num_paths) {
+  Quiet q;
+  const Scene& scene = static_cast<RefScene*>(s)->scene;
+  RefPhotonMap* pm = new RefPhotonMap();
+  PhotonMap ref;
+  RayTracer rayTracer;
+  ref.m_rayTracer = rayTracer;
+  if (numPhotons > 0) {
+    float lightPdf = 1.f / scene.lightsources().size();
+    int photonsPerLS = (int)(numPhotons * lightPdf);
+    int p0 = first_path < 0 ? 0 : first_path;
+    int p1 = num_paths < 0 ? photonsPerLS : std::min(photonsPerLS, p0 + num_paths);
+    uint64_t li = 0;
+    for (LightSource lightSource : scene.lightsources()) {
+      Vec3f lsNormal = lightSource.normal();
+      for (int i = p0; i < p1; i++) {
+        set_stream(seed, RTO_DOMAIN_PHOTON, li * (uint64_t)photonsPerLS + (uint64_t)i);
+        Vec3f startPosition = lightSource.randAreaPosition(),
+              startDirection = ref.m_rayTracer.hsphereUniformSample(lsNormal, M_PI / 2.f);
+        float pdf = dot(normalize(startDirection), normalize(lsNormal)),
+              weight = lightSource.radiance(startPosition) / (pdf * lightPdf);
+        Ray ray(startPosition, startDirection);
+        Particle photon({0., 0., 0.}, {0., 0., 0.}, weight);
+        int depth = ref.calculatePhotonPath(scene, ray, photon, 0, false);
+        if (depth >= 0) pm->depth_hist[depth]++;
+      }
+      li++;
+    }
+  }
+  pm->list = ref.m_list;
+  if (!pm->list.empty()) pm->tree = new kdtree(pm->list.begin(), pm->list.end());
+  return pm;
+}
+
+// Wrap a given particle list (7 floats each: position, incomeDirection, weight) in the reference kd-tree.
+void* ref_photon_map_from_list(const float* particles, int64_t n) {
+  RefPhotonMap* pm = new RefPhotonMap();
+  for (int64_t i = 0; i < n; i++) {
+    const float* a = particles + 7 * i;
+    pm->list.push_back(Particle(Vec3f(a[0], a[1], a[2]), Vec3f(a[3], a[4], a[5]), a[6]));
+  }
+  if (!pm->list.empty()) pm->tree = new kdtree(pm->list.begin(), pm->list.end());
+  return pm;
+}
+void ref_photon_map_destroy(void* p) { delete static_cast<RefPhotonMap*>(p); }
+int64_t ref_photon_map_size(void* p) { return (int64_t)static_cast<RefPhotonMap*>(p)->list.size(); }
+void ref_photon_map_get(void* p, float* particles, int32_t* depth_hist) {
+  RefPhotonMap* pm = static_cast<RefPhotonMap*>(p);
+  for (size_t i = 0; i < pm->list.size(); i++) {
+    const Particle& a = pm->list[i];
+    for (int c = 0; c < 3; c++) {
+      particles[7 * i + c] = a.position()[c];
+      particles[7 * i + 3 + c] = a.incomeDirection()[c];
+    }
+    particles[7 * i + 6] = a.weight();
+  }
+  if (depth_hist)
+    for (int i = 0; i < 20; i++) depth_hist[i] = pm->depth_hist[i];
+}
+// The tree as built by kdtree::make_tree (kdtree.h:60-69): node array order + child links as indices.
+void ref_kdtree_layout(void* p, float* nodes7, int32_t* left, int32_t* right, int32_t* root) {
+  RefPhotonMap* pm = static_cast<RefPhotonMap*>(p);
+  kdtree* t = pm->tree;
+  const auto* base = t->m_nodes.data();
+  for (size_t i = 0; i < t->m_nodes.size(); i++) {
+    const Particle& a = t->m_nodes[i].m_point;
+    for (int c = 0; c < 3; c++) {
+      nodes7[7 * i + c] = a.position()[c];
+      nodes7[7 * i + 3 + c] = a.incomeDirection()[c];
+    }
+    nodes7[7 * i + 6] = a.weight();
+    left[i] = t->m_nodes[i].m_left ? (int32_t)(t->m_nodes[i].m_left - base) : -1;
+    right[i] = t->m_nodes[i].m_right ? (int32_t)(t->m_nodes[i].m_right - base) : -1;
+  }
+  *root = t->m_root ? (int32_t)(t->m_root - base) : -1;
+}
+// kdtree::knearest (kdtree.h:180-195): k result particles per query, in the reference's output order.
+// Returns 0, or 1 when the reference throws (empty tree / k too large).
+int ref_knn(void* p, const float* q3, int64_t nq, int k, float* out7, int64_t* visited) {
+  RefPhotonMap* pm = static_cast<RefPhotonMap*>(p);
+  if (!pm->tree) return 1;
+  try {
+    for (int64_t i = 0; i < nq; i++) {
+      Particle query;
+      query.position() = Vec3f(q3[3 * i], q3[3 * i + 1], q3[3 * i + 2]);
+      std::vector<Particle> result;
+      pm->tree->knearest(query, k, result);
+      if (visited) visited[i] = (int64_t)pm->tree->m_visited;
+      for (int j = 0; j < k; j++) {
+        float* o = out7 + 7 * (i * k + j);
+        for (int c = 0; c < 3; c++) {
+          o[c] = result[j].position()[c];
+          o[3 + c] = result[j].incomeDirection()[c];
+        }
+        o[6] = result[j].weight();
+      }
+    }
+  } catch (const std::exception& e) {
+    return 1;
+  }
+  return 0;
+}
+
+// ---------------------------------------------------------------- the render loop
+// The pixel loop of Renderer::render (Renderer.cpp:219-260) over the window [x0,x1) x [y0,y1) and
+// the sample range [s0,s1) of an N-sample w x h render; sample i of pixel (x,y) draws from stream
+// (seed, PIXEL, i*w*h + y*w + x).  calculateColorRay/Path, shade, normalizeColor, jitterSample,
+// Camera::rayAt are the reference's own.  Window-relative outputs, row-major:
+//   samples  [(s-s0)][(y-y0)][(x-x0)][3]   clamped per-sample colours (Renderer.cpp:254)   (nullable)
+//   found    same shape, 1 byte: posIntersectionFound                                      (nullable)
+//   sum_rgb  [(y-y0)][(x-x0)][3]  += in sample order (Renderer.cpp:258)
+//   counter  [(y-y0)][(x-x0)]     += (Renderer.cpp:255-257)
+// photon_map: handle from ref_photon_map_* or null.  Returns 0, or 1 on a reference exception.
+int ref_render(void* s, int N, int mode, int numPhotons, int k, uint64_t seed, void* photon_map, int x0, int y0,
+               int x1, int y1, int s0, int s1, float* samples, int8_t* found, float* sum_rgb, int32_t* counter) {
+  Quiet q;
+  RefScene* rs = static_cast<RefScene*>(s);
+  RefPhotonMap* pm = static_cast<RefPhotonMap*>(photon_map);
+  size_t w = rs->w, h = rs->h;
+  RayTracer rayTracer;
+  Renderer r = (numPhotons > 0) ? Renderer(rs->scene, N, mode, rayTracer, numPhotons, k)
+                                : Renderer(rs->scene, N, mode, rayTracer);
+  const Camera& camera = r.m_scene.camera();
+  kdtree empty_tree((Particle*)nullptr, (Particle*)nullptr);
+  kdtree& photonTree = (pm && pm->tree) ? *pm->tree : empty_tree;
+  int ww = x1 - x0, wh = y1 - y0;
+  try {
+    for (int i = s0; i < s1; i++) {
+      for (int y = y0; y < y1; y++) {
+        for (int x = x0; x < x1; x++) {
+          set_stream(seed, RTO_DOMAIN_PIXEL, (uint64_t)i * (w * h) + (uint64_t)y * w + (uint64_t)x);
+          Vec3f noise = r.m_rayTracer.jitterSample(i, r.m_numRays);
+          float shiftX = noise[0];
+          float shiftY = noise[1];
+          Ray ray = camera.rayAt((x + shiftX) / (float)w, 1.f - (y + shiftY) / (float)h);
+          bool posIntersectionFound = true;
+          Vec3f color(0.f, 0.f, 0.f);
+          switch (r.m_mode) {
+            case RAYTRACE:
+              if (not photonTree.empty())
+                color = r.calculateColorRay(ray, posIntersectionFound, photonTree);
+              else
+                color = r.calculateColorRay(ray, posIntersectionFound);
+              break;
+            case PATHTRACE:
+              if (not photonTree.empty())
+                color = r.calculateColorPath(ray, posIntersectionFound, 0, 3, photonTree);
+              else
+                color = r.calculateColorPath(ray, posIntersectionFound, 0, 3);
+              break;
+            default:
+              break;
+          }
+          Vec3f colorResponse = r.normalizeColor(color);
+          size_t wi = (size_t)(y - y0) * ww + (x - x0);
+          if (posIntersectionFound) counter[wi]++;
+          for (int c = 0; c < 3; c++) sum_rgb[3 * wi + c] += colorResponse[c];
+          if (samples) {
+            size_t si = ((size_t)(i - s0) * wh * ww + wi);
+            for (int c = 0; c < 3; c++) samples[3 * si + c] = colorResponse[c];
+            if (found) found[si] = posIntersectionFound;
+          }
+        }
+      }
+    }
+  } catch (const std::exception& e) {
+    return 1;
+  }
+  return 0;
+}
+
+// Image::fillBackground (Image.cpp:12-21) into a w*h*3 row-major buffer.
+void ref_background(int w, int h, float* rgb) {
+  Image image(w, h);
+  image.fillBackground();
+  for (int y = 0; y < h; y++)
+    for (int x = 0; x < w; x++)
+      for (int c = 0; c < 3; c++) rgb[3 * ((size_t)y * w + x) + c] = image(x, y)[c];
+}
+
+// The composite of Renderer.cpp:262-265 after N samples: bg_inout holds the background on entry
+// (Image::fillBackground) and the final image on exit.
+void ref_composite(int w, int h, int N, const float* sum_rgb, const int32_t* counter, float* bg_inout) {
+  int i = N - 1;
+  for (int y = 0; y < h; y++)
+    for (int x = 0; x < w; x++) {
+      size_t p = (size_t)y * w + x;
+      Vec3f update(sum_rgb[3 * p], sum_rgb[3 * p + 1], sum_rgb[3 * p + 2]);
+      Vec3f image(bg_inout[3 * p], bg_inout[3 * p + 1], bg_inout[3 * p + 2]);
+      Vec3f save = (update / float(i + 1)) + image * (i + 1 - counter[p]) / float(i + 1);
+      for (int c = 0; c < 3; c++) bg_inout[3 * p + c] = save[c];
+    }
+}
+
+// Image::savePPM (Image.cpp:23-43).
+void ref_save_ppm(int w, int h, const float* rgb, const char* path) {
+  Image image(w, h);
+  for (int y = 0; y < h; y++)
+    for (int x = 0; x < w; x++)
+      image(x, y) = Vec3f(rgb[3 * ((size_t)y * w + x)], rgb[3 * ((size_t)y * w + x) + 1],
+                          rgb[3 * ((size_t)y * w + x) + 2]);
+  image.savePPM(path);
+}
+
+uint64_t ref_words_drawn(void) { return g_words_drawn; }
+
+}  // extern "C"
