@@ -1,0 +1,242 @@
+"""gen_golden.py -- regenerate tests/golden/ from the UNMODIFIED reference (oracle/_ref/libref_cb.so).
+
+TEST INFRASTRUCTURE.  Run in the build container (needs /root/reference):
+
+    python oracle/gen_golden.py [--only scenes,rng,...] [--heavy]
+
+Every file written here is an OUTPUT OF THE REFERENCE'S OWN CODE (scene assembly, loadOFF, rayTrace,
+evaluateColorResponse, the samplers, PhotonMap, kdtree::knearest, calculateColor*), driven through
+oracle/ref_harness.cpp with the shared counter-based RNG engine.  The GPU box has no /root/reference,
+so the parity tests there compare against these vectors (and against the CPU restatement, which the
+CPU-side tests pin against the same library bit for bit).
+"""
+from __future__ import annotations
+
+import argparse
+import hashlib
+import os
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path[0] = ROOT  # (the script dir would shadow the oracle package with oracle.py)
+from oracle import oracle as O  # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+MESHES = "/root/reference/meshes"
+SEED = 1
+
+
+def log(*a):
+    print("[gen_golden]", *a, flush=True)
+
+
+def save(name, **arrays):
+    path = os.path.join(GOLD, name)
+    os.makedirs(os.path.dirname(path), exist_ok=True)
+    np.savez_compressed(path, **arrays)
+    log("wrote", name, f"{os.path.getsize(path) / 1024:.0f} KiB")
+
+
+def scenes():
+    ref = O.RefOracle()
+    os.makedirs(os.path.join(GOLD, "scenes"), exist_ok=True)
+    for name, off in (("stock", None), ("lowres", f"{MESHES}/example_low_res.off"), ("example", f"{MESHES}/example.off")):
+        flat = ref.create_scene(420, 420, custom_off=off)
+        flat.save(os.path.join(GOLD, "scenes", f"{name}.rtscene"))
+        log("scene", name, "V,T,M,L =", flat.V, flat.T, flat.M, flat.L)
+    # non-square camera (the CLI default 380x270) for the host-side camera test
+    flat = ref.create_scene(380, 270)
+    save("camera_380x270.npz", cam=flat.cam)
+    # the reference's OFF loader on our own tiny fixture (quads + comment + polygon fan)
+    pos, nrm, tri = ref.load_off(os.path.join(GOLD, "fixture_mixed.off"))
+    save("fixture_mixed_loaded.npz", pos=pos, nrm=nrm, tri=tri)
+
+
+def rng():
+    ref = O.RefOracle()
+    out = {}
+    for i, idx in enumerate((0, 5, 123456789012)):
+        out[f"words_{i}"] = ref.rng_words(SEED, O.DOMAIN_PIXEL, idx, 64)
+        out[f"uf_{i}"] = ref.rng_uniform_float(SEED, O.DOMAIN_PIXEL, idx, 256, -0.01, 0.01)
+        out[f"ud_{i}"] = ref.rng_uniform_double(SEED, O.DOMAIN_PHOTON, idx, 256, 0.0, 1.0000000278275352)
+        out[f"idx_{i}"] = np.array([idx], np.uint64)
+    save("rng.npz", **out)
+
+
+def sampling():
+    ref = O.RefOracle()
+    ref.create_scene(420, 420)
+    g = np.random.default_rng(11)
+    normals = g.normal(size=(4096, 3)).astype(np.float32)
+    out = dict(normals=normals,
+               hsphere=ref.hsphere(SEED, O.DOMAIN_PHOTON, 1000, normals),
+               jitter_0_1=ref.jitter(SEED, O.DOMAIN_PIXEL, 0, 4096, 0, 1),
+               jitter_77_128=ref.jitter(SEED, O.DOMAIN_PIXEL, 0, 4096, 77, 128),
+               jitter_1000_1024=ref.jitter(SEED, O.DOMAIN_PIXEL, 0, 4096, 1000, 1024))
+    for l in range(3):
+        out[f"light_{l}"] = ref.light_sample(l, SEED, O.DOMAIN_PIXEL, 0, 4096)
+    pts = g.uniform(-2, 2, (2048, 3)).astype(np.float32)
+    out["pts"] = pts
+    for l in range(3):
+        out[f"light_eval_{l}"] = ref.light_eval(l, pts)
+    xy = np.stack(np.meshgrid(np.arange(0, 420, 7), np.arange(0, 420, 7)), -1).reshape(-1, 2).astype(np.int32)
+    shift = g.uniform(0, 1, (len(xy), 2)).astype(np.float32)
+    out["cam_xy"], out["cam_shift"], out["cam_rays"] = xy, shift, ref.camera_rays(xy, shift)
+    save("sampling.npz", **out)
+
+
+def bsdf():
+    ref = O.RefOracle()
+    flat = ref.create_scene(420, 420)
+    g = np.random.default_rng(12)
+    v = g.normal(size=(8192, 9)).astype(np.float32)
+    # the two hand-checked cases of SURVEY.md 8a-B
+    v[0] = [0, 1, 0, .3, 1, .2, -.2, 1, .1]
+    out = dict(inputs=v, mats=flat.mats)
+    for m in range(flat.M):
+        out[f"bsdf_{m}"] = ref.bsdf(flat.mats[m], v)
+    save("bsdf.npz", **out)
+
+
+def make_rays(ref, flat, n_random, seed):
+    """Primary rays on a grid, random rays, and shadow/bounce-like rays leaving hit points."""
+    g = np.random.default_rng(seed)
+    xy = np.stack(np.meshgrid(np.arange(0, 420, 5), np.arange(0, 420, 5)), -1).reshape(-1, 2).astype(np.int32)
+    prim = ref.camera_rays(xy, g.uniform(0, 1, (len(xy), 2)).astype(np.float32))
+    rnd = np.concatenate([g.uniform(-1.5, 1.5, (n_random, 3)), g.normal(size=(n_random, 3))], 1).astype(np.float32)
+    h = ref.trace(prim)
+    hitp = prim[:, :3] + prim[:, 3:] * h["uvd"][:, 2:3]
+    ok = h["hit"] == 1
+    # secondary rays start (almost) ON a surface, like the reference's shadow and bounce rays
+    lights = flat.lights[:, :3]
+    sec = []
+    for l in range(len(lights)):
+        sec.append(np.concatenate([hitp[ok], lights[l][None] - hitp[ok]], 1))
+    sec.append(np.concatenate([hitp[ok], g.normal(size=(ok.sum(), 3))], 1))
+    return np.concatenate([prim, rnd] + sec).astype(np.float32)
+
+
+def trace():
+    ref = O.RefOracle()
+    for name, off, nrand in (("stock", None, 20000), ("lowres", f"{MESHES}/example_low_res.off", 6000),
+                             ("example", f"{MESHES}/example.off", 3000)):
+        flat = ref.create_scene(420, 420, custom_off=off)
+        rays = make_rays(ref, flat, nrand, 21)
+        if name == "example":
+            rays = rays[::3]
+        t = time.time()
+        h = ref.trace(rays)
+        log("trace", name, len(rays), "rays", f"{time.time() - t:.1f}s", "hit rate", h["hit"].mean())
+        save(f"trace_{name}.npz", rays=rays, hit=h["hit"].astype(np.int8), mesh=h["mesh"].astype(np.int8),
+             tri3=h["tri3"], uvd=h["uvd"])
+
+
+def to8(img):
+    """Image::savePPM quantisation (Image.cpp:31-38): unsigned(255.f * v)."""
+    return (np.float32(255.0) * img.astype(np.float32)).astype(np.uint32).astype(np.uint8)
+
+
+def render_case(ref, name, N, mode, window=None, photons=0, k=0, keep_float=True, want_samples=False):
+    pm = ref.photon_map_create(photons, SEED) if photons else None
+    t = time.time()
+    r = ref.render(N, mode, SEED, num_photons=photons, k=k, photon_map=pm, window=window, want_samples=want_samples)
+    w, h = ref.flat.w, ref.flat.h
+    out = dict(N=np.array([N]), mode=np.array([mode]), photons=np.array([photons]), k=np.array([k]),
+               window=np.array(window if window else (0, 0, w, h)), counter=r["counter"].astype(np.int16))
+    if keep_float:
+        out["sum_rgb"] = r["sum_rgb"]
+    if window is None:
+        img = ref.composite(N, r["sum_rgb"], r["counter"], ref.background(w, h))
+        out["image8"] = to8(img)
+    if want_samples:
+        out["samples"] = r["samples"]
+        out["found"] = r["found"]
+    if pm is not None:
+        plist, hist = pm.get()
+        out["photon_count"] = np.array([len(plist)])
+        out["depth_hist"] = hist
+    log("render", name, f"{time.time() - t:.1f}s")
+    save(f"render_{name}.npz", **out)
+
+
+def render_light():
+    ref = O.RefOracle()
+    ref.create_scene(420, 420)
+    render_case(ref, "stock_m0_N1", 1, 0)
+    render_case(ref, "stock_m1_N4_win", 4, 1, window=(100, 150, 228, 214), want_samples=True)
+    render_case(ref, "stock_m0_p3000_k10_win", 1, 0, window=(100, 150, 228, 214), photons=3000, k=10,
+                want_samples=True)
+    render_case(ref, "stock_m1_p3000_k5_N2_win", 2, 1, window=(100, 150, 228, 214), photons=3000, k=5,
+                want_samples=True)
+    ref.create_scene(420, 420, custom_off=f"{MESHES}/example_low_res.off")
+    render_case(ref, "lowres_m0_N1_win", 1, 0, window=(120, 100, 248, 228), want_samples=True)
+    render_case(ref, "lowres_m1_N2_win", 2, 1, window=(150, 130, 214, 194), want_samples=True)
+
+
+def render_heavy():
+    """Minutes of reference CPU time each."""
+    ref = O.RefOracle()
+    ref.create_scene(420, 420)
+    render_case(ref, "stock_m1_N128", 128, 1, keep_float=True)
+    render_case(ref, "stock_m0_p50000_k10_N1", 1, 0, photons=50000, k=10, keep_float=False)
+    ref.create_scene(420, 420, custom_off=f"{MESHES}/example.off")
+    render_case(ref, "example_m1_N2_win", 2, 1, window=(170, 150, 234, 214), want_samples=True)
+    render_case(ref, "example_m0_N1", 1, 0, keep_float=False)
+
+
+def photons():
+    ref = O.RefOracle()
+    ref.create_scene(420, 420)
+    pm = ref.photon_map_create(3000, SEED)
+    plist, hist = pm.get()
+    nodes, left, right, root = pm.layout()
+    g = np.random.default_rng(31)
+    q = np.concatenate([g.uniform(-1.5, 1.5, (1500, 3)), plist[g.integers(0, len(plist), 500), :3] +
+                        g.normal(scale=1e-3, size=(500, 3))]).astype(np.float32)
+    q[-1] = plist[7, :3]  # an exact hit: m_bestdist == 0 path (kdtree.h:101)
+    out = dict(list=plist, hist=hist, nodes=nodes, left=left, right=right, root=np.array([root]), queries=q)
+    for k in (1, 5, 10, 50):
+        res, visited = pm.knn(q, k)
+        out[f"knn_{k}"] = res[:, :, :3]  # positions identify the photons
+        out[f"visited_{k}"] = visited.astype(np.int32)
+    # depth histogram of the two BASELINE photon counts (statistical golden for emission)
+    for n in (50000,):
+        pm2 = ref.photon_map_create(n, SEED)
+        l2, h2 = pm2.get()
+        out[f"hist_{n}"] = h2
+        out[f"count_{n}"] = np.array([len(l2)])
+    save("photons.npz", **out)
+
+
+def stock_binary():
+    """md5 of the unmodified reference program's own output (stock RNG) -- guards oracle drift."""
+    build = os.path.join(HERE, "_ref", "build")
+    os.makedirs(build, exist_ok=True)
+    subprocess.run([O.REF_BIN, "-width", "420", "-height", "420", "-m", "0", "-N", "1"], cwd=build, check=True,
+                   stdout=subprocess.DEVNULL)
+    md5 = hashlib.md5(open(os.path.join(build, "output.ppm"), "rb").read()).hexdigest()
+    log("stock binary -m 0 -N 1 420x420 md5", md5)
+    with open(os.path.join(GOLD, "stock_binary_md5.txt"), "w") as f:
+        f.write(f"{md5}  RayTracer -width 420 -height 420 -m 0 -N 1 (unmodified reference, g++ 13.3 -O3 "
+                f"-ffp-contract=off, stock minstd_rand0 engine)\n")
+
+
+ALL = dict(scenes=scenes, rng=rng, sampling=sampling, bsdf=bsdf, trace=trace, photons=photons,
+           render_light=render_light, stock_binary=stock_binary)
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--only", default="")
+    ap.add_argument("--heavy", action="store_true")
+    a = ap.parse_args()
+    O.build(ref=True)
+    names = [n for n in a.only.split(",") if n] or list(ALL)
+    for n in names:
+        (ALL | dict(render_heavy=render_heavy))[n]()
+    if a.heavy and "render_heavy" not in names:
+        render_heavy()

@@ -1,0 +1,867 @@
+// capi.cu -- the C ABI declared in include/rt_b200.h: context, device memory, wavefront scheduling.
+//
+// No CPU fallback lives here: every entry point needs a CUDA device and fails with RT_ERR_NO_DEVICE /
+// RT_ERR_CUDA otherwise.  Nothing under oracle/ is linked or called.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/rt_b200.h"
+#include "host_build.h"
+#include "kernels.h"
+
+using namespace rtb;
+
+namespace {
+thread_local std::string g_err;
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+#define CU(call)                                                                                      \
+  do {                                                                                                \
+    cudaError_t e_ = (call);                                                                          \
+    if (e_ != cudaSuccess)                                                                            \
+      return fail(e_ == cudaErrorMemoryAllocation ? RT_ERR_OOM : RT_ERR_CUDA,                         \
+                  std::string(#call) + ": " + cudaGetErrorString(e_));                                \
+  } while (0)
+
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  cudaError_t ensure(size_t count) {
+    if (count <= n) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+    cudaError_t e = cudaMalloc((void**)&p, std::max<size_t>(count, 1) * sizeof(T));
+    if (e == cudaSuccess) n = count;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+};
+
+inline float3 h3(const float* a) { return make_float3(a[0], a[1], a[2]); }
+}  // namespace
+
+struct rt_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  rt_params params{};
+  int V = 0, T = 0, M = 0, L = 0;
+  int num_sms = 148;
+  // scene
+  DevBuf<float4> d_nodes, d_tris, d_pos, d_nrm;
+  DevBuf<int4> d_tri_vidx;
+  DevBuf<DMaterial> d_mats;
+  DScene scene{};
+  Bvh bvh;
+  // photon map
+  std::vector<float> kd_nodes7;
+  DevBuf<float4> d_kd_pos, d_kd_dir;
+  int kd_height = 0;
+  bool photon_map_built = false;
+  uint64_t photon_map_seed = 0;
+  int photon_map_requested = -1;
+  // wavefront work buffers
+  DevBuf<int> d_pix_map;
+  int npix = 0;
+  int pix_w = -1, pix_h = -1, pix_rank = -1, pix_count = -1, pix_tile = -1;
+  DevBuf<float4> d_col0, d_col1, d_qo0, d_qo1, d_qd0, d_qd1, d_acc;
+  DevBuf<int> d_acc_cnt, d_out_cnt;
+  DevBuf<float> d_out_rgb;
+  DevBuf<unsigned int> d_qcount;
+  DevBuf<unsigned long long> d_counters;
+  DevBuf<unsigned char> d_scratch;
+  std::vector<cudaEvent_t> seg_events;  // pairs around every k_segment launch of the current render
+  size_t seg_events_used = 0;
+  rt_stats stats{};
+};
+
+namespace {
+
+int bind(rt_ctx* c) {
+  if (!c) return fail(RT_ERR_INVALID, "null context");
+  CU(cudaSetDevice(c->device));
+  return RT_OK;
+}
+
+// Pixels owned by this shard, tile by tile, 8x4 micro-tiles inside a tile so that the 32 lanes of a
+// warp cover a compact block of the image (coherent primary rays).
+void build_pix_map(const rt_params& p, std::vector<int>& map) {
+  map.clear();
+  const int W = p.width, H = p.height;
+  const int tile = p.shard_tile > 0 ? p.shard_tile : 16;
+  const int count = p.shard_count > 1 ? p.shard_count : 1;
+  const int rank = count > 1 ? p.shard_rank : 0;
+  const int tx_n = (W + tile - 1) / tile, ty_n = (H + tile - 1) / tile;
+  for (int ty = 0; ty < ty_n; ty++)
+    for (int tx = 0; tx < tx_n; tx++) {
+      if ((ty * tx_n + tx) % count != rank) continue;
+      for (int my = 0; my < tile; my += 4)
+        for (int mx = 0; mx < tile; mx += 8)
+          for (int dy = 0; dy < 4; dy++)
+            for (int dx = 0; dx < 8; dx++) {
+              int x = tx * tile + mx + dx, y = ty * tile + my + dy;
+              if (mx + dx < tile && my + dy < tile && x < W && y < H) map.push_back(y * W + x);
+            }
+    }
+}
+
+int ensure_pix_map(rt_ctx* c) {
+  const rt_params& p = c->params;
+  int count = p.shard_count > 1 ? p.shard_count : 1, rank = count > 1 ? p.shard_rank : 0;
+  int tile = p.shard_tile > 0 ? p.shard_tile : 16;
+  if (c->pix_w == p.width && c->pix_h == p.height && c->pix_rank == rank && c->pix_count == count &&
+      c->pix_tile == tile)
+    return RT_OK;
+  std::vector<int> map;
+  build_pix_map(p, map);
+  CU(c->d_pix_map.ensure(map.size()));
+  if (!map.empty()) CU(cudaMemcpy(c->d_pix_map.p, map.data(), map.size() * sizeof(int), cudaMemcpyHostToDevice));
+  c->npix = (int)map.size();
+  c->pix_w = p.width;
+  c->pix_h = p.height;
+  c->pix_rank = rank;
+  c->pix_count = count;
+  c->pix_tile = tile;
+  return RT_OK;
+}
+
+int ensure_work(rt_ctx* c, size_t paths, bool path_mode) {
+  CU(c->d_col0.ensure(paths));
+  if (path_mode) {
+    CU(c->d_col1.ensure(paths));
+    CU(c->d_qo0.ensure(paths));
+    CU(c->d_qd0.ensure(paths));
+    CU(c->d_qo1.ensure(paths));
+    CU(c->d_qd1.ensure(paths));
+  }
+  CU(c->d_qcount.ensure(4));
+  CU(c->d_counters.ensure(kCntNum));
+  return RT_OK;
+}
+
+int validate_params(const rt_params* p) {
+  if (!p) return fail(RT_ERR_INVALID, "null params");
+  if (p->width < 1 || p->height < 1) return fail(RT_ERR_INVALID, "width/height must be >= 1");
+  if (p->num_rays < 0) return fail(RT_ERR_INVALID, "num_rays must be >= 0");
+  if (p->num_photons < 0) return fail(RT_ERR_INVALID, "num_photons must be >= 0");
+  if (p->num_photons > 0 && (p->k < 1 || p->k > RT_MAX_K))
+    return fail(RT_ERR_INVALID, "k must be in [1, " + std::to_string(RT_MAX_K) + "] when a photon map is used");
+  if (p->shard_count > 1 && (p->shard_rank < 0 || p->shard_rank >= p->shard_count))
+    return fail(RT_ERR_INVALID, "shard_rank out of range");
+  if ((int64_t)p->width * p->height > (int64_t)1 << 30) return fail(RT_ERR_INVALID, "image too large");
+  if (p->sample_first < 0 || (p->sample_count > 0 && p->sample_first + p->sample_count > p->num_rays))
+    return fail(RT_ERR_INVALID, "sample range outside [0, num_rays)");
+  return RT_OK;
+}
+
+void fill_args(rt_ctx* c, RenderArgs& a, const int* pix_map, int npix, bool use_photons) {
+  const rt_params& p = c->params;
+  a.scene = c->scene;
+  a.width = p.width;
+  a.height = p.height;
+  a.num_rays = p.num_rays;
+  a.jitter_d = (int)sqrtf((float)p.num_rays);  // RayTracer.h:111
+  if (a.jitter_d < 1) a.jitter_d = 1;
+  a.mode = p.mode == 1 ? 1 : 0;                // CommandLine.h:84-87: anything else is ray tracing
+  a.photon = use_photons ? 1 : 0;
+  a.k = p.k;
+  a.num_photons = p.num_photons;
+  a.brute = (p.flags & RT_FLAG_BRUTE_FORCE) ? 1 : 0;
+  a.seed_mixed = mix64(p.seed + kGolden);
+  a.pix_map = pix_map;
+  a.npix = npix;
+  a.col0 = c->d_col0.p;
+  a.col1 = c->d_col1.p;
+  a.q_o[0] = c->d_qo0.p;
+  a.q_o[1] = c->d_qo1.p;
+  a.q_d[0] = c->d_qd0.p;
+  a.q_d[1] = c->d_qd1.p;
+  a.q_count = c->d_qcount.p;
+  a.counters = c->d_counters.p;
+}
+
+// one wavefront batch: samples [s0, s0+nsamp) of the pixels in pix_map
+int run_batch(rt_ctx* c, RenderArgs& a, int s0, int nsamp) {
+  a.s0 = s0;
+  a.nsamp = nsamp;
+  const int ctas = c->num_sms * segment_ctas_per_sm(a.mode, a.photon);
+  const long long paths = (long long)a.npix * nsamp;
+  int grid0 = (int)std::min<long long>((paths + kBlock - 1) / kBlock, (long long)ctas);
+  if (grid0 < 1) grid0 = 1;
+  CU(cudaMemsetAsync(c->d_qcount.p, 0, 4 * sizeof(unsigned), c->stream));
+  const int nseg = a.mode == 1 ? 3 : 1;
+  for (int seg = 0; seg < nseg; seg++) {
+    while (c->seg_events.size() < c->seg_events_used + 2) {
+      cudaEvent_t e;
+      CU(cudaEventCreate(&e));
+      c->seg_events.push_back(e);
+    }
+    CU(cudaEventRecord(c->seg_events[c->seg_events_used++], c->stream));
+    launch_segment(a, seg, grid0, c->stream);
+    CU(cudaEventRecord(c->seg_events[c->seg_events_used++], c->stream));
+    c->stats.kernel_launches++;
+  }
+  CU(cudaGetLastError());
+  return RT_OK;
+}
+
+int pull_counters(rt_ctx* c) {
+  unsigned long long h[kCntNum];
+  CU(cudaMemcpy(h, c->d_counters.p, sizeof(h), cudaMemcpyDeviceToHost));
+  rt_stats& s = c->stats;
+  s.shadow_rays = h[kCntShadow];
+  s.photon_rays = h[kCntPhotonRays];
+  s.knn_queries = h[kCntKnn];
+  uint64_t nearest = h[kCntNearest];
+  s.bounce_rays = nearest >= s.samples ? nearest - s.samples : 0;
+  s.primary_rays = nearest - s.bounce_rays;
+  s.rays = nearest + s.shadow_rays + s.photon_rays;
+  return RT_OK;
+}
+
+int photons_per_light(const rt_ctx* c, float* light_pdf_out) {
+  // PhotonMap.h:19-20: float lightPdf = 1.f / size; int photonsPerLS = (int)(numOfPhotons * lightPdf)
+  if (c->L < 1) return 0;
+  float light_pdf = 1.f / (float)c->L;
+  if (light_pdf_out) *light_pdf_out = light_pdf;
+  return (int)((float)c->params.num_photons * light_pdf);
+}
+
+bool use_photon_map(const rt_ctx* c) { return c->params.num_photons > 0 && c->scene.kd_count > 0; }
+
+int prepare_photons(rt_ctx* c) {
+  const rt_params& p = c->params;
+  if (p.num_photons <= 0) return RT_OK;
+  if (!c->photon_map_built || c->photon_map_seed != p.seed || c->photon_map_requested != p.num_photons) {
+    int rc = rt_build_photon_map(c);
+    if (rc != RT_OK) return rc;
+  }
+  // Renderer.cpp:239,245: an empty tree silently selects the direct-lighting overloads
+  if (c->scene.kd_count > 0 && p.k > c->scene.kd_count)
+    return fail(RT_ERR_K_TOO_LARGE, "k is greater than the number of nodes");  // kdtree.h:182-183
+  return RT_OK;
+}
+
+// the whole render: batches of samples -> ordered accumulation -> scatter into full-frame buffers
+int render_to_device(rt_ctx* c, float* out_rgb_dev, int* out_cnt_dev) {
+  int rc = bind(c);
+  if (rc) return rc;
+  if ((rc = prepare_photons(c))) return rc;
+  if ((rc = ensure_pix_map(c))) return rc;
+  const rt_params& p = c->params;
+  const size_t npx = (size_t)p.width * p.height;
+  const bool path_mode = p.mode == 1;
+  // batch size: bounded by free HBM (96 B per path in path mode) and by 2^31 paths
+  int spb = p.samples_per_batch;
+  if (spb <= 0) {
+    size_t free_b = 0, total_b = 0;
+    CU(cudaMemGetInfo(&free_b, &total_b));
+    size_t budget = std::min<size_t>(free_b / 2, (size_t)24 << 30);
+    size_t max_paths = std::min<size_t>(budget / 96, (size_t)1 << 30);
+    spb = (int)std::max<size_t>(1, std::min<size_t>(max_paths / std::max(c->npix, 1), 1 << 20));
+  }
+  const int samp_first = p.sample_first;
+  const int samp_end = p.sample_count > 0 ? p.sample_first + p.sample_count : p.num_rays;
+  spb = std::max(1, std::min(spb, std::max(samp_end - samp_first, 1)));
+  if ((rc = ensure_work(c, (size_t)c->npix * spb, path_mode))) return rc;
+  CU(c->d_acc.ensure(c->npix));
+  CU(c->d_acc_cnt.ensure(c->npix));
+  CU(cudaMemsetAsync(c->d_acc.p, 0, sizeof(float4) * (size_t)c->npix, c->stream));
+  CU(cudaMemsetAsync(c->d_acc_cnt.p, 0, sizeof(int) * (size_t)c->npix, c->stream));
+  RenderArgs a;
+  fill_args(c, a, c->d_pix_map.p, c->npix, use_photon_map(c));
+  c->seg_events_used = 0;
+  CU(cudaEventRecord(c->ev0, c->stream));
+  if (c->npix > 0) {
+    for (int s0 = samp_first; s0 < samp_end; s0 += spb) {
+      int ns = std::min(spb, samp_end - s0);
+      if ((rc = run_batch(c, a, s0, ns))) return rc;
+      launch_resolve(c->d_col0.p, c->npix, ns, c->d_acc.p, c->d_acc_cnt.p, c->stream);
+      c->stats.kernel_launches++;
+    }
+  }
+  CU(cudaMemsetAsync(out_rgb_dev, 0, sizeof(float) * 3 * npx, c->stream));
+  CU(cudaMemsetAsync(out_cnt_dev, 0, sizeof(int) * npx, c->stream));
+  if (c->npix > 0) {
+    launch_scatter(c->d_acc.p, c->d_acc_cnt.p, c->d_pix_map.p, c->npix, out_rgb_dev, out_cnt_dev, c->stream);
+    c->stats.kernel_launches++;
+  }
+  CU(cudaEventRecord(c->ev1, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  CU(cudaGetLastError());
+  float ms = 0.f;
+  CU(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+  c->stats.device_ms = ms;
+  double seg_ms = 0.0;
+  for (size_t i = 0; i + 1 < c->seg_events_used; i += 2) {
+    float t = 0.f;
+    CU(cudaEventElapsedTime(&t, c->seg_events[i], c->seg_events[i + 1]));
+    seg_ms += t;
+  }
+  c->stats.trace_ms = seg_ms;
+  c->stats.samples += (uint64_t)c->npix * (uint64_t)std::max(samp_end - samp_first, 0);
+  return pull_counters(c);
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* rt_last_error(void) { return g_err.c_str(); }
+
+int rt_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+int rt_destroy(rt_ctx* c) {
+  if (!c) return RT_OK;
+  cudaSetDevice(c->device);
+  c->d_nodes.release();
+  c->d_tris.release();
+  c->d_pos.release();
+  c->d_nrm.release();
+  c->d_tri_vidx.release();
+  c->d_mats.release();
+  c->d_kd_pos.release();
+  c->d_kd_dir.release();
+  c->d_pix_map.release();
+  c->d_col0.release();
+  c->d_col1.release();
+  c->d_qo0.release();
+  c->d_qo1.release();
+  c->d_qd0.release();
+  c->d_qd1.release();
+  c->d_acc.release();
+  c->d_acc_cnt.release();
+  c->d_out_cnt.release();
+  c->d_out_rgb.release();
+  c->d_qcount.release();
+  c->d_counters.release();
+  c->d_scratch.release();
+  for (cudaEvent_t e : c->seg_events) cudaEventDestroy(e);
+  if (c->ev0) cudaEventDestroy(c->ev0);
+  if (c->ev1) cudaEventDestroy(c->ev1);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+  return RT_OK;
+}
+
+int rt_set_params(rt_ctx* c, const rt_params* p) {
+  if (!c) return fail(RT_ERR_INVALID, "null context");
+  int rc = validate_params(p);
+  if (rc) return rc;
+  c->params = *p;
+  return RT_OK;
+}
+
+int rt_create(const rt_scene* s, const rt_params* p, int device, rt_ctx** out) {
+  if (!s || !out) return fail(RT_ERR_INVALID, "null scene/out");
+  *out = nullptr;
+  int rc = validate_params(p);
+  if (rc) return rc;
+  if (s->num_vertices < 0 || s->num_triangles < 0 || s->num_meshes < 0 || s->num_lights < 0)
+    return fail(RT_ERR_INVALID, "negative scene counts");
+  if (s->num_lights > kMaxLights) return fail(RT_ERR_INVALID, "too many lights (max 8)");
+  if (s->num_triangles > 0 && (!s->positions || !s->normals || !s->triangles || !s->mesh_first_triangle ||
+                               !s->mesh_first_vertex || !s->materials))
+    return fail(RT_ERR_INVALID, "null scene arrays");
+  if (s->num_lights > 0 && !s->lights) return fail(RT_ERR_INVALID, "null lights");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) {
+    cudaGetLastError();
+    return fail(RT_ERR_NO_DEVICE, "no CUDA device available (this library has no CPU fallback)");
+  }
+  if (device < 0 || device >= ndev) return fail(RT_ERR_INVALID, "device ordinal out of range");
+  for (int t = 0; t < 3 * s->num_triangles; t++)
+    if (s->triangles[t] < 0 || s->triangles[t] >= s->num_vertices)
+      return fail(RT_ERR_INVALID, "triangle vertex index out of range");
+
+  rt_ctx* c = new rt_ctx();
+  c->device = device;
+  c->params = *p;
+  c->V = s->num_vertices;
+  c->T = s->num_triangles;
+  c->M = s->num_meshes;
+  c->L = s->num_lights;
+#define CUC(call)                                                                   \
+  do {                                                                              \
+    cudaError_t e_ = (call);                                                        \
+    if (e_ != cudaSuccess) {                                                        \
+      std::string m_ = std::string(#call) + ": " + cudaGetErrorString(e_);          \
+      rt_destroy(c);                                                                \
+      return fail(e_ == cudaErrorMemoryAllocation ? RT_ERR_OOM : RT_ERR_CUDA, m_);  \
+    }                                                                               \
+  } while (0)
+  CUC(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CUC(cudaGetDeviceProperties(&prop, device));
+  c->num_sms = prop.multiProcessorCount;
+  CUC(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  CUC(cudaEventCreate(&c->ev0));
+  CUC(cudaEventCreate(&c->ev1));
+
+  // ---- BVH (host, reference split policy) ----
+  float extent = 0.f;
+  for (int i = 0; i < 3 * c->V; i++) extent = std::max(extent, std::fabs(s->positions[i]));
+  for (int l = 0; l < c->L; l++)
+    for (int a = 0; a < 3; a++) extent = std::max(extent, std::fabs(s->lights[l].position[a]) + s->lights[l].side);
+  for (int a = 0; a < 3; a++) extent = std::max(extent, std::fabs(s->camera.position[a]));
+  float pad_fraction = p->bvh_pad > 0.f ? p->bvh_pad : 1.0f / 16384.0f;
+  build_bvh(c->V, s->positions, c->T, s->triangles, c->M, s->mesh_first_triangle, extent, pad_fraction, c->bvh);
+  if (c->bvh.depth > kStackDepth) {
+    rt_destroy(c);
+    return fail(RT_ERR_INVALID, "BVH deeper than the traversal stack");
+  }
+  c->stats.bvh_nodes = (int)(c->bvh.nodes.size() / 16);
+  c->stats.bvh_depth = c->bvh.depth;
+
+  // ---- upload ----
+  std::vector<float4> h_pos(std::max(c->V, 1)), h_nrm(std::max(c->V, 1)), h_tris(3 * (size_t)std::max(c->T, 1));
+  std::vector<int4> h_vidx(std::max(c->T, 1));
+  for (int v = 0; v < c->V; v++) {
+    h_pos[v] = make_float4(s->positions[3 * v], s->positions[3 * v + 1], s->positions[3 * v + 2], 0.f);
+    h_nrm[v] = make_float4(s->normals[3 * v], s->normals[3 * v + 1], s->normals[3 * v + 2], 0.f);
+  }
+  {
+    int m = 0;
+    for (int t = 0; t < c->T; t++) {
+      while (m + 1 < c->M && t >= s->mesh_first_triangle[m + 1]) m++;
+      h_vidx[t] = make_int4(s->triangles[3 * t], s->triangles[3 * t + 1], s->triangles[3 * t + 2], m);
+    }
+  }
+  for (int slot = 0; slot < c->T; slot++) {
+    int gid = c->bvh.slot_tri[slot];
+    const float* p0 = s->positions + 3 * (size_t)s->triangles[3 * gid];
+    const float* p1 = s->positions + 3 * (size_t)s->triangles[3 * gid + 1];
+    const float* p2 = s->positions + 3 * (size_t)s->triangles[3 * gid + 2];
+    // Ray.cpp:11: edge1 = p1 - p0, edge2 = p2 - p0 (binary32 subtractions, done once here)
+    volatile float e1x = p1[0] - p0[0], e1y = p1[1] - p0[1], e1z = p1[2] - p0[2];
+    volatile float e2x = p2[0] - p0[0], e2y = p2[1] - p0[1], e2z = p2[2] - p0[2];
+    int gid_bits = gid;
+    float gid_f;
+    std::memcpy(&gid_f, &gid_bits, 4);
+    h_tris[3 * (size_t)slot] = make_float4(p0[0], p0[1], p0[2], gid_f);
+    h_tris[3 * (size_t)slot + 1] = make_float4(e1x, e1y, e1z, 0.f);
+    h_tris[3 * (size_t)slot + 2] = make_float4(e2x, e2y, e2z, 0.f);
+  }
+  std::vector<DMaterial> h_mats(std::max(c->M, 1));
+  for (int m = 0; m < c->M; m++) {
+    const rt_material& a = s->materials[m];
+    h_mats[m] = DMaterial{a.kd, a.alpha, h3(a.albedo), h3(a.f0)};
+  }
+  CUC(c->d_nodes.ensure(c->bvh.nodes.size() / 4));
+  CUC(c->d_tris.ensure(h_tris.size()));
+  CUC(c->d_pos.ensure(h_pos.size()));
+  CUC(c->d_nrm.ensure(h_nrm.size()));
+  CUC(c->d_tri_vidx.ensure(h_vidx.size()));
+  CUC(c->d_mats.ensure(h_mats.size()));
+  CUC(cudaMemcpy(c->d_nodes.p, c->bvh.nodes.data(), c->bvh.nodes.size() * sizeof(float), cudaMemcpyHostToDevice));
+  CUC(cudaMemcpy(c->d_tris.p, h_tris.data(), h_tris.size() * sizeof(float4), cudaMemcpyHostToDevice));
+  CUC(cudaMemcpy(c->d_pos.p, h_pos.data(), h_pos.size() * sizeof(float4), cudaMemcpyHostToDevice));
+  CUC(cudaMemcpy(c->d_nrm.p, h_nrm.data(), h_nrm.size() * sizeof(float4), cudaMemcpyHostToDevice));
+  CUC(cudaMemcpy(c->d_tri_vidx.p, h_vidx.data(), h_vidx.size() * sizeof(int4), cudaMemcpyHostToDevice));
+  CUC(cudaMemcpy(c->d_mats.p, h_mats.data(), h_mats.size() * sizeof(DMaterial), cudaMemcpyHostToDevice));
+  CUC(c->d_counters.ensure(kCntNum));
+  CUC(cudaMemset(c->d_counters.p, 0, sizeof(unsigned long long) * kCntNum));
+  CUC(c->d_kd_pos.ensure(1));
+  CUC(c->d_kd_dir.ensure(1));
+
+  DScene& S = c->scene;
+  S.nodes = c->d_nodes.p;
+  S.tris = c->d_tris.p;
+  S.tri_vidx = c->d_tri_vidx.p;
+  S.pos = c->d_pos.p;
+  S.nrm = c->d_nrm.p;
+  S.mats = c->d_mats.p;
+  S.num_lights = c->L;
+  S.num_tris = c->T;
+  for (int l = 0; l < c->L; l++) {
+    const rt_light& a = s->lights[l];
+    S.lights[l] = DLight{h3(a.position), h3(a.color),  h3(a.normal), h3(a.vertical), h3(a.horizontal),
+                         a.intensity,    a.side,       a.ac,         a.al,           a.aq,
+                         a.factor};
+  }
+  S.cam = DCamera{h3(s->camera.position), h3(s->camera.lower_left), h3(s->camera.horizontal), h3(s->camera.vertical)};
+  S.kd_pos = c->d_kd_pos.p;
+  S.kd_dir = c->d_kd_dir.p;
+  S.kd_count = 0;
+#undef CUC
+  *out = c;
+  return RT_OK;
+}
+
+int rt_render_accumulate_device(rt_ctx* c, float* sum_rgb_device, int32_t* counter_device) {
+  if (!c || !sum_rgb_device || !counter_device) return fail(RT_ERR_INVALID, "null argument");
+  return render_to_device(c, sum_rgb_device, counter_device);
+}
+
+int rt_render_accumulate(rt_ctx* c, float* sum_rgb, int32_t* counter) {
+  if (!c || !sum_rgb || !counter) return fail(RT_ERR_INVALID, "null argument");
+  int rc = bind(c);
+  if (rc) return rc;
+  const size_t npx = (size_t)c->params.width * c->params.height;
+  CU(c->d_out_rgb.ensure(3 * npx));
+  CU(c->d_out_cnt.ensure(npx));
+  if ((rc = render_to_device(c, c->d_out_rgb.p, c->d_out_cnt.p))) return rc;
+  CU(cudaMemcpy(sum_rgb, c->d_out_rgb.p, sizeof(float) * 3 * npx, cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(counter, c->d_out_cnt.p, sizeof(int) * npx, cudaMemcpyDeviceToHost));
+  return RT_OK;
+}
+
+// Renderer.cpp:262-265 after the last sample (i + 1 == N):
+//   saveImage = updateImage / float(N) + image * (N - counter) / float(N)
+int rt_composite(int32_t width, int32_t height, int32_t num_rays, const float* sum_rgb, const int32_t* counter,
+                 float* rgb_inout) {
+  if (!sum_rgb || !counter || !rgb_inout || width < 1 || height < 1) return fail(RT_ERR_INVALID, "bad argument");
+  const float fn = (float)num_rays;
+  for (size_t px = 0; px < (size_t)width * height; px++) {
+    const float miss = (float)(num_rays - counter[px]);
+    for (int ch = 0; ch < 3; ch++) {
+      volatile float a = sum_rgb[3 * px + ch] / fn;
+      volatile float b = rgb_inout[3 * px + ch] * miss;
+      volatile float cc = b / fn;
+      rgb_inout[3 * px + ch] = a + cc;
+    }
+  }
+  return RT_OK;
+}
+
+int rt_render(rt_ctx* c, float* rgb_inout) {
+  if (!c || !rgb_inout) return fail(RT_ERR_INVALID, "null argument");
+  const rt_params& p = c->params;
+  const size_t npx = (size_t)p.width * p.height;
+  if (p.num_rays < 1) return RT_OK;  // Renderer.cpp:219: no pass, image = saveImage (we leave the input)
+  std::vector<float> sum(3 * npx);
+  std::vector<int32_t> cnt(npx);
+  int rc = rt_render_accumulate(c, sum.data(), cnt.data());
+  if (rc) return rc;
+  if (p.shard_count > 1) {
+    // composite only the pixels this shard owns
+    std::vector<int> map;
+    build_pix_map(p, map);
+    std::vector<float> full(rgb_inout, rgb_inout + 3 * npx);
+    rt_composite(p.width, p.height, p.num_rays, sum.data(), cnt.data(), full.data());
+    for (int px : map)
+      for (int ch = 0; ch < 3; ch++) rgb_inout[3 * (size_t)px + ch] = full[3 * (size_t)px + ch];
+    return RT_OK;
+  }
+  return rt_composite(p.width, p.height, p.num_rays, sum.data(), cnt.data(), rgb_inout);
+}
+
+int rt_render_samples(rt_ctx* c, int32_t x0, int32_t y0, int32_t x1, int32_t y1, int32_t s0, int32_t s1, float* rgb,
+                      uint8_t* found) {
+  if (!c || !rgb) return fail(RT_ERR_INVALID, "null argument");
+  int rc = bind(c);
+  if (rc) return rc;
+  const rt_params& p = c->params;
+  if (x0 < 0 || y0 < 0 || x1 > p.width || y1 > p.height || x0 >= x1 || y0 >= y1 || s0 < 0 || s0 >= s1)
+    return fail(RT_ERR_INVALID, "bad window / sample range");
+  if ((rc = prepare_photons(c))) return rc;
+  const int ww = x1 - x0, wh = y1 - y0, ns = s1 - s0;
+  std::vector<int> map((size_t)ww * wh);
+  for (int y = y0; y < y1; y++)
+    for (int x = x0; x < x1; x++) map[(size_t)(y - y0) * ww + (x - x0)] = y * p.width + x;
+  const size_t paths = map.size() * (size_t)ns;
+  if (paths > ((size_t)1 << 30)) return fail(RT_ERR_INVALID, "window too large");
+  DevBuf<int> d_map;
+  CU(d_map.ensure(map.size()));
+  CU(cudaMemcpy(d_map.p, map.data(), map.size() * sizeof(int), cudaMemcpyHostToDevice));
+  if ((rc = ensure_work(c, paths, p.mode == 1))) {
+    d_map.release();
+    return rc;
+  }
+  RenderArgs a;
+  fill_args(c, a, d_map.p, (int)map.size(), use_photon_map(c));
+  c->seg_events_used = 0;
+  rc = run_batch(c, a, s0, ns);
+  std::vector<float4> h(paths);
+  cudaError_t e = cudaStreamSynchronize(c->stream);
+  if (e == cudaSuccess) e = cudaMemcpy(h.data(), c->d_col0.p, paths * sizeof(float4), cudaMemcpyDeviceToHost);
+  d_map.release();
+  if (rc) return rc;
+  if (e != cudaSuccess) return fail(RT_ERR_CUDA, cudaGetErrorString(e));
+  c->stats.samples += paths;
+  for (size_t i = 0; i < paths; i++) {
+    rgb[3 * i] = h[i].x;
+    rgb[3 * i + 1] = h[i].y;
+    rgb[3 * i + 2] = h[i].z;
+    if (found) found[i] = h[i].w != 0.f;
+  }
+  return RT_OK;
+}
+
+static int trace_common(rt_ctx* c, const rt_ray* rays, int64_t n, rt_hit* hits, uint8_t* occluded, int32_t flags) {
+  int rc = bind(c);
+  if (rc) return rc;
+  if (n < 0 || (n > 0 && !rays)) return fail(RT_ERR_INVALID, "bad ray batch");
+  if (n == 0) return RT_OK;
+  DevBuf<float> d_rays, d_uvt;
+  DevBuf<int> d_tri;
+  DevBuf<unsigned char> d_occ;
+  int ret = RT_OK;
+  cudaError_t e = d_rays.ensure(6 * (size_t)n);
+  if (e == cudaSuccess) e = d_uvt.ensure(3 * (size_t)n);
+  if (e == cudaSuccess) e = d_tri.ensure((size_t)n);
+  if (e == cudaSuccess) e = d_occ.ensure((size_t)n);
+  if (e == cudaSuccess) e = cudaMemcpy(d_rays.p, rays, sizeof(rt_ray) * (size_t)n, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) {
+    launch_trace_rays(c->scene, d_rays.p, n, d_tri.p, d_uvt.p, (flags & RT_FLAG_BRUTE_FORCE) ? 1 : 0, occluded ? 1 : 0,
+                      d_occ.p, c->stream);
+    c->stats.kernel_launches++;
+    e = cudaStreamSynchronize(c->stream);
+  }
+  if (e == cudaSuccess) {
+    if (occluded) {
+      e = cudaMemcpy(occluded, d_occ.p, (size_t)n, cudaMemcpyDeviceToHost);
+    } else {
+      std::vector<int> tri((size_t)n);
+      std::vector<float> uvt(3 * (size_t)n);
+      e = cudaMemcpy(tri.data(), d_tri.p, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost);
+      if (e == cudaSuccess) e = cudaMemcpy(uvt.data(), d_uvt.p, sizeof(float) * 3 * (size_t)n, cudaMemcpyDeviceToHost);
+      for (int64_t i = 0; i < n && e == cudaSuccess; i++)
+        hits[i] = rt_hit{tri[i], uvt[3 * i], uvt[3 * i + 1], uvt[3 * i + 2]};
+    }
+  }
+  if (e != cudaSuccess) ret = fail(RT_ERR_CUDA, cudaGetErrorString(e));
+  d_rays.release();
+  d_uvt.release();
+  d_tri.release();
+  d_occ.release();
+  return ret;
+}
+
+int rt_trace_rays(rt_ctx* c, const rt_ray* rays, int64_t n, rt_hit* hits, int32_t flags) {
+  if (n > 0 && !hits) return fail(RT_ERR_INVALID, "null hits");
+  return trace_common(c, rays, n, hits, nullptr, flags);
+}
+int rt_occluded(rt_ctx* c, const rt_ray* rays, int64_t n, uint8_t* occluded, int32_t flags) {
+  if (n > 0 && !occluded) return fail(RT_ERR_INVALID, "null output");
+  return trace_common(c, rays, n, nullptr, occluded, flags);
+}
+
+int rt_eval_bsdf(rt_ctx* c, const rt_material* m, const float* n_wi_wo, int64_t n, float* rgb) {
+  int rc = bind(c);
+  if (rc) return rc;
+  if (!m || n < 0 || (n > 0 && (!n_wi_wo || !rgb))) return fail(RT_ERR_INVALID, "bad argument");
+  if (n == 0) return RT_OK;
+  DevBuf<float> d_in, d_out;
+  cudaError_t e = d_in.ensure(9 * (size_t)n);
+  if (e == cudaSuccess) e = d_out.ensure(3 * (size_t)n);
+  if (e == cudaSuccess) e = cudaMemcpy(d_in.p, n_wi_wo, sizeof(float) * 9 * (size_t)n, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) {
+    launch_bsdf(DMaterial{m->kd, m->alpha, h3(m->albedo), h3(m->f0)}, d_in.p, n, d_out.p, c->stream);
+    c->stats.kernel_launches++;
+    e = cudaStreamSynchronize(c->stream);
+  }
+  if (e == cudaSuccess) e = cudaMemcpy(rgb, d_out.p, sizeof(float) * 3 * (size_t)n, cudaMemcpyDeviceToHost);
+  d_in.release();
+  d_out.release();
+  if (e != cudaSuccess) return fail(RT_ERR_CUDA, cudaGetErrorString(e));
+  return RT_OK;
+}
+
+int rt_photons_per_light(const rt_ctx* c, int32_t* out) {
+  if (!c || !out) return fail(RT_ERR_INVALID, "null argument");
+  *out = photons_per_light(c, nullptr);
+  return RT_OK;
+}
+
+int rt_emit_photons(rt_ctx* c, int32_t first_path, int32_t num_paths, rt_photon* out, int64_t capacity,
+                    int64_t* per_light_counts, int32_t* depth_histogram20) {
+  int rc = bind(c);
+  if (rc) return rc;
+  float light_pdf = 0.f;
+  const int per_light = photons_per_light(c, &light_pdf);
+  if (first_path < 0) first_path = 0;
+  int last = num_paths < 0 ? per_light : std::min(per_light, first_path + num_paths);
+  int npaths = std::max(0, last - first_path);
+  if (per_light_counts)
+    for (int l = 0; l < c->L; l++) per_light_counts[l] = 0;
+  if (depth_histogram20)
+    for (int i = 0; i < 20; i++) depth_histogram20[i] = 0;
+  if (npaths == 0 || c->L == 0) return RT_OK;
+  const size_t total = (size_t)c->L * npaths;
+  DevBuf<float4> d_a, d_b;
+  cudaError_t e = d_a.ensure(total);
+  if (e == cudaSuccess) e = d_b.ensure(total);
+  std::vector<float4> ha(total), hb(total);
+  float ms = 0.f;
+  if (e == cudaSuccess) {
+    cudaEventRecord(c->ev0, c->stream);
+    launch_emit(c->scene, mix64(c->params.seed + kGolden), per_light, light_pdf, first_path, npaths,
+                (c->params.flags & RT_FLAG_BRUTE_FORCE) ? 1 : 0, d_a.p, d_b.p, c->d_counters.p, c->stream);
+    cudaEventRecord(c->ev1, c->stream);
+    c->stats.kernel_launches++;
+    e = cudaStreamSynchronize(c->stream);
+    if (e == cudaSuccess) cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+  }
+  if (e == cudaSuccess) e = cudaMemcpy(ha.data(), d_a.p, total * sizeof(float4), cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess) e = cudaMemcpy(hb.data(), d_b.p, total * sizeof(float4), cudaMemcpyDeviceToHost);
+  d_a.release();
+  d_b.release();
+  if (e != cudaSuccess) return fail(RT_ERR_CUDA, cudaGetErrorString(e));
+  c->stats.photon_ms = ms;
+  // stable compaction in (light, path) order == the order PhotonMap.h:94-96,109-111 appends in
+  int64_t count = 0;
+  for (size_t q = 0; q < total; q++) {
+    int status;
+    std::memcpy(&status, &hb[q].w, 4);
+    int hist = status >> 8;
+    if (hist > 0 && hist <= 20 && depth_histogram20) depth_histogram20[hist - 1]++;
+    if (!(status & 1)) continue;
+    if (count < capacity && out) {
+      rt_photon& ph = out[count];
+      ph.position[0] = ha[q].x;
+      ph.position[1] = ha[q].y;
+      ph.position[2] = ha[q].z;
+      ph.direction[0] = hb[q].x;
+      ph.direction[1] = hb[q].y;
+      ph.direction[2] = hb[q].z;
+      ph.weight = ha[q].w;
+    }
+    count++;
+    if (per_light_counts) per_light_counts[q / npaths]++;
+  }
+  if (out && count > capacity) return fail(RT_ERR_INVALID, "photon output capacity too small");
+  return pull_counters(c);
+}
+
+int rt_set_photons(rt_ctx* c, const rt_photon* photons, int64_t n) {
+  int rc = bind(c);
+  if (rc) return rc;
+  if (n < 0 || (n > 0 && !photons)) return fail(RT_ERR_INVALID, "bad photon list");
+  if (n >= (1 << 28)) return fail(RT_ERR_INVALID, "too many photons");
+  static_assert(sizeof(rt_photon) == 28, "rt_photon must match Particle (28 bytes)");
+  c->kd_nodes7.assign((const float*)photons, (const float*)photons + 7 * n);
+  build_kdtree(c->kd_nodes7, &c->kd_height);
+  if (c->kd_height > kKdStack) return fail(RT_ERR_INVALID, "kd-tree deeper than the device stack");
+  std::vector<float4> hp(std::max<int64_t>(n, 1)), hd(std::max<int64_t>(n, 1));
+  for (int64_t i = 0; i < n; i++) {
+    const float* a = &c->kd_nodes7[7 * i];
+    hp[i] = make_float4(a[0], a[1], a[2], a[6]);
+    hd[i] = make_float4(a[3], a[4], a[5], 0.f);
+  }
+  CU(c->d_kd_pos.ensure(hp.size()));
+  CU(c->d_kd_dir.ensure(hd.size()));
+  CU(cudaMemcpy(c->d_kd_pos.p, hp.data(), hp.size() * sizeof(float4), cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(c->d_kd_dir.p, hd.data(), hd.size() * sizeof(float4), cudaMemcpyHostToDevice));
+  c->scene.kd_pos = c->d_kd_pos.p;
+  c->scene.kd_dir = c->d_kd_dir.p;
+  c->scene.kd_count = (int)n;
+  c->stats.photons_stored = n;
+  c->photon_map_built = true;
+  c->photon_map_seed = c->params.seed;
+  c->photon_map_requested = c->params.num_photons;
+  return RT_OK;
+}
+
+int rt_build_photon_map(rt_ctx* c) {
+  int rc = bind(c);
+  if (rc) return rc;
+  const int per_light = photons_per_light(c, nullptr);
+  std::vector<rt_photon> list((size_t)std::max(1, per_light * c->L));
+  std::vector<int64_t> counts(std::max(c->L, 1));
+  if ((rc = rt_emit_photons(c, 0, -1, list.data(), (int64_t)list.size(), counts.data(), nullptr))) return rc;
+  int64_t n = 0;
+  for (int l = 0; l < c->L; l++) n += counts[l];
+  return rt_set_photons(c, list.data(), n);
+}
+
+int rt_get_photons(rt_ctx* c, rt_photon* out, int64_t capacity, int64_t* count) {
+  if (!c || !count) return fail(RT_ERR_INVALID, "null argument");
+  int64_t n = (int64_t)c->kd_nodes7.size() / 7;
+  *count = n;
+  if (out) {
+    if (capacity < n) return fail(RT_ERR_INVALID, "capacity too small");
+    std::memcpy(out, c->kd_nodes7.data(), sizeof(float) * 7 * (size_t)n);
+  }
+  return RT_OK;
+}
+
+int rt_get_kdtree(rt_ctx* c, rt_photon* nodes, int32_t* left, int32_t* right, int32_t* root, int64_t capacity) {
+  if (!c || !root) return fail(RT_ERR_INVALID, "null argument");
+  int64_t n = (int64_t)c->kd_nodes7.size() / 7;
+  if (capacity < n) return fail(RT_ERR_INVALID, "capacity too small");
+  if (nodes) std::memcpy(nodes, c->kd_nodes7.data(), sizeof(float) * 7 * (size_t)n);
+  std::vector<int32_t> l, r;
+  kdtree_links(n, l, r, root);
+  if (left) std::memcpy(left, l.data(), sizeof(int32_t) * (size_t)n);
+  if (right) std::memcpy(right, r.data(), sizeof(int32_t) * (size_t)n);
+  return RT_OK;
+}
+
+int rt_knn(rt_ctx* c, const float* queries, int64_t n, int32_t k, int32_t* node_index) {
+  int rc = bind(c);
+  if (rc) return rc;
+  if (n < 0 || (n > 0 && (!queries || !node_index))) return fail(RT_ERR_INVALID, "bad argument");
+  if (c->scene.kd_count == 0) return fail(RT_ERR_EMPTY_TREE, "tree is empty");  // kdtree.h:181
+  if (k > c->scene.kd_count) return fail(RT_ERR_K_TOO_LARGE, "k is greater than the number of nodes");
+  if (k < 1 || k > RT_MAX_K) return fail(RT_ERR_INVALID, "k must be in [1, 64]");
+  if (n == 0) return RT_OK;
+  DevBuf<float> d_q;
+  DevBuf<int> d_idx;
+  cudaError_t e = d_q.ensure(3 * (size_t)n);
+  if (e == cudaSuccess) e = d_idx.ensure((size_t)n * k);
+  if (e == cudaSuccess) e = cudaMemcpy(d_q.p, queries, sizeof(float) * 3 * (size_t)n, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) {
+    launch_knn(c->scene, d_q.p, n, k, d_idx.p, c->d_counters.p, c->stream);
+    c->stats.kernel_launches++;
+    e = cudaStreamSynchronize(c->stream);
+  }
+  if (e == cudaSuccess) e = cudaMemcpy(node_index, d_idx.p, sizeof(int) * (size_t)n * k, cudaMemcpyDeviceToHost);
+  d_q.release();
+  d_idx.release();
+  if (e != cudaSuccess) return fail(RT_ERR_CUDA, cudaGetErrorString(e));
+  return RT_OK;
+}
+
+int rt_get_stats(rt_ctx* c, rt_stats* out) {
+  if (!c || !out) return fail(RT_ERR_INVALID, "null argument");
+  *out = c->stats;
+  return RT_OK;
+}
+int rt_reset_stats(rt_ctx* c) {
+  if (!c) return fail(RT_ERR_INVALID, "null context");
+  int nodes = c->stats.bvh_nodes, depth = c->stats.bvh_depth;
+  int64_t stored = c->stats.photons_stored;
+  int rc = bind(c);
+  if (rc) return rc;
+  CU(cudaMemset(c->d_counters.p, 0, sizeof(unsigned long long) * kCntNum));
+  c->stats = rt_stats{};
+  c->stats.bvh_nodes = nodes;
+  c->stats.bvh_depth = depth;
+  c->stats.photons_stored = stored;
+  return RT_OK;
+}
+int rt_get_bvh(rt_ctx* c, float* nodes16, int64_t capacity_nodes, int32_t* num_nodes, int32_t* depth) {
+  if (!c) return fail(RT_ERR_INVALID, "null context");
+  int n = (int)(c->bvh.nodes.size() / 16);
+  if (num_nodes) *num_nodes = n;
+  if (depth) *depth = c->bvh.depth;
+  if (nodes16) {
+    if (capacity_nodes < n) return fail(RT_ERR_INVALID, "capacity too small");
+    std::memcpy(nodes16, c->bvh.nodes.data(), c->bvh.nodes.size() * sizeof(float));
+  }
+  return RT_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,223 @@
+// host_build.cpp -- see host_build.h.  Host C++ only.
+#include "host_build.h"
+
+#include <algorithm>
+#include <atomic>
+#include <cfloat>
+#include <cmath>
+#include <cstring>
+#include <limits>
+#include <thread>
+
+namespace rtb {
+namespace {
+
+struct Box {
+  float lo[3], hi[3];
+  void reset() {
+    for (int a = 0; a < 3; a++) {
+      lo[a] = FLT_MAX;
+      hi[a] = -FLT_MAX;
+    }
+  }
+  void grow(const Box& b) {
+    for (int a = 0; a < 3; a++) {
+      lo[a] = std::min(lo[a], b.lo[a]);
+      hi[a] = std::max(hi[a], b.hi[a]);
+    }
+  }
+};
+
+// BVH.h:131-140: first axis whose extent is strictly larger than everything before it
+inline int cut_axis(const Box& b) {
+  float longest = 0.f;
+  int axis = 0;
+  for (int a = 0; a < 3; a++) {
+    float len = b.hi[a] - b.lo[a];
+    if (len > longest) {
+      longest = len;
+      axis = a;
+    }
+  }
+  return axis;
+}
+
+struct Builder {
+  float pad;
+  float* nodes;
+  int32_t* slot_tri;
+  std::vector<Box> tri_box;           // per global triangle, exact
+  std::vector<float> key[3];          // BVH.h:143-148: p0[a] + p1[a] + p2[a]
+  std::atomic<int> max_depth{0};
+
+  void write_child(float* node, int side, const Box* b, int32_t ref) {
+    float* lo = node + 6 * side;
+    float* hi = lo + 3;
+    for (int a = 0; a < 3; a++) {
+      lo[a] = b ? b->lo[a] - pad : std::numeric_limits<float>::quiet_NaN();
+      hi[a] = b ? b->hi[a] + pad : std::numeric_limits<float>::quiet_NaN();
+    }
+    std::memcpy(node + 12 + side, &ref, 4);
+  }
+  void note_depth(int d) {
+    int cur = max_depth.load();
+    while (d > cur && !max_depth.compare_exchange_weak(cur, d)) {
+    }
+  }
+
+  // Subtree over idx[0..n): internal nodes [node_base, node_base+n-1), slots [slot_base, slot_base+n).
+  int32_t build(int32_t* idx, int n, int node_base, int slot_base, int depth, Box& box, int fork_levels) {
+    if (n == 1) {
+      slot_tri[slot_base] = idx[0];
+      box = tri_box[idx[0]];
+      note_depth(depth);
+      return ~slot_base;
+    }
+    box.reset();
+    for (int i = 0; i < n; i++) box.grow(tri_box[idx[i]]);
+    const std::vector<float>& k = key[cut_axis(box)];
+    std::sort(idx, idx + n, [&k](int32_t a, int32_t b) { return k[a] < k[b]; });  // BVH.h:141-150
+    int nl = n / 2;                                                              // BVH.h:151-158
+    Box bl, br;
+    int32_t rl, rr;
+    if (fork_levels > 0 && n > 32768) {
+      std::thread t([&]() { rl = build(idx, nl, node_base + 1, slot_base, depth + 1, bl, fork_levels - 1); });
+      rr = build(idx + nl, n - nl, node_base + nl, slot_base + nl, depth + 1, br, fork_levels - 1);
+      t.join();
+    } else {
+      rl = build(idx, nl, node_base + 1, slot_base, depth + 1, bl, 0);
+      rr = build(idx + nl, n - nl, node_base + nl, slot_base + nl, depth + 1, br, 0);
+    }
+    float* node = nodes + 16 * (size_t)node_base;
+    write_child(node, 0, &bl, rl);
+    write_child(node, 1, &br, rr);
+    node[14] = node[15] = 0.f;
+    return node_base;
+  }
+
+  struct Item {
+    int32_t ref;
+    Box box;
+    float key[3];
+  };
+  // top level over mesh subtrees: same policy on the mesh boxes (key = lo + hi on the cut axis)
+  int32_t build_top(Item* items, int n, int node_base, int depth, Box& box, int sub_depth) {
+    if (n == 1) {
+      box = items[0].box;
+      return items[0].ref;
+    }
+    box.reset();
+    for (int i = 0; i < n; i++) box.grow(items[i].box);
+    int axis = cut_axis(box);
+    std::sort(items, items + n, [axis](const Item& a, const Item& b) { return a.key[axis] < b.key[axis]; });
+    int nl = n / 2;
+    Box bl, br;
+    int32_t rl = build_top(items, nl, node_base + 1, depth + 1, bl, sub_depth);
+    int32_t rr = build_top(items + nl, n - nl, node_base + nl, depth + 1, br, sub_depth);
+    float* node = nodes + 16 * (size_t)node_base;
+    write_child(node, 0, &bl, rl);
+    write_child(node, 1, &br, rr);
+    node[14] = node[15] = 0.f;
+    note_depth(depth + 1 + sub_depth);
+    return node_base;
+  }
+};
+
+}  // namespace
+
+void build_bvh(int num_vertices, const float* P, int T, const int32_t* tri, int M, const int32_t* mesh_first_triangle,
+               float extent, float pad_fraction, Bvh& out) {
+  (void)num_vertices;
+  Builder B;
+  out.pad = B.pad = extent * pad_fraction;
+  B.tri_box.resize(T);
+  for (int a = 0; a < 3; a++) B.key[a].resize(T);
+  for (int t = 0; t < T; t++) {
+    Box& b = B.tri_box[t];
+    b.reset();
+    const float* p[3] = {P + 3 * (size_t)tri[3 * t], P + 3 * (size_t)tri[3 * t + 1], P + 3 * (size_t)tri[3 * t + 2]};
+    for (int a = 0; a < 3; a++) {
+      for (int v = 0; v < 3; v++) {
+        b.lo[a] = std::min(b.lo[a], p[v][a]);
+        b.hi[a] = std::max(b.hi[a], p[v][a]);
+      }
+      B.key[a][t] = p[0][a] + p[1][a] + p[2][a];
+    }
+  }
+  int nonempty = 0;
+  for (int m = 0; m < M; m++)
+    if (mesh_first_triangle[m + 1] > mesh_first_triangle[m]) nonempty++;
+  size_t num_nodes = (size_t)std::max(T - nonempty, 0) + (size_t)std::max(nonempty - 1, 0);
+  if (num_nodes == 0) num_nodes = 1;  // T <= 1: a root with at most one leaf child
+  out.nodes.assign(16 * num_nodes, 0.f);
+  out.slot_tri.assign(T, 0);
+  B.nodes = out.nodes.data();
+  B.slot_tri = out.slot_tri.data();
+
+  std::vector<int32_t> idx(T);
+  for (int t = 0; t < T; t++) idx[t] = t;
+  std::vector<Builder::Item> items;
+  int node_base = std::max(nonempty - 1, 0);
+  int sub_depth = 0;
+  for (int m = 0; m < M; m++) {
+    int t0 = mesh_first_triangle[m], n = mesh_first_triangle[m + 1] - t0;
+    if (n <= 0) continue;
+    Builder::Item it;
+    B.max_depth = 0;
+    it.ref = B.build(idx.data() + t0, n, node_base, t0, 0, it.box, 3);
+    sub_depth = std::max(sub_depth, B.max_depth.load());
+    for (int a = 0; a < 3; a++) it.key[a] = it.box.lo[a] + it.box.hi[a];
+    items.push_back(it);
+    node_base += n - 1;
+  }
+  B.max_depth = sub_depth;
+  if (items.empty()) {
+    B.write_child(B.nodes, 0, nullptr, -1);
+    B.write_child(B.nodes, 1, nullptr, -1);
+  } else if (items.size() == 1 && items[0].ref < 0) {  // a single triangle in the whole scene
+    B.write_child(B.nodes, 0, &items[0].box, items[0].ref);
+    B.write_child(B.nodes, 1, nullptr, -1);
+  } else if (items.size() > 1) {
+    Box root;
+    B.build_top(items.data(), (int)items.size(), 0, 0, root, sub_depth);
+  }  // else: the single mesh's root already sits at node 0
+  out.depth = B.max_depth.load() + 1;
+}
+
+namespace {
+struct KdItem {
+  float v[7];
+};
+int make_tree(KdItem* nodes, size_t begin, size_t end, size_t index) {  // kdtree.h:60-69
+  if (end <= begin) return 0;
+  size_t n = begin + (end - begin) / 2;
+  std::nth_element(nodes + begin, nodes + n, nodes + end,
+                   [index](const KdItem& a, const KdItem& b) { return a.v[index] < b.v[index]; });
+  index = (index + 1) % 3;
+  int hl = make_tree(nodes, begin, n, index);
+  int hr = make_tree(nodes, n + 1, end, index);
+  return 1 + std::max(hl, hr);
+}
+int32_t link_tree(size_t begin, size_t end, int32_t* left, int32_t* right) {
+  if (end <= begin) return -1;
+  size_t n = begin + (end - begin) / 2;
+  left[n] = link_tree(begin, n, left, right);
+  right[n] = link_tree(n + 1, end, left, right);
+  return (int32_t)n;
+}
+}  // namespace
+
+void build_kdtree(std::vector<float>& photons7, int* height_out) {
+  static_assert(sizeof(KdItem) == 28, "Particle is 28 bytes");
+  size_t n = photons7.size() / 7;
+  int h = make_tree(reinterpret_cast<KdItem*>(photons7.data()), 0, n, 0);
+  if (height_out) *height_out = h;
+}
+
+void kdtree_links(int64_t n, std::vector<int32_t>& left, std::vector<int32_t>& right, int32_t* root) {
+  left.assign(n, -1);
+  right.assign(n, -1);
+  *root = link_tree(0, (size_t)n, left.data(), right.data());
+}
+
+}  // namespace rtb

@@ -1,0 +1,526 @@
+// rt_device.cuh -- device-side building blocks of the render hot path (sm_100a).
+//
+// Everything that decides WHICH triangle a ray hits, WHERE the hit point is and WHETHER a shadow ray
+// is blocked is strict IEEE binary32 in the reference's operation order with no fused multiply-add
+// (occlusion decisions at t ~ 1e-7 are bit-chaotic).  Those routines
+// use the round-to-nearest intrinsics (__fmul_rn/__fadd_rn/...), which nvcc never contracts, so the
+// result does not depend on -fmad; the file is compiled with -fmad=false as a second line of defence.
+// Reference citations are file:line under /root/reference/source.
+#pragma once
+#include <cuda_runtime.h>
+#include <float.h>
+#include <stdint.h>
+
+namespace rtb {
+
+// ------------------------------------------------------------------------------------------------
+// strict float3 algebra (Vec3.h)
+// ------------------------------------------------------------------------------------------------
+#define RT_DI __device__ __forceinline__
+
+RT_DI float3 f3(float x, float y, float z) { return make_float3(x, y, z); }
+RT_DI float3 f3(float4 a) { return make_float3(a.x, a.y, a.z); }
+RT_DI float3 v_add(float3 a, float3 b) { return f3(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y), __fadd_rn(a.z, b.z)); }
+RT_DI float3 v_sub(float3 a, float3 b) { return f3(__fsub_rn(a.x, b.x), __fsub_rn(a.y, b.y), __fsub_rn(a.z, b.z)); }
+RT_DI float3 v_neg(float3 a) { return f3(-a.x, -a.y, -a.z); }
+RT_DI float3 v_mul(float3 a, float3 b) { return f3(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y), __fmul_rn(a.z, b.z)); }
+RT_DI float3 v_scl(float3 a, float s) { return f3(__fmul_rn(a.x, s), __fmul_rn(a.y, s), __fmul_rn(a.z, s)); }
+RT_DI float3 v_dvs(float3 a, float s) { return f3(__fdiv_rn(a.x, s), __fdiv_rn(a.y, s), __fdiv_rn(a.z, s)); }
+// Vec3.h:220-223  (a0*b0 + a1*b1) + a2*b2
+RT_DI float v_dot(float3 a, float3 b) {
+  return __fadd_rn(__fadd_rn(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y)), __fmul_rn(a.z, b.z));
+}
+// Vec3.h:225-232
+RT_DI float3 v_cross(float3 a, float3 b) {
+  return f3(__fsub_rn(__fmul_rn(a.y, b.z), __fmul_rn(a.z, b.y)), __fsub_rn(__fmul_rn(a.z, b.x), __fmul_rn(a.x, b.z)),
+            __fsub_rn(__fmul_rn(a.x, b.y), __fmul_rn(a.y, b.x)));
+}
+// Vec3.h:165-167: (float)sqrt((double)x).  A correctly rounded binary32 sqrt gives the same value
+// (double rounding is innocuous for sqrt when the wide format has >= 2*24+2 bits).
+RT_DI float v_len(float3 a) { return __fsqrt_rn(v_dot(a, a)); }
+RT_DI float v_dist(float3 a, float3 b) { return v_len(v_sub(a, b)); }
+// Vec3.h:170-178: zero stays zero; otherwise multiply by 1/len (not divide by len).
+RT_DI float3 v_norm(float3 a) {
+  float l = v_len(a);
+  if (l == 0.0f) return a;
+  float inv = __frcp_rn(l);  // == 1.0f / l, correctly rounded
+  return v_scl(a, inv);
+}
+// Vec3.h:180-199
+RT_DI void v_two_orthogonals(float3 n, float3& u, float3& v) {
+  if (fabsf(n.x) < fabsf(n.y)) {
+    if (fabsf(n.x) < fabsf(n.z))
+      u = f3(0.f, -n.z, n.y);
+    else
+      u = f3(-n.y, n.x, 0.f);
+  } else {
+    if (fabsf(n.y) < fabsf(n.z))
+      u = f3(n.z, 0.f, -n.x);
+    else
+      u = f3(-n.y, n.x, 0.f);
+  }
+  v = v_cross(n, u);
+}
+
+// ------------------------------------------------------------------------------------------------
+// counter-based random stream (DESIGN.md "RNG contract"); word -> uniform arithmetic of libstdc++'s
+// generate_canonical for a 32-bit engine
+// ------------------------------------------------------------------------------------------------
+constexpr uint64_t kGolden = 0x9E3779B97F4A7C15ull;
+constexpr uint64_t kDomainPixel = 1ull;
+constexpr uint64_t kDomainPhoton = 2ull;
+
+__host__ __device__ __forceinline__ uint64_t mix64(uint64_t z) {
+  z ^= z >> 30;
+  z *= 0xBF58476D1CE4E5B9ull;
+  z ^= z >> 27;
+  z *= 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  return z;
+}
+__host__ __device__ __forceinline__ uint64_t stream_key(uint64_t seed_mixed, uint64_t domain, uint64_t index) {
+  return mix64(seed_mixed ^ ((domain << 56) | index));  // seed_mixed = mix64(seed + kGolden), host-computed
+}
+
+struct Rng {
+  uint64_t key;
+  uint64_t pair;      // cached pair(ctr/2)
+  uint32_t ctr;       // next word index
+  uint32_t pair_idx;  // which pair is cached (0xffffffff = none)
+  RT_DI void init(uint64_t k, uint32_t first_word) {
+    key = k;
+    ctr = first_word;
+    pair_idx = 0xffffffffu;
+    pair = 0;
+  }
+  RT_DI uint32_t word() {
+    uint32_t j = ctr >> 1;
+    if (j != pair_idx) {
+      pair = mix64(key + (uint64_t)(j + 1u) * kGolden);
+      pair_idx = j;
+    }
+    uint32_t w = (ctr & 1u) ? (uint32_t)(pair >> 32) : (uint32_t)pair;
+    ctr++;
+    return w;
+  }
+  RT_DI float canonical_f() {
+    float f = __fmul_rn(__uint2float_rn(word()), 2.3283064365386963e-10f);  // float(w) / 2^32 (exact scaling)
+    if (f >= 1.0f) f = 0.99999994f;                                        // nextafterf(1, 0)
+    return f;
+  }
+  RT_DI double canonical_d() {
+    double lo = (double)word();
+    double hi = (double)word();
+    double g = __dmul_rn(__dadd_rn(lo, __dmul_rn(hi, 4294967296.0)), 5.421010862427522e-20);  // / 2^64
+    if (g >= 1.0) g = 0.99999999999999989;  // nextafter(1.0, 0.0)
+    return g;
+  }
+  // uniform_real_distribution: canonical * (b - a) + a
+  RT_DI float uniform_f(float a, float b) { return __fadd_rn(__fmul_rn(canonical_f(), __fsub_rn(b, a)), a); }
+  RT_DI double uniform_d0(double b) { return __dadd_rn(__dmul_rn(canonical_d(), b), 0.0); }  // a == 0.0
+};
+
+// ------------------------------------------------------------------------------------------------
+// device scene
+// ------------------------------------------------------------------------------------------------
+struct DMaterial {  // Material.h:62-64
+  float kd, alpha;
+  float3 albedo, f0;
+};
+struct DLight {  // LightSource.h:61-65
+  float3 position, color, normal, vertical, horizontal;
+  float intensity, side, ac, al, aq, factor;
+};
+struct DCamera {  // Camera.h:34-40
+  float3 position, lower_left, horizontal, vertical;
+};
+
+constexpr int kMaxLights = 8;
+constexpr int kStackDepth = 40;  // BVH traversal stack entries per ray (host checks bvh depth <= this)
+constexpr int kBlock = 128;      // threads per CTA of the wavefront kernels
+constexpr int kMaxK = 64;
+constexpr int kKdStack = 32;     // kd-tree recursion depth bound (host checks)
+
+struct DScene {
+  const float4* __restrict__ nodes;     // 4 x float4 per BVH node (see bvh_build.h)
+  const float4* __restrict__ tris;      // 3 x float4 per triangle slot, BVH leaf order: (p0,gid) (e1,-) (e2,-)
+  const int4* __restrict__ tri_vidx;    // per GLOBAL triangle: v0, v1, v2 (global vertex ids), mesh
+  const float4* __restrict__ pos;       // per vertex
+  const float4* __restrict__ nrm;       // per vertex
+  const DMaterial* __restrict__ mats;   // per mesh
+  DLight lights[kMaxLights];
+  int num_lights;
+  int num_tris;
+  DCamera cam;
+  // photon map: kd-tree in the array order of kdtree::make_tree (kdtree.h:60-69), links implicit
+  const float4* __restrict__ kd_pos;  // xyz = position, w = weight
+  const float4* __restrict__ kd_dir;  // xyz = incomeDirection
+  int kd_count;
+};
+
+struct HitRec {
+  float t, u, v;
+  int gid;  // global triangle index, scene order
+};
+
+// ------------------------------------------------------------------------------------------------
+// Ray.cpp:9-24  Moller-Trumbore with the absolute epsilon on det.  e1/e2 are the host-precomputed
+// p1-p0 / p2-p0 (the same binary32 subtractions the reference performs per test).  Early exits skip
+// work the reference would discard; accepted hits get bit-identical u, v, t.
+// ------------------------------------------------------------------------------------------------
+RT_DI bool mt_intersect(float3 o, float3 d, float3 p0, float3 e1, float3 e2, float& u, float& v, float& t) {
+  float3 pvec = v_cross(d, e2);
+  float det = v_dot(e1, pvec);
+  if (fabsf(det) < 0.000001f) return false;
+  float inv_det = __frcp_rn(det);  // == 1.0f / det
+  float3 tvec = v_sub(o, p0);
+  u = __fmul_rn(v_dot(tvec, pvec), inv_det);
+  if (u < 0.f || u > 1.f) return false;
+  float3 qvec = v_cross(tvec, e1);
+  v = __fmul_rn(v_dot(d, qvec), inv_det);
+  if (!(v >= 0.f && __fadd_rn(u, v) <= 1.f)) return false;
+  t = __fmul_rn(v_dot(e2, qvec), inv_det);
+  return true;
+}
+
+// RayTracer.h:40 acceptance, made order-independent: the reference scans in scene order with a
+// strict `dt < closest`, i.e. it returns the minimum t and, among exactly equal t, the lowest index.
+RT_DI void accept_nearest(HitRec& h, float t, float u, float v, int gid) {
+  if (t > 0.f && t < FLT_MAX && (t < h.t || (t == h.t && gid < h.gid))) {
+    h.t = t;
+    h.u = u;
+    h.v = v;
+    h.gid = gid;
+  }
+}
+
+// Conservative slab test against a padded box (see bvh_build.h for the padding argument).  NaNs from
+// 0*inf drop out of fminf/fmaxf.  A child is visited when its interval overlaps [0, best_t].
+RT_DI bool box_hit(float3 lo, float3 hi, float3 o, float3 inv, float best_t, float& tnear) {
+  float t0x = (lo.x - o.x) * inv.x, t1x = (hi.x - o.x) * inv.x;
+  float t0y = (lo.y - o.y) * inv.y, t1y = (hi.y - o.y) * inv.y;
+  float t0z = (lo.z - o.z) * inv.z, t1z = (hi.z - o.z) * inv.z;
+  float tmin = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fminf(t0z, t1z));
+  float tmax = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fmaxf(t0z, t1z));
+  tnear = tmin;
+  return (tmin <= tmax) && (tmax >= 0.f) && (tmin <= best_t);
+}
+
+// Nearest-hit (ANY=false) or any-hit (ANY=true) traversal of the flattened BVH.
+// `stack` points at this thread's column of a [kStackDepth][blockDim.x] shared-memory array.
+template <bool ANY>
+RT_DI bool bvh_traverse(const DScene& S, float3 o, float3 d, int* stack, int stride, HitRec& h) {
+  h.t = FLT_MAX;
+  h.u = 0.f;
+  h.v = 0.f;
+  h.gid = 0x7fffffff;
+  const float3 inv = f3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+  int sp = 0;
+  int cur = 0;
+  for (;;) {
+    const float4 n0 = __ldg(S.nodes + 4 * cur);
+    const float4 n1 = __ldg(S.nodes + 4 * cur + 1);
+    const float4 n2 = __ldg(S.nodes + 4 * cur + 2);
+    const float4 n3 = __ldg(S.nodes + 4 * cur + 3);
+    float tn0, tn1;
+    bool h0 = box_hit(f3(n0.x, n0.y, n0.z), f3(n0.w, n1.x, n1.y), o, inv, h.t, tn0);
+    bool h1 = box_hit(f3(n1.z, n1.w, n2.x), f3(n2.y, n2.z, n2.w), o, inv, h.t, tn1);
+    int c0 = __float_as_int(n3.x), c1 = __float_as_int(n3.y);
+#pragma unroll
+    for (int side = 0; side < 2; side++) {
+      bool& hs = side ? h1 : h0;
+      int c = side ? c1 : c0;
+      if (hs && c < 0) {  // leaf child: one triangle
+        int slot = ~c;
+        float4 A = __ldg(S.tris + 3 * slot), B = __ldg(S.tris + 3 * slot + 1), C = __ldg(S.tris + 3 * slot + 2);
+        float u, v, t;
+        if (mt_intersect(o, d, f3(A), f3(B), f3(C), u, v, t)) {
+          if (ANY) {
+            if (t > 0.f && t < FLT_MAX) return true;
+          } else {
+            accept_nearest(h, t, u, v, __float_as_int(A.w));
+          }
+        }
+        hs = false;
+      }
+    }
+    if (h0 && h1) {
+      bool first0 = tn0 <= tn1;
+      stack[sp * stride] = first0 ? c1 : c0;
+      sp++;
+      cur = first0 ? c0 : c1;
+    } else if (h0) {
+      cur = c0;
+    } else if (h1) {
+      cur = c1;
+    } else {
+      if (sp == 0) break;
+      sp--;
+      cur = stack[sp * stride];
+    }
+  }
+  return ANY ? false : (h.gid != 0x7fffffff);
+}
+
+// RayTracer.h:27-53 as written: scan every triangle (parity hook / tiny scenes).
+template <bool ANY>
+RT_DI bool brute_trace(const DScene& S, float3 o, float3 d, HitRec& h) {
+  h.t = FLT_MAX;
+  h.u = 0.f;
+  h.v = 0.f;
+  h.gid = 0x7fffffff;
+  for (int s = 0; s < S.num_tris; s++) {
+    float4 A = __ldg(S.tris + 3 * s), B = __ldg(S.tris + 3 * s + 1), C = __ldg(S.tris + 3 * s + 2);
+    float u, v, t;
+    if (mt_intersect(o, d, f3(A), f3(B), f3(C), u, v, t)) {
+      if (ANY) {
+        if (t > 0.f && t < FLT_MAX) return true;
+      } else {
+        accept_nearest(h, t, u, v, __float_as_int(A.w));
+      }
+    }
+  }
+  return ANY ? false : (h.gid != 0x7fffffff);
+}
+
+// ------------------------------------------------------------------------------------------------
+// sampling
+// ------------------------------------------------------------------------------------------------
+// RayTracer.h:109-117 (sums formed in double, rounded once); jd = int(sqrt(float(N))) from the host
+RT_DI void jitter_sample(Rng& g, int sample, int jd, float& x, float& y) {
+  int j2 = sample / jd, i2 = sample % jd;
+  double fd = (double)(float)jd;
+  x = (float)__ddiv_rn(__dadd_rn((double)(float)i2, g.uniform_d0(1.0)), fd);
+  y = (float)__ddiv_rn(__dadd_rn((double)(float)j2, g.uniform_d0(1.0)), fd);
+}
+// Camera.h:27-30 through Renderer.cpp:233-234
+RT_DI void camera_ray(const DCamera& c, int x, int y, float sx, float sy, int w, int h, float3& o, float3& d) {
+  float u = __fdiv_rn(__fadd_rn((float)x, sx), (float)w);
+  float v = __fsub_rn(1.f, __fdiv_rn(__fadd_rn((float)y, sy), (float)h));
+  o = c.position;
+  d = v_norm(v_sub(v_add(v_add(c.lower_left, v_scl(c.horizontal, u)), v_scl(c.vertical, v)), c.position));
+}
+// RayTracer.h:95-107 with maxRayAngle = float(pi/2).  asin in binary64 like the reference; the
+// reference's cosf/sinf (glibc) are replaced by binary64 sin/cos rounded to binary32, which agrees
+// with a correctly rounded binary32 result (glibc's are within 0.56 ulp) -- transcendental, so parity
+// downstream of this routine is statistical by contract (SURVEY.md section 7 "Hard parts").
+RT_DI float3 hsphere_uniform_sample(Rng& g, float3 normal) {
+  const double hi = 1.0000000278275352;  // 2*float(pi/2)/pi
+  normal = v_norm(normal);
+  float3 v1, v2;
+  v_two_orthogonals(normal, v1, v2);
+  v1 = v_norm(v1);
+  v2 = v_norm(v2);
+  float theta = (float)asin(g.uniform_d0(hi));
+  float phi = (float)__dmul_rn(6.283185307179586, g.uniform_d0(hi));
+  double sp, cp, st, ct;
+  sincos((double)phi, &sp, &cp);
+  sincos((double)theta, &st, &ct);
+  float3 direction = v_norm(v_add(v_scl(v1, (float)cp), v_scl(v2, (float)sp)));
+  return v_norm(v_add(v_scl(normal, (float)ct), v_scl(direction, (float)st)));
+}
+// LightSource.h:46-49: the first draw scales m_horizontal, the second m_vertical (g++ evaluates the
+// right operand of the outer + first; pinned against the reference build by the oracle tests).
+RT_DI float3 light_rand_area_position(const DLight& l, Rng& g) {
+  float a = g.uniform_f(-l.side, l.side);
+  float b = g.uniform_f(-l.side, l.side);
+  return v_add(v_add(l.position, v_scl(l.vertical, b)), v_scl(l.horizontal, a));
+}
+// LightSource.h:51-54
+RT_DI float light_radiance(const DLight& l, float3 p) {
+  float d = v_dist(p, l.position);
+  return __fdiv_rn(l.intensity, __fadd_rn(__fadd_rn(l.ac, __fmul_rn(l.al, d)), __fmul_rn(__fmul_rn(l.aq, d), d)));
+}
+// LightSource.h:56-59
+RT_DI float3 light_evaluate(const DLight& l, float3 p) { return v_scl(v_scl(l.color, l.factor), light_radiance(l, p)); }
+
+// ------------------------------------------------------------------------------------------------
+// Material.h:25-69, in the reference's mixed binary32/binary64 promotions.  pow(x,2) and pow(x,5)
+// are formed by multiplication in binary64 (<= 2 ulp of binary64 from glibc's pow, invisible after
+// the rounding to binary32 that follows except with probability ~1e-8).
+// ------------------------------------------------------------------------------------------------
+RT_DI float g_schlick(float alpha, float3 w, float3 n) {
+  float k = (float)__dmul_rn((double)alpha, 0.7978845608028654);  // alpha * sqrt(2/pi)
+  float nw = v_dot(n, w);
+  return __fdiv_rn(nw, __fadd_rn(__fmul_rn(nw, __fsub_rn(1.f, k)), k));
+}
+RT_DI float3 specular_response(const DMaterial& m, float3 n, float3 wi, float3 wo) {
+  const double kPi = 3.141592653589793;
+  float3 wh = v_norm(v_add(wi, wo));
+  float a2 = __fmul_rn(m.alpha, m.alpha);
+  double nh = (double)v_dot(n, wh);
+  double inner = __dadd_rn(1.0, __dmul_rn((double)__fsub_rn(a2, 1.f), __dmul_rn(nh, nh)));
+  float D = (float)__ddiv_rn((double)a2, __dmul_rn(kPi, __dmul_rn(inner, inner)));
+  double x = __dsub_rn(1.0, fmax(0.0, (double)v_dot(wi, wh)));
+  double x2 = __dmul_rn(x, x);
+  float fr = (float)__dmul_rn(__dmul_rn(x2, x2), x);
+  float3 F = v_add(m.f0, v_scl(v_sub(f3(1.f, 1.f, 1.f), m.f0), fr));
+  float G = __fmul_rn(g_schlick(m.alpha, wi, n), g_schlick(m.alpha, wo, n));
+  float denom = (float)__dmul_rn(__dmul_rn(4.0, (double)v_dot(n, wi)), (double)v_dot(n, wo));
+  return v_dvs(v_scl(v_scl(F, D), G), denom);
+}
+RT_DI float3 evaluate_color_response(const DMaterial& m, float3 n, float3 wi, float3 wo) {
+  float3 diffuse = v_dvs(m.albedo, 3.14159274f);  // albedo / float(M_PI)
+  float3 spec = specular_response(m, v_norm(n), v_norm(wi), v_norm(wo));
+  float3 r = v_add(v_scl(diffuse, m.kd), v_scl(spec, __fsub_rn(1.f, m.kd)));
+  if (r.x < 0.f) r.x = 0.f;
+  if (r.y < 0.f) r.y = 0.f;
+  if (r.z < 0.f) r.z = 0.f;
+  return r;
+}
+// Renderer.cpp:279-283: fmax(fmin(c,1),0) -- a NaN channel becomes 1
+RT_DI float3 normalize_color(float3 c) {
+  return f3(fmaxf(fminf(c.x, 1.f), 0.f), fmaxf(fminf(c.y, 1.f), 0.f), fmaxf(fminf(c.z, 1.f), 0.f));
+}
+
+// Renderer.cpp:36,42-43,274-277: hit normal and hit point from barycentrics (w*A + u*B) + v*C
+RT_DI void hit_geometry(const DScene& S, const HitRec& h, float3& n, float3& P, int& mesh) {
+  int4 vi = __ldg(S.tri_vidx + h.gid);
+  mesh = vi.w;
+  float w = __fsub_rn(__fsub_rn(1.f, h.u), h.v);
+  float3 n0 = f3(__ldg(S.nrm + vi.x)), n1 = f3(__ldg(S.nrm + vi.y)), n2 = f3(__ldg(S.nrm + vi.z));
+  float3 p0 = f3(__ldg(S.pos + vi.x)), p1 = f3(__ldg(S.pos + vi.y)), p2 = f3(__ldg(S.pos + vi.z));
+  n = v_norm(v_add(v_add(v_scl(n0, w), v_scl(n1, h.u)), v_scl(n2, h.v)));
+  P = v_add(v_add(v_scl(p0, w), v_scl(p1, h.u)), v_scl(p2, h.v));
+}
+
+// ------------------------------------------------------------------------------------------------
+// kdtree::knearest (kdtree.h:87-107,180-195), quirks included.  The max-heap reproduces libstdc++'s
+// make_heap / pop_heap / push_heap / sort_heap element moves so that ties end in the same order.
+// hd/hi: this thread's heap arrays (distance, node index), element j at hd[j*hs].
+// ------------------------------------------------------------------------------------------------
+struct KdHeap {
+  float* hd;
+  int* hi;
+  int hs;  // stride between consecutive heap elements
+  RT_DI float d(int j) const { return hd[j * hs]; }
+  RT_DI int i(int j) const { return hi[j * hs]; }
+  RT_DI void set(int j, float dd, int ii) {
+    hd[j * hs] = dd;
+    hi[j * hs] = ii;
+  }
+  RT_DI void move(int dst, int src) { set(dst, d(src), i(src)); }
+  // std::__push_heap
+  RT_DI void push_up(int hole, int top, float vd, int vi) {
+    int parent = (hole - 1) / 2;
+    while (hole > top && d(parent) < vd) {
+      move(hole, parent);
+      hole = parent;
+      parent = (hole - 1) / 2;
+    }
+    set(hole, vd, vi);
+  }
+  // std::__adjust_heap
+  RT_DI void adjust(int hole, int len, float vd, int vi) {
+    const int top = hole;
+    int second = hole;
+    while (second < (len - 1) / 2) {
+      second = 2 * (second + 1);
+      if (d(second) < d(second - 1)) second--;
+      move(hole, second);
+      hole = second;
+    }
+    if ((len & 1) == 0 && second == (len - 2) / 2) {
+      second = 2 * (second + 1);
+      move(hole, second - 1);
+      hole = second - 1;
+    }
+    push_up(hole, top, vd, vi);
+  }
+  // std::make_heap over [0,len)
+  RT_DI void make(int len) {
+    if (len < 2) return;
+    for (int parent = (len - 2) / 2;; parent--) {
+      float vd = d(parent);
+      int vi = i(parent);
+      adjust(parent, len, vd, vi);
+      if (parent == 0) return;
+    }
+  }
+  // std::pop_heap over [0,len): max goes to len-1
+  RT_DI void pop(int len) {
+    if (len > 1) {
+      float vd = d(len - 1);
+      int vi = i(len - 1);
+      move(len - 1, 0);
+      adjust(0, len - 1, vd, vi);
+    }
+  }
+  // std::sort_heap over [0,len)
+  RT_DI void sort(int len) {
+    while (len > 1) {
+      pop(len);
+      len--;
+    }
+  }
+};
+
+// Fills heap (sorted ascending on return).  kd_stack: this thread's frames, 3 ints per frame at
+// stride ks: begin, end|axis<<30 packed?  -> we keep (begin, end, dx bits) and recompute the axis from depth.
+RT_DI void kd_knearest(const DScene& S, float3 q, int k, KdHeap& H, int* kst, int ks, unsigned long long& visits) {
+  for (int j = 0; j < k; j++) H.set(j, v_dist(f3(__ldg(S.kd_pos + j)), q), j);  // kdtree.h:186
+  H.make(k);
+  float best = H.d(0);  // m_bestdist (a distance, not squared)
+  // explicit recursion: frame = (far_begin, far_end, dx, axis_of_children)
+  int sp = 0;
+  int b = 0, e = S.kd_count, axis = 0;
+  for (;;) {
+    // descend along the near side
+    while (e > b) {
+      int n = b + (e - b) / 2;
+      visits++;
+      float4 p = __ldg(S.kd_pos + n);
+      float dnode = v_dist(f3(p), q);
+      if (dnode < best) {
+        H.pop(k);
+        best = H.d(0);  // distance of the heap's new top BEFORE the insertion (kdtree.h:93-96)
+        H.set(k - 1, dnode, n);
+        H.push_up(k - 1, 0, dnode, n);
+      }
+      if (best == 0.f) {
+        b = e;  // kdtree.h:101: return without visiting children
+        break;
+      }
+      float pa = axis == 0 ? p.x : (axis == 1 ? p.y : p.z);
+      float qa = axis == 0 ? q.x : (axis == 1 ? q.y : q.z);
+      float dx = __fsub_rn(pa, qa);
+      int nb, ne, fb, fe;
+      if (dx > 0.f) {
+        nb = b;
+        ne = n;
+        fb = n + 1;
+        fe = e;
+      } else {
+        nb = n + 1;
+        ne = e;
+        fb = b;
+        fe = n;
+      }
+      axis = axis == 2 ? 0 : axis + 1;
+      kst[(3 * sp) * ks] = fb;
+      kst[(3 * sp + 1) * ks] = fe | (axis << 28);
+      kst[(3 * sp + 2) * ks] = __float_as_int(dx);
+      sp++;
+      b = nb;
+      e = ne;
+    }
+    // unwind: first frame whose far side survives `dx*dx >= m_bestdist` (kdtree.h:105, squared vs not)
+    bool resumed = false;
+    while (sp > 0) {
+      sp--;
+      float dx = __int_as_float(kst[(3 * sp + 2) * ks]);
+      double dx2 = __dmul_rn((double)dx, (double)dx);
+      if (dx2 >= (double)best) continue;
+      int fe = kst[(3 * sp + 1) * ks];
+      b = kst[(3 * sp) * ks];
+      axis = (fe >> 28) & 3;
+      e = fe & 0x0fffffff;
+      resumed = true;
+      break;
+    }
+    if (!resumed) break;
+  }
+  H.sort(k);
+}
+
+}  // namespace rtb

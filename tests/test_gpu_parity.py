@@ -1,0 +1,318 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the committed golden vectors of the
+unmodified reference and against the CPU oracle on the same seeded inputs.
+
+Bars (BASELINE.json north_star):
+  * nearest-hit triangle ids (and u, v, t) bit-exact for the same rays;
+  * -m 0 images within 1/255 per pixel on >= 99.9 % of the pixels (we observe bit-identical);
+  * transcendental-dependent paths (-m 1 bounces, photon emission): per-sample agreement rate and an
+    RMSE bound, stated in each test.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import scene_path
+
+pytestmark = pytest.mark.gpu
+
+SEED = 1
+
+
+def beq(a, b):
+    a, b = np.ascontiguousarray(a, np.float32), np.ascontiguousarray(b, np.float32)
+    return a.shape == b.shape and bool((a.view(np.uint32) == b.view(np.uint32)).all())
+
+
+@pytest.fixture(scope="module")
+def rt():
+    import ray_tracing_engine_b200 as m
+    if m.device_count() < 1:
+        pytest.fail("no CUDA device: the -m gpu tests need the B200 (there is no CPU fallback)")
+    return m
+
+
+@pytest.fixture(scope="module")
+def O():
+    from oracle import oracle
+    return oracle
+
+
+def make_renderer(rt, name, N=1, mode=0, **kw):
+    scene = rt.Scene.load(scene_path(name))
+    return rt.Renderer(scene, N, mode, seed=SEED, **kw)
+
+
+# ----------------------------------------------------------------------------- nearest hit: bit exact
+@pytest.mark.parametrize("name", ["stock", "lowres", "example"])
+def test_trace_matches_reference_golden(rt, gold, name):
+    g = gold(f"trace_{name}.npz")
+    r = make_renderer(rt, name)
+    for brute in (False, True):
+        h = r.rayTrace(g["rays"], brute_force=brute)
+        assert (h["hit"] == g["hit"]).all(), f"hit flags differ (brute={brute})"
+        assert (h["mesh"] == g["mesh"]).all()
+        assert (h["tri3"] == g["tri3"]).all(), "vertex triple differs from RayTracer::rayTrace"
+        assert beq(h["uvd"], g["uvd"]), "u, v, d are not bit-identical"
+    occ = r.occluded(g["rays"])
+    assert (occ == g["hit"]).all(), "any-hit disagrees with `rayTrace(...) == true`"
+
+
+def test_trace_bvh_equals_bruteforce_at_scale(rt):
+    """Size-independent property: BVH traversal returns exactly what the O(T) scan returns
+    (2M rays on the 11 666-triangle scene, including rays that start on surfaces)."""
+    r = make_renderer(rt, "example")
+    g = np.random.default_rng(5)
+    n = 1_000_000
+    o = g.uniform(-1.5, 1.5, (n, 3)).astype(np.float32)
+    o[: n // 2] *= 0.3  # concentrate half of the origins inside the mesh's bounding box
+    d = g.normal(size=(n, 3)).astype(np.float32)
+    rays = np.concatenate([o, d], 1)
+    a = r.rayTrace(rays)
+    # second generation: rays leaving the hit points (t ~ 0 self-intersections matter here)
+    ok = a["hit"] == 1
+    p = (o + d * a["uvd"][:, 2:3])[ok]
+    rays2 = np.concatenate([p, g.normal(size=p.shape).astype(np.float32)], 1)
+    for batch in (rays, rays2):
+        x, y = r.rayTrace(batch), r.rayTrace(batch, brute_force=True)
+        assert (x["tri_index"] == y["tri_index"]).all()
+        assert beq(x["uvd"], y["uvd"])
+        assert (r.occluded(batch) == r.occluded(batch, brute_force=True)).all()
+
+
+def test_trace_edge_cases(rt):
+    r = make_renderer(rt, "stock")
+    rays = np.zeros((5, 6), np.float32)
+    rays[0] = [0, 0, 0, 0, 0, 0]                    # zero direction
+    rays[1] = [0, 0, 0, np.nan, 0, 1]               # NaN direction (asin(>1) case of hsphereUniformSample)
+    rays[2] = [0, 0, 5, 0, 0, 1]                    # pointing away from everything
+    rays[3] = [0, -1, 0, 0, 1, 0]                   # starting exactly on the floor
+    rays[4] = [0, 0, 0, 0, -1e-30, 0]               # denormal-scale direction
+    a, b = r.rayTrace(rays), r.rayTrace(rays, brute_force=True)
+    assert (a["tri_index"] == b["tri_index"]).all() and beq(a["uvd"], b["uvd"])
+    assert a["hit"][0] == 0 and a["hit"][1] == 0 and a["hit"][2] == 0
+    assert len(r.rayTrace(np.zeros((0, 6), np.float32))["hit"]) == 0
+
+
+# ----------------------------------------------------------------------------- shading pieces
+def test_bsdf_matches_reference_golden(rt, gold):
+    g = gold("bsdf.npz")
+    r = make_renderer(rt, "stock")
+    for m in range(5):
+        out = r.evaluateColorResponse(g["mats"][m], g["inputs"])
+        want = g[f"bsdf_{m}"]
+        nan = np.isnan(want)
+        assert (np.isnan(out) == nan).all()
+        # tolerance stated by SURVEY.md 8a-B: 1e-5 relative; observed: bit-identical
+        np.testing.assert_allclose(out[~nan], want[~nan], rtol=1e-5, atol=1e-30)
+        frac_exact = (out[~nan].view(np.uint32) == want[~nan].view(np.uint32)).mean()
+        assert frac_exact > 0.999, frac_exact
+
+
+# ----------------------------------------------------------------------------- -m 0 images
+def test_render_m0_stock_matches_reference_image(rt, gold):
+    g = gold("render_stock_m0_N1.npz")
+    r = make_renderer(rt, "stock", N=1, mode=0)
+    s, c = r.render_accumulate()
+    assert (c == g["counter"]).all()
+    img = r.render(rt.Image(420, 420).fillBackground())
+    d = np.abs(img.to8().astype(int) - g["image8"].astype(int)).max(axis=-1)
+    assert (d <= 1).mean() >= 0.999, f"only {(d <= 1).mean():.5f} of the pixels within 1/255"
+    # what we actually observe: the accumulators are bit-identical to the reference's
+    assert beq(s, g["sum_rgb"]), f"{(s != g['sum_rgb']).any(axis=-1).sum()} pixels differ"
+    st = r.stats()
+    assert st["primary_rays"] >= 176400 and st["shadow_rays"] == 3 * int(c.sum())
+
+
+def test_render_m0_lowres_window(rt, gold):
+    g = gold("render_lowres_m0_N1_win.npz")
+    r = make_renderer(rt, "lowres", N=1, mode=0)
+    rgb, found = r.render_samples(window=tuple(g["window"]))
+    assert (found == g["found"]).all()
+    assert beq(rgb, g["samples"])
+
+
+def test_render_m0_example_full_image(rt, gold):
+    path = os.path.join(os.path.dirname(__file__), "golden", "render_example_m0_N1.npz")
+    if not os.path.exists(path):
+        pytest.skip("heavy golden not generated")
+    g = gold("render_example_m0_N1.npz")
+    r = make_renderer(rt, "example", N=1, mode=0)
+    img = r.render(rt.Image(420, 420).fillBackground())
+    d = np.abs(img.to8().astype(int) - g["image8"].astype(int)).max(axis=-1)
+    assert (d <= 1).mean() >= 0.999
+    assert (d == 0).mean() >= 0.999
+
+
+# ----------------------------------------------------------------------------- -m 1 (transcendental bounce)
+def _sample_agreement(rgb, want):
+    return float((np.abs(rgb - want).max(axis=-1) <= 1e-6).mean())
+
+
+@pytest.mark.parametrize("case,name,N", [("stock_m1_N4_win", "stock", 4), ("lowres_m1_N2_win", "lowres", 2),
+                                         ("example_m1_N2_win", "example", 2)])
+def test_render_m1_windows(rt, gold, case, name, N):
+    path = os.path.join(os.path.dirname(__file__), "golden", f"render_{case}.npz")
+    if not os.path.exists(path):
+        pytest.skip("heavy golden not generated")
+    g = gold(f"render_{case}.npz")
+    r = make_renderer(rt, name, N=N, mode=1)
+    rgb, found = r.render_samples(window=tuple(g["window"]))
+    assert (found == g["found"]).all(), "primary hits are transcendental-free and must match exactly"
+    # bounce directions go through asin/sin/cos: a last-bit difference there can flip a t~1e-7 shadow
+    # decision, so we require >= 97 % of the samples identical and a small mean difference.
+    frac = _sample_agreement(rgb, g["samples"])
+    assert frac >= 0.97, frac
+    assert abs(float(rgb.mean()) - float(g["samples"].mean())) < 5e-3
+
+
+def test_render_m1_stock_N128_converged_mean(rt, gold):
+    """BASELINE cfg 2 on the stock scene: the 420x420 N=128 path trace against the reference's own
+    N=128 render with the same random streams.  RMSE bound: the reference's sample standard deviation
+    is ~0.25 per channel, so two INDEPENDENT N=128 renders differ by RMSE ~ 0.25*sqrt(2/128) = 0.031;
+    sharing the streams we require 10x better than that."""
+    path = os.path.join(os.path.dirname(__file__), "golden", "render_stock_m1_N128.npz")
+    if not os.path.exists(path):
+        pytest.skip("heavy golden not generated")
+    g = gold("render_stock_m1_N128.npz")
+    r = make_renderer(rt, "stock", N=128, mode=1)
+    s, c = r.render_accumulate()
+    assert (c == g["counter"]).all()
+    rmse = float(np.sqrt(np.mean((s / 128.0 - g["sum_rgb"] / 128.0) ** 2)))
+    assert rmse < 3.1e-3, rmse
+    assert abs(float(s.mean()) - float(g["sum_rgb"].mean())) / 128.0 < 1e-3
+
+
+def test_render_matches_port_oracle_other_seed_and_size(rt, O):
+    """Live comparison against the CPU restatement on inputs no golden file holds."""
+    flat = O.FlatScene.load(scene_path("stock"))
+    flat.w, flat.h = 96, 64  # camera stays the aspect-1 one: both sides use the same 4 vectors
+    port = O.PortOracle(flat)
+    scene = rt.Scene.load(scene_path("stock"))
+    for mode, N in ((0, 3), (1, 5)):
+        want = port.render(N, mode, 99, want_samples=True)
+        r = rt.Renderer(scene, N, mode, seed=99, width=96, height=64)
+        rgb, found = r.render_samples()
+        assert (found == want["found"]).all()
+        if mode == 0:
+            assert beq(rgb, want["samples"])
+        else:
+            assert _sample_agreement(rgb, want["samples"]) >= 0.97
+        s, c = r.render_accumulate()
+        assert (c == want["counter"]).all()
+        if mode == 0:
+            assert beq(s, want["sum_rgb"])
+        st, pc = r.stats(), port.counters(reset=True)
+        if mode == 0:
+            assert st["rays"] == 2 * pc["rays"]  # render_samples + render_accumulate traced the same work twice
+
+
+# ----------------------------------------------------------------------------- photon map
+def test_kdtree_and_knn_match_reference(rt, gold):
+    g = gold("photons.npz")
+    r = make_renderer(rt, "stock")
+    r.set(num_photons=3000, k=10)
+    r.set_photons(g["list"])
+    nodes, left, right, root = r.kdtree()
+    assert beq(nodes, g["nodes"]) and (left == g["left"]).all() and (right == g["right"]).all()
+    assert root == int(g["root"][0])
+    for k in (1, 5, 10, 50):
+        idx = r.knearest(g["queries"], k)
+        got = nodes[idx][:, :, :3]
+        assert beq(got, g[f"knn_{k}"]), f"k={k}: the k photons or their order differ from kdtree::knearest"
+
+
+def test_knn_errors(rt, gold):
+    g = gold("photons.npz")
+    r = make_renderer(rt, "stock")
+    with pytest.raises(rt.RtError) as e:
+        r.knearest(np.zeros((1, 3), np.float32), 3)
+    assert e.value.code == -4  # tree is empty (kdtree.h:181)
+    r.set_photons(g["list"][:5])
+    with pytest.raises(rt.RtError) as e:
+        r.knearest(np.zeros((1, 3), np.float32), 6)
+    assert e.value.code == -5  # k is greater than the number of nodes (kdtree.h:182-183)
+
+
+def test_photon_emission_against_oracle(rt, O, gold):
+    """Emission goes through asin/sin/cos at every bounce: statistical parity by contract.  We check
+    the stored count and the depth histogram against the reference (within 4 sigma per bin) and
+    that the large majority of paths are bit-identical."""
+    g = gold("photons.npz")
+    r = make_renderer(rt, "stock")
+    r.set(num_photons=3000, k=10)
+    plist, counts, hist = r.emit_photons()
+    want = g["list"]
+    assert abs(len(plist) - len(want)) <= 4 * np.sqrt(len(want))
+    assert (np.abs(hist - g["hist"]) <= 4 * np.sqrt(np.maximum(g["hist"], 1)) + 2).all()
+    same = {tuple(p) for p in want.view(np.uint32).reshape(len(want), 7).tolist()}
+    got = sum(tuple(p) in same for p in plist.view(np.uint32).reshape(len(plist), 7).tolist())
+    assert got / len(want) > 0.85, got / len(want)
+    # sharded emission concatenates to the single-process list (the multi-GPU contract)
+    per = r.photons_per_light()
+    a, ca, _ = r.emit_photons(0, per // 2)
+    b, cb, _ = r.emit_photons(per // 2, per - per // 2)
+    parts, oa, ob = [], 0, 0
+    for l in range(3):
+        parts += [a[oa:oa + ca[l]], b[ob:ob + cb[l]]]
+        oa += ca[l]
+        ob += cb[l]
+    assert beq(np.concatenate(parts), plist)
+    r.set(num_photons=50000)
+    plist50, _, hist50 = r.emit_photons()
+    assert abs(len(plist50) - int(g["count_50000"][0])) <= 4 * np.sqrt(len(plist50))
+    assert (np.abs(hist50 - g["hist_50000"]) <= 4 * np.sqrt(np.maximum(g["hist_50000"], 1)) + 2).all()
+
+
+@pytest.mark.parametrize("case,N,mode,k", [("stock_m0_p3000_k10_win", 1, 0, 10), ("stock_m1_p3000_k5_N2_win", 2, 1, 5)])
+def test_photon_render_on_shared_list(rt, gold, case, N, mode, k):
+    """Gather parity is tested on a SHARED photon list (the reference's own), SURVEY.md section 7."""
+    g, ph = gold(f"render_{case}.npz"), gold("photons.npz")
+    r = make_renderer(rt, "stock", N=N, mode=mode)
+    r.set(num_photons=3000, k=k)
+    r.set_photons(ph["list"])
+    rgb, found = r.render_samples(window=tuple(g["window"]))
+    assert (found == g["found"]).all()
+    if mode == 0:
+        frac = (rgb.view(np.uint32) == g["samples"].view(np.uint32)).all(axis=-1).mean()
+        assert frac >= 0.999, frac
+    else:
+        assert _sample_agreement(rgb, g["samples"]) >= 0.97
+
+
+def test_photon_render_full_pipeline_cfg4_like(rt, gold):
+    """-m 0 -p 50000 -k 10 on the stock scene, photons emitted on the GPU: per-pixel comparison with
+    the reference image is statistical here (different photons where a transcendental bit differs)."""
+    path = os.path.join(os.path.dirname(__file__), "golden", "render_stock_m0_p50000_k10_N1.npz")
+    if not os.path.exists(path):
+        pytest.skip("heavy golden not generated")
+    g = gold("render_stock_m0_p50000_k10_N1.npz")
+    r = make_renderer(rt, "stock", N=1, mode=0)
+    r.set(num_photons=50000, k=10)
+    img = r.render(rt.Image(420, 420).fillBackground())
+    a, b = img.to8().astype(float) / 255, g["image8"].astype(float) / 255
+    assert abs(a.mean() - b.mean()) < 0.01
+    assert np.sqrt(np.mean((a - b) ** 2)) < 0.08
+    assert r.stats()["knn_queries"] == int((g["counter"] > 0).sum())
+
+
+# ----------------------------------------------------------------------------- sharding
+def test_tile_sharding_is_exact(rt):
+    scene = rt.Scene.load(scene_path("stock"))
+    full = rt.Renderer(scene, 3, 1, seed=4, width=100, height=70)
+    s, c = full.render_accumulate()
+    acc_s, acc_c = np.zeros_like(s), np.zeros_like(c)
+    for rank in range(3):
+        part = rt.Renderer(scene, 3, 1, seed=4, width=100, height=70, shard_rank=rank, shard_count=3)
+        ps, pc = part.render_accumulate()
+        assert not ((ps != 0).any(axis=-1) & (acc_s != 0).any(axis=-1)).any(), "shards overlap"
+        acc_s += ps
+        acc_c += pc
+    assert beq(acc_s, s) and (acc_c == c).all(), "sum over shards must be bit-identical to the 1-GPU frame"
+
+
+def test_batching_does_not_change_the_result(rt):
+    scene = rt.Scene.load(scene_path("stock"))
+    a = rt.Renderer(scene, 7, 1, seed=2, width=64, height=64).render_accumulate()
+    b = rt.Renderer(scene, 7, 1, seed=2, width=64, height=64, samples_per_batch=2).render_accumulate()
+    assert beq(a[0], b[0]) and (a[1] == b[1]).all()
