@@ -115,13 +115,13 @@ def test_render_m0_stock_matches_reference_image(rt, gold):
     r = make_renderer(rt, "stock", N=1, mode=0)
     s, c = r.render_accumulate()
     assert (c == g["counter"]).all()
+    st = r.stats()
+    assert st["primary_rays"] == 176400 and st["shadow_rays"] == 3 * int(c.sum()) and st["rays"] == 705600
     img = r.render(rt.Image(420, 420).fillBackground())
     d = np.abs(img.to8().astype(int) - g["image8"].astype(int)).max(axis=-1)
     assert (d <= 1).mean() >= 0.999, f"only {(d <= 1).mean():.5f} of the pixels within 1/255"
     # what we actually observe: the accumulators are bit-identical to the reference's
     assert beq(s, g["sum_rgb"]), f"{(s != g['sum_rgb']).any(axis=-1).sum()} pixels differ"
-    st = r.stats()
-    assert st["primary_rays"] >= 176400 and st["shadow_rays"] == 3 * int(c.sum())
 
 
 def test_render_m0_lowres_window(rt, gold):
