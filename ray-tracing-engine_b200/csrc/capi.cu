@@ -79,6 +79,9 @@ struct rt_ctx {
   int npix = 0;
   int pix_w = -1, pix_h = -1, pix_rank = -1, pix_count = -1, pix_tile = -1;
   DevBuf<float4> d_col0, d_col1, d_qo0, d_qo1, d_qd0, d_qd1, d_acc;
+  DevBuf<float4> d_hit, d_sh_o, d_sh_d, d_contrib;
+  DevBuf<unsigned char> d_occ;
+  DevBuf<int> d_hit_path;
   DevBuf<int> d_acc_cnt, d_out_cnt;
   DevBuf<float> d_out_rgb;
   DevBuf<unsigned int> d_qcount;
@@ -139,16 +142,26 @@ int ensure_pix_map(rt_ctx* c) {
   return RT_OK;
 }
 
+// bytes of wavefront state per path slot (ensure_work below)
+constexpr size_t kBytesPerPath = 16 * 2 + 32 * 2 + 16 + 3 * (32 + 16 + 1) + 4;
+
 int ensure_work(rt_ctx* c, size_t paths, bool path_mode) {
+  const size_t shadow = shadow_slots_for((unsigned)paths);
   CU(c->d_col0.ensure(paths));
+  CU(c->d_qo0.ensure(paths));
+  CU(c->d_qd0.ensure(paths));
+  CU(c->d_hit.ensure(paths));
+  CU(c->d_hit_path.ensure(paths));
+  CU(c->d_sh_o.ensure(shadow));
+  CU(c->d_sh_d.ensure(shadow));
+  CU(c->d_contrib.ensure(shadow));
+  CU(c->d_occ.ensure(shadow));
   if (path_mode) {
     CU(c->d_col1.ensure(paths));
-    CU(c->d_qo0.ensure(paths));
-    CU(c->d_qd0.ensure(paths));
     CU(c->d_qo1.ensure(paths));
     CU(c->d_qd1.ensure(paths));
   }
-  CU(c->d_qcount.ensure(4));
+  CU(c->d_qcount.ensure(kQNum));
   CU(c->d_counters.ensure(kCntNum));
   return RT_OK;
 }
@@ -184,12 +197,19 @@ void fill_args(rt_ctx* c, RenderArgs& a, const int* pix_map, int npix, bool use_
   a.seed_mixed = mix64(p.seed + kGolden);
   a.pix_map = pix_map;
   a.npix = npix;
+  a.stack_depth = std::max(c->bvh.depth, 1);
   a.col0 = c->d_col0.p;
   a.col1 = c->d_col1.p;
-  a.q_o[0] = c->d_qo0.p;
-  a.q_o[1] = c->d_qo1.p;
-  a.q_d[0] = c->d_qd0.p;
-  a.q_d[1] = c->d_qd1.p;
+  a.ray_o[0] = c->d_qo0.p;
+  a.ray_o[1] = c->d_qo1.p;
+  a.ray_d[0] = c->d_qd0.p;
+  a.ray_d[1] = c->d_qd1.p;
+  a.hit = c->d_hit.p;
+  a.sh_o = c->d_sh_o.p;
+  a.sh_d = c->d_sh_d.p;
+  a.contrib = c->d_contrib.p;
+  a.occ = c->d_occ.p;
+  a.hit_path = c->d_hit_path.p;
   a.q_count = c->d_qcount.p;
   a.counters = c->d_counters.p;
 }
@@ -198,21 +218,38 @@ void fill_args(rt_ctx* c, RenderArgs& a, const int* pix_map, int npix, bool use_
 int run_batch(rt_ctx* c, RenderArgs& a, int s0, int nsamp) {
   a.s0 = s0;
   a.nsamp = nsamp;
-  const int ctas = c->num_sms * segment_ctas_per_sm(a.mode, a.photon);
   const long long paths = (long long)a.npix * nsamp;
-  int grid0 = (int)std::min<long long>((paths + kBlock - 1) / kBlock, (long long)ctas);
-  if (grid0 < 1) grid0 = 1;
-  CU(cudaMemsetAsync(c->d_qcount.p, 0, 4 * sizeof(unsigned), c->stream));
-  const int nseg = a.mode == 1 ? 3 : 1;
-  for (int seg = 0; seg < nseg; seg++) {
-    while (c->seg_events.size() < c->seg_events_used + 2) {
+  const int persistent = c->num_sms * trace_ctas_per_sm(a.stack_depth);
+  int grid = (int)std::min<long long>((paths + kBlock - 1) / kBlock, (long long)persistent);
+  if (grid < 1) grid = 1;
+  const int grid_shade = (int)std::min<long long>((paths + kBlock - 1) / kBlock, (long long)c->num_sms * 8);
+  CU(cudaMemsetAsync(c->d_qcount.p, 0, kQNum * sizeof(unsigned), c->stream));
+  auto mark = [&]() -> int {
+    while (c->seg_events.size() < c->seg_events_used + 1) {
       cudaEvent_t e;
       CU(cudaEventCreate(&e));
       c->seg_events.push_back(e);
     }
     CU(cudaEventRecord(c->seg_events[c->seg_events_used++], c->stream));
-    launch_segment(a, seg, grid0, c->stream);
-    CU(cudaEventRecord(c->seg_events[c->seg_events_used++], c->stream));
+    return RT_OK;
+  };
+  int rc;
+  launch_raygen(a, c->stream);
+  c->stats.kernel_launches++;
+  const int nseg = a.mode == 1 ? 3 : 1;
+  for (int seg = 0; seg < nseg; seg++) {
+    if ((rc = mark())) return rc;
+    launch_trace_nearest(a, seg, grid, c->stream);
+    if ((rc = mark())) return rc;
+    launch_shade(a, seg, std::max(grid_shade, 1), c->stream);
+    c->stats.kernel_launches += 2;
+    if (!a.photon) {
+      if ((rc = mark())) return rc;
+      launch_trace_any(a, seg, grid, c->stream);
+      if ((rc = mark())) return rc;
+      c->stats.kernel_launches++;
+    }
+    launch_combine(a, seg, std::max(grid_shade, 1), c->stream);
     c->stats.kernel_launches++;
   }
   CU(cudaGetLastError());
@@ -265,13 +302,13 @@ int render_to_device(rt_ctx* c, float* out_rgb_dev, int* out_cnt_dev) {
   const rt_params& p = c->params;
   const size_t npx = (size_t)p.width * p.height;
   const bool path_mode = p.mode == 1;
-  // batch size: bounded by free HBM (96 B per path in path mode) and by 2^31 paths
+  // batch size: bounded by free HBM (kBytesPerPath of wavefront state per path) and by 2^30 paths
   int spb = p.samples_per_batch;
   if (spb <= 0) {
     size_t free_b = 0, total_b = 0;
     CU(cudaMemGetInfo(&free_b, &total_b));
     size_t budget = std::min<size_t>(free_b / 2, (size_t)24 << 30);
-    size_t max_paths = std::min<size_t>(budget / 96, (size_t)1 << 30);
+    size_t max_paths = std::min<size_t>(budget / kBytesPerPath, (size_t)1 << 30);
     spb = (int)std::max<size_t>(1, std::min<size_t>(max_paths / std::max(c->npix, 1), 1 << 20));
   }
   const int samp_first = p.sample_first;
@@ -348,6 +385,12 @@ int rt_destroy(rt_ctx* c) {
   c->d_col1.release();
   c->d_qo0.release();
   c->d_qo1.release();
+  c->d_hit.release();
+  c->d_sh_o.release();
+  c->d_sh_d.release();
+  c->d_contrib.release();
+  c->d_occ.release();
+  c->d_hit_path.release();
   c->d_qd0.release();
   c->d_qd1.release();
   c->d_acc.release();
@@ -380,7 +423,8 @@ int rt_create(const rt_scene* s, const rt_params* p, int device, rt_ctx** out) {
   if (rc) return rc;
   if (s->num_vertices < 0 || s->num_triangles < 0 || s->num_meshes < 0 || s->num_lights < 0)
     return fail(RT_ERR_INVALID, "negative scene counts");
-  if (s->num_lights > kMaxLights) return fail(RT_ERR_INVALID, "too many lights (max 8)");
+  if (s->num_lights > kShadowLights)
+    return fail(RT_ERR_INVALID, "more than 3 light sources are not supported by the shadow-ray queue layout");
   if (s->num_triangles > 0 && (!s->positions || !s->normals || !s->triangles || !s->mesh_first_triangle ||
                                !s->mesh_first_vertex || !s->materials))
     return fail(RT_ERR_INVALID, "null scene arrays");
@@ -425,6 +469,10 @@ int rt_create(const rt_scene* s, const rt_params* p, int device, rt_ctx** out) {
   for (int l = 0; l < c->L; l++)
     for (int a = 0; a < 3; a++) extent = std::max(extent, std::fabs(s->lights[l].position[a]) + s->lights[l].side);
   for (int a = 0; a < 3; a++) extent = std::max(extent, std::fabs(s->camera.position[a]));
+  if (!(extent < 1e8f)) {  // keeps lo * safe_inv(d) finite in the slab test (rt_device.cuh)
+    rt_destroy(c);
+    return fail(RT_ERR_INVALID, "scene coordinates must be finite and smaller than 1e8");
+  }
   float pad_fraction = p->bvh_pad > 0.f ? p->bvh_pad : 1.0f / 16384.0f;
   build_bvh(c->V, s->positions, c->T, s->triangles, c->M, s->mesh_first_triangle, extent, pad_fraction, c->bvh);
   if (c->bvh.depth > kStackDepth) {
@@ -613,19 +661,30 @@ static int trace_common(rt_ctx* c, const rt_ray* rays, int64_t n, rt_hit* hits, 
   int rc = bind(c);
   if (rc) return rc;
   if (n < 0 || (n > 0 && !rays)) return fail(RT_ERR_INVALID, "bad ray batch");
+  if (n >= ((int64_t)1 << 31)) return fail(RT_ERR_INVALID, "too many rays in one call");
   if (n == 0) return RT_OK;
-  DevBuf<float> d_rays, d_uvt;
-  DevBuf<int> d_tri;
+  std::vector<float4> ho((size_t)n), hd((size_t)n);
+  for (int64_t i = 0; i < n; i++) {
+    ho[i] = make_float4(rays[i].origin[0], rays[i].origin[1], rays[i].origin[2], 0.f);
+    hd[i] = make_float4(rays[i].direction[0], rays[i].direction[1], rays[i].direction[2], 0.f);
+  }
+  DevBuf<float4> d_o, d_d, d_h;
   DevBuf<unsigned char> d_occ;
   int ret = RT_OK;
-  cudaError_t e = d_rays.ensure(6 * (size_t)n);
-  if (e == cudaSuccess) e = d_uvt.ensure(3 * (size_t)n);
-  if (e == cudaSuccess) e = d_tri.ensure((size_t)n);
+  cudaError_t e = d_o.ensure((size_t)n);
+  if (e == cudaSuccess) e = d_d.ensure((size_t)n);
+  if (e == cudaSuccess) e = d_h.ensure((size_t)n);
   if (e == cudaSuccess) e = d_occ.ensure((size_t)n);
-  if (e == cudaSuccess) e = cudaMemcpy(d_rays.p, rays, sizeof(rt_ray) * (size_t)n, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = c->d_qcount.ensure(kQNum);
+  if (e == cudaSuccess) e = cudaMemcpy(d_o.p, ho.data(), sizeof(float4) * (size_t)n, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(d_d.p, hd.data(), sizeof(float4) * (size_t)n, cudaMemcpyHostToDevice);
   if (e == cudaSuccess) {
-    launch_trace_rays(c->scene, d_rays.p, n, d_tri.p, d_uvt.p, (flags & RT_FLAG_BRUTE_FORCE) ? 1 : 0, occluded ? 1 : 0,
-                      d_occ.p, c->stream);
+    const int depth = std::max(c->bvh.depth, 1);
+    const int persistent = c->num_sms * trace_ctas_per_sm(depth);
+    int grid = (int)std::min<int64_t>((n + kBlock - 1) / kBlock, persistent);
+    launch_trace_rays(c->scene, d_o.p, d_d.p, (unsigned)n, d_h.p, d_occ.p, occluded ? 1 : 0,
+                      (flags & RT_FLAG_BRUTE_FORCE) ? 1 : 0, depth, c->d_qcount.p + kQFetchNearest0, std::max(grid, 1),
+                      c->stream);
     c->stats.kernel_launches++;
     e = cudaStreamSynchronize(c->stream);
   }
@@ -633,18 +692,19 @@ static int trace_common(rt_ctx* c, const rt_ray* rays, int64_t n, rt_hit* hits, 
     if (occluded) {
       e = cudaMemcpy(occluded, d_occ.p, (size_t)n, cudaMemcpyDeviceToHost);
     } else {
-      std::vector<int> tri((size_t)n);
-      std::vector<float> uvt(3 * (size_t)n);
-      e = cudaMemcpy(tri.data(), d_tri.p, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost);
-      if (e == cudaSuccess) e = cudaMemcpy(uvt.data(), d_uvt.p, sizeof(float) * 3 * (size_t)n, cudaMemcpyDeviceToHost);
-      for (int64_t i = 0; i < n && e == cudaSuccess; i++)
-        hits[i] = rt_hit{tri[i], uvt[3 * i], uvt[3 * i + 1], uvt[3 * i + 2]};
+      std::vector<float4> hh((size_t)n);
+      e = cudaMemcpy(hh.data(), d_h.p, sizeof(float4) * (size_t)n, cudaMemcpyDeviceToHost);
+      for (int64_t i = 0; i < n && e == cudaSuccess; i++) {
+        int tri;
+        std::memcpy(&tri, &hh[i].w, 4);
+        hits[i] = tri >= 0 ? rt_hit{tri, hh[i].y, hh[i].z, hh[i].x} : rt_hit{-1, 0.f, 0.f, 0.f};
+      }
     }
   }
   if (e != cudaSuccess) ret = fail(RT_ERR_CUDA, cudaGetErrorString(e));
-  d_rays.release();
-  d_uvt.release();
-  d_tri.release();
+  d_o.release();
+  d_d.release();
+  d_h.release();
   d_occ.release();
   return ret;
 }

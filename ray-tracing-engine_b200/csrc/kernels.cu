@@ -1,46 +1,252 @@
-// kernels.cu -- the sm_100a kernels of the render hot path.
+// kernels.cu -- the sm_100a kernels of the render hot path (wavefront formulation).
 //
-//   k_segment<MODE,PHOTON>  one path segment of the wavefront: (seg 0: jitter + camera ray) ->
-//                           nearest-hit BVH traversal -> shade (3 any-hit shadow rays + microfacet BSDF,
-//                           or k-nearest-photon gather) -> bounce sample -> compacted ray queue
-//                           replaces Renderer.cpp:106-201,33-104 / RayTracer.h:27-53,95-117
-//   k_resolve / k_scatter   ordered per-pixel accumulation of the clamped samples (Renderer.cpp:254-258)
-//   k_emit                  photon emission + Russian-roulette random walk (PhotonMap.h:14-50,92-155)
-//   k_trace / k_knn / k_bsdf parity hooks over caller-supplied batches
+// Per batch of paths (nsamp samples x npix pixels) and per path segment s = 0..2:
+//
+//   k_raygen            (s = 0) jitter + camera ray                     Renderer.cpp:229-234
+//   k_trace<NEAREST>    persistent nearest-hit BVH traversal            RayTracer.h:27-53, Ray.cpp:9-24
+//   k_shade<MODE,PHOT>  hit point/normal, 3 area-light samples -> 3 shadow rays + their BSDF*radiance,
+//                       hemisphere bounce -> next ray queue (compacted); or the k-nearest-photon gather
+//                                                                        Renderer.cpp:33-104,143-170
+//   k_trace<ANY>        persistent any-hit traversal of the shadow rays Renderer.cpp:52-55
+//   k_combine           ordered sum of the unoccluded light terms, per-sample clamp on the last segment
+//                                                                        Renderer.cpp:59,168,254
+//   k_resolve/k_scatter ordered accumulation over samples               Renderer.cpp:255-258
+//   k_emit              photon emission + Russian-roulette random walk  PhotonMap.h:14-50,92-155
+//
+// Why a wavefront: the first version fused a whole segment (1 nearest + 3 sequential any-hit traversals
+// + shading) into one thread; ncu showed 70 % issue-slot use but only 8.1 / 6.5 of 32 lanes active on
+// the bounce segments (profiles/r1_v1_k_segment_full.csv).  Here every ray is its own work item, a warp
+// that runs low on live rays refills its idle lanes from the queue, and the shadow rays of 32
+// neighbouring hit points towards one light share a warp.
 //
 // No tensor-core work exists on this path (nothing is a dense contraction): the kernels are
-// pointer-chasing traversals bounded by L1/L2 latency and the fp32 issue rate.
+// pointer-chasing traversals bounded by L1/L2 latency and the fp32/ALU issue rate.
+#include <limits.h>
+
 #include "kernels.h"
 
 namespace rtb {
 
-// ----------------------------------------------------------------------------------------------
-// shading helpers shared by the segment and emission kernels
-// ----------------------------------------------------------------------------------------------
-template <bool ANY>
-RT_DI bool trace(const DScene& S, float3 o, float3 d, int* stack, int brute, HitRec& h) {
-  if (brute) return brute_trace<ANY>(S, o, d, h);
-  return bvh_traverse<ANY>(S, o, d, stack, kBlock, h);
-}
+constexpr unsigned kFull = 0xffffffffu;
+constexpr int kDone = INT_MIN;    // traversal cursor value: no work (never a valid ~slot)
+constexpr int kRefillBelow = 22;  // refill a warp's idle lanes when fewer lanes than this are live
 
-// Renderer.cpp:33-61
-RT_DI float3 shade_direct(const DScene& S, float3 dir, float3 n, float3 P, const DMaterial& m, Rng& g, int* stack,
-                          int brute, unsigned& n_shadow) {
-  float3 color = f3(0.f, 0.f, 0.f);
-  const float3 wo = v_neg(dir);
-  for (int l = 0; l < S.num_lights; l++) {
-    const DLight& L = S.lights[l];
-    float3 to_light = v_sub(light_rand_area_position(L, g), P);
-    HitRec hs;
-    n_shadow++;
-    if (trace<true>(S, P, to_light, stack, brute, hs)) continue;  // any hit on (0,+inf), Renderer.cpp:52-55
-    float3 bsdf = evaluate_color_response(m, n, to_light, wo);
-    float3 radiance = light_evaluate(L, P);
-    color = v_add(color, v_mul(radiance, bsdf));
+// ----------------------------------------------------------------------------------------------
+// k_trace: persistent warps, one ray per lane, lanes refilled from the queue as their rays finish.
+// Shared memory: per thread a stack of (node ref, tnear) pairs, [depth][kBlock] ints each.
+// ----------------------------------------------------------------------------------------------
+template <bool ANY, bool BLOCKED>
+__global__ void __launch_bounds__(kBlock)
+    k_trace(const DScene S, const float4* __restrict__ ro, const float4* __restrict__ rd, const unsigned* n_ptr,
+            unsigned n_fixed, float4* __restrict__ hits, unsigned char* __restrict__ occ, unsigned* fetch, int depth) {
+  extern __shared__ int s_dyn[];
+  int* st_ref = s_dyn + threadIdx.x;
+  int* st_tn = s_dyn + depth * kBlock + threadIdx.x;
+  const unsigned items = n_ptr ? *n_ptr : n_fixed;                  // rays (or hit points when BLOCKED)
+  const unsigned n = BLOCKED ? shadow_slots_for(items) : items;    // queue slots to visit
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned lt_mask = (1u << lane) - 1u;
+
+  unsigned idx = 0;
+  float3 o = f3(0, 0, 0), d = f3(0, 0, 0), inv = f3(0, 0, 0), oinv = f3(0, 0, 0);
+  HitRec h;
+  h.t = FLT_MAX;
+  h.u = h.v = 0.f;
+  h.gid = 0x7fffffff;
+  int sp = 0, cur = kDone;
+  bool exhausted = false;  // warp-uniform
+
+  for (;;) {
+    // ---- refill idle lanes -------------------------------------------------------------------
+    const bool need = (cur == kDone);
+    const unsigned need_mask = __ballot_sync(kFull, need);
+    if (!exhausted && need_mask) {
+      const unsigned cnt = __popc(need_mask);
+      unsigned base = 0;
+      if (lane == 0) base = atomicAdd(fetch, cnt);
+      base = __shfl_sync(kFull, base, 0);
+      if (base + cnt >= n) exhausted = true;
+      if (need) {
+        const unsigned my = base + __popc(need_mask & lt_mask);
+        bool valid = my < n;
+        if (BLOCKED && valid) valid = ((my / 96u) * 32u + (my & 31u)) < items;
+        if (valid) {
+          const float4 a = __ldg(ro + my), b = __ldg(rd + my);
+          idx = my;
+          o = f3(a);
+          d = f3(b);
+          inv = f3(safe_inv(d.x), safe_inv(d.y), safe_inv(d.z));
+          oinv = f3(o.x * inv.x, o.y * inv.y, o.z * inv.z);
+          h.t = FLT_MAX;
+          h.u = h.v = 0.f;
+          h.gid = 0x7fffffff;
+          sp = 0;
+          cur = 0;  // root
+        }
+      }
+    }
+    if (__ballot_sync(kFull, cur != kDone) == 0) {
+      if (exhausted) break;
+      continue;
+    }
+    // ---- traverse until the warp runs low on live rays ------------------------------------------
+    for (;;) {
+      if (cur != kDone) {
+        bool finished = false;
+        if (cur >= 0) {  // internal node: test both children
+          const float4 n0 = __ldg(S.nodes + 4 * cur), n1 = __ldg(S.nodes + 4 * cur + 1);
+          const float4 n2 = __ldg(S.nodes + 4 * cur + 2), n3 = __ldg(S.nodes + 4 * cur + 3);
+          float tn0, tn1;
+          const bool h0 = box_hit_fma(f3(n0.x, n0.y, n0.z), f3(n0.w, n1.x, n1.y), inv, oinv, h.t, tn0);
+          const bool h1 = box_hit_fma(f3(n1.z, n1.w, n2.x), f3(n2.y, n2.z, n2.w), inv, oinv, h.t, tn1);
+          const int c0 = __float_as_int(n3.x), c1 = __float_as_int(n3.y);
+          if (h0 && h1) {
+            const bool first0 = tn0 <= tn1;
+            st_ref[sp * kBlock] = first0 ? c1 : c0;
+            if (!ANY) st_tn[sp * kBlock] = __float_as_int(first0 ? tn1 : tn0);
+            sp++;
+            cur = first0 ? c0 : c1;
+          } else if (h0) {
+            cur = c0;
+          } else if (h1) {
+            cur = c1;
+          } else {
+            cur = kDone;  // pop below
+          }
+        } else {  // leaf: one triangle
+          const int slot = ~cur;
+          const float4 A = __ldg(S.tris + 3 * slot), B = __ldg(S.tris + 3 * slot + 1), C = __ldg(S.tris + 3 * slot + 2);
+          float u, v, t;
+          if (mt_intersect(o, d, f3(A), f3(B), f3(C), u, v, t)) {
+            if (ANY) {
+              if (t > 0.f && t < FLT_MAX) {
+                finished = true;  // occluded: stop this ray
+                h.gid = 0;
+              }
+            } else {
+              accept_nearest(h, t, u, v, __float_as_int(A.w));
+            }
+          }
+          cur = kDone;  // pop below
+        }
+        if (cur == kDone && !finished) {  // pop the next entry whose box can still matter
+          while (sp > 0) {
+            sp--;
+            const int ref = st_ref[sp * kBlock];
+            if (ANY || __int_as_float(st_tn[sp * kBlock]) <= h.t) {
+              cur = ref;
+              break;
+            }
+          }
+        }
+        if (cur == kDone) {  // ray complete: write the result now, the lane becomes idle
+          if (ANY)
+            occ[idx] = (h.gid != 0x7fffffff) ? 1 : 0;
+          else
+            hits[idx] = make_float4(h.t, h.u, h.v, __int_as_float(h.gid != 0x7fffffff ? h.gid : -1));
+        }
+      }
+      const unsigned live = __ballot_sync(kFull, cur != kDone);
+      if (live == 0) break;
+      if (!exhausted && __popc(live) < kRefillBelow) break;
+    }
   }
-  return color;
 }
 
+// RayTracer.h:27-53 exactly as written: every ray scans every triangle (parity hook, RT_FLAG_BRUTE_FORCE)
+template <bool ANY, bool BLOCKED>
+__global__ void __launch_bounds__(kBlock)
+    k_trace_brute(const DScene S, const float4* __restrict__ ro, const float4* __restrict__ rd, const unsigned* n_ptr,
+                  unsigned n_fixed, float4* __restrict__ hits, unsigned char* __restrict__ occ) {
+  const unsigned items = n_ptr ? *n_ptr : n_fixed;
+  const unsigned n = BLOCKED ? shadow_slots_for(items) : items;
+  for (unsigned i = blockIdx.x * kBlock + threadIdx.x; i < n; i += gridDim.x * kBlock) {
+    if (BLOCKED && ((i / 96u) * 32u + (i & 31u)) >= items) continue;
+    HitRec h;
+    const float3 o = f3(__ldg(ro + i)), d = f3(__ldg(rd + i));
+    const bool f = brute_trace<ANY>(S, o, d, h);
+    if (ANY)
+      occ[i] = f ? 1 : 0;
+    else
+      hits[i] = make_float4(h.t, h.u, h.v, __int_as_float(f ? h.gid : -1));
+  }
+}
+
+size_t trace_smem_bytes(int stack_depth) { return (size_t)2 * stack_depth * kBlock * sizeof(int); }
+
+int trace_ctas_per_sm(int stack_depth) {
+  int n = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_trace<false, false>, kBlock, trace_smem_bytes(stack_depth));
+  return n < 1 ? 1 : n;
+}
+
+template <bool ANY, bool BLOCKED>
+static void launch_trace_t(const DScene& S, const float4* ro, const float4* rd, const unsigned* n_ptr, unsigned n_fixed,
+                           float4* hits, unsigned char* occ, unsigned* fetch, int brute, int depth, int grid,
+                           cudaStream_t st) {
+  if (brute) {
+    k_trace_brute<ANY, BLOCKED><<<grid, kBlock, 0, st>>>(S, ro, rd, n_ptr, n_fixed, hits, occ);
+  } else {
+    cudaMemsetAsync(fetch, 0, sizeof(unsigned), st);
+    k_trace<ANY, BLOCKED><<<grid, kBlock, trace_smem_bytes(depth), st>>>(S, ro, rd, n_ptr, n_fixed, hits, occ, fetch,
+                                                                         depth);
+  }
+}
+
+void launch_trace_nearest(const RenderArgs& a, int seg, int grid, cudaStream_t st) {
+  const unsigned* n_ptr = seg == 0 ? nullptr : a.q_count + kQHits0 + (seg - 1);
+  launch_trace_t<false, false>(a.scene, a.ray_o[seg & 1], a.ray_d[seg & 1], n_ptr, (unsigned)a.npix * (unsigned)a.nsamp,
+                               a.hit, nullptr, a.q_count + kQFetchNearest0 + seg, a.brute, a.stack_depth, grid, st);
+}
+void launch_trace_any(const RenderArgs& a, int seg, int grid, cudaStream_t st) {
+  launch_trace_t<true, true>(a.scene, a.sh_o, a.sh_d, a.q_count + kQHits0 + seg, 0, nullptr, a.occ,
+                             a.q_count + kQFetchAny0 + seg, a.brute, a.stack_depth, grid, st);
+}
+void launch_trace_rays(const DScene& s, const float4* ro, const float4* rd, unsigned n, float4* hits,
+                       unsigned char* occluded, int any, int brute, int stack_depth, unsigned* fetch_counter, int grid,
+                       cudaStream_t st) {
+  if (any)
+    launch_trace_t<true, false>(s, ro, rd, nullptr, n, nullptr, occluded, fetch_counter, brute, stack_depth, grid, st);
+  else
+    launch_trace_t<false, false>(s, ro, rd, nullptr, n, hits, nullptr, fetch_counter, brute, stack_depth, grid, st);
+}
+
+// ----------------------------------------------------------------------------------------------
+// k_raygen: path p -> primary ray (Renderer.cpp:229-234)
+// ----------------------------------------------------------------------------------------------
+RT_DI uint64_t path_stream_key(const RenderArgs& A, unsigned p, int& pixel, int& sample) {
+  const int sl = p / (unsigned)A.npix;
+  const int pl = p - sl * A.npix;
+  pixel = __ldg(A.pix_map + pl);
+  sample = A.s0 + sl;
+  return stream_key(A.seed_mixed, kDomainPixel, (uint64_t)sample * ((uint64_t)A.width * A.height) + (uint64_t)pixel);
+}
+
+__global__ void __launch_bounds__(256) k_raygen(const RenderArgs A) {
+  const unsigned n = (unsigned)A.npix * (unsigned)A.nsamp;
+  for (unsigned p = blockIdx.x * 256 + threadIdx.x; p < n; p += gridDim.x * 256) {
+    int pixel, sample;
+    Rng g;
+    g.init(path_stream_key(A, p, pixel, sample), 0);
+    float sx, sy;
+    jitter_sample(g, sample, A.jitter_d, sx, sy);
+    const int y = pixel / A.width, x = pixel - y * A.width;
+    float3 o, d;
+    camera_ray(A.scene.cam, x, y, sx, sy, A.width, A.height, o, d);
+    A.ray_o[0][p] = make_float4(o.x, o.y, o.z, __int_as_float((int)p));
+    A.ray_d[0][p] = make_float4(d.x, d.y, d.z, 0.f);
+  }
+}
+void launch_raygen(const RenderArgs& a, cudaStream_t st) {
+  long long n = (long long)a.npix * a.nsamp;
+  int grid = (int)((n + 255) / 256 < 148 * 16 ? (n + 255) / 256 : 148 * 16);
+  if (grid < 1) grid = 1;
+  k_raygen<<<grid, 256, 0, st>>>(a);
+}
+
+// ----------------------------------------------------------------------------------------------
+// k_shade: one thread per ray of the segment
+// ----------------------------------------------------------------------------------------------
 // Renderer.cpp:63-104
 RT_DI float3 shade_photon(const DScene& S, float3 dir, float3 n, float3 P, const DMaterial& m, int k, int num_photons,
                           unsigned long long& visits) {
@@ -62,146 +268,152 @@ RT_DI float3 shade_photon(const DScene& S, float3 dir, float3 n, float3 P, const
   return v_scl(bsdf, rad);
 }
 
-// ----------------------------------------------------------------------------------------------
-// k_segment
-// ----------------------------------------------------------------------------------------------
 template <int MODE, bool PHOTON>
-__global__ void __launch_bounds__(kBlock) k_segment(const RenderArgs A, const int seg) {
-  __shared__ int s_stack[kStackDepth * kBlock];
-  int* stack = s_stack + threadIdx.x;
+__global__ void __launch_bounds__(kBlock) k_shade(const RenderArgs A, const int seg) {
   const DScene& S = A.scene;
-  const unsigned n = seg == 0 ? (unsigned)A.npix * (unsigned)A.nsamp : A.q_count[seg - 1];
-  const float4* qo_in = A.q_o[(seg + 1) & 1];
-  const float4* qd_in = A.q_d[(seg + 1) & 1];
-  float4* qo_out = A.q_o[seg & 1];
-  float4* qd_out = A.q_d[seg & 1];
+  const unsigned n = seg == 0 ? (unsigned)A.npix * (unsigned)A.nsamp : A.q_count[kQHits0 + seg - 1];
+  const float4* qo_in = A.ray_o[seg & 1];
+  const float4* qd_in = A.ray_d[seg & 1];
+  float4* qo_out = A.ray_o[(seg + 1) & 1];
+  float4* qd_out = A.ray_d[(seg + 1) & 1];
   const unsigned lane = threadIdx.x & 31u;
-  unsigned n_near = 0, n_shadow = 0, n_knn = 0;
+  unsigned n_hit = 0, n_knn = 0;
   unsigned long long n_visits = 0;
 
   for (unsigned base = blockIdx.x * kBlock; base < n; base += gridDim.x * kBlock) {
     const unsigned i = base + threadIdx.x;
-    bool push = false;
-    float3 next_o = f3(0, 0, 0), next_d = f3(0, 0, 0);
+    bool found = false;
     unsigned p = 0;
+    float3 o = f3(0, 0, 0), d = f3(0, 0, 0);
+    HitRec h;
     if (i < n) {
-      float3 o, d;
+      const float4 a = qo_in[i], b = qd_in[i], hr = A.hit[i];
+      o = f3(a);
+      d = f3(b);
+      p = (unsigned)__float_as_int(a.w);
+      h.t = hr.x;
+      h.u = hr.y;
+      h.v = hr.z;
+      h.gid = __float_as_int(hr.w);
+      found = h.gid >= 0;
+    }
+    // compacted index j of this hit (warp-aggregated)
+    const unsigned mask = __ballot_sync(kFull, found);
+    unsigned j = 0;
+    if (mask) {
+      unsigned j0 = 0;
+      if (lane == (unsigned)(__ffs(mask) - 1)) j0 = atomicAdd(A.q_count + kQHits0 + seg, (unsigned)__popc(mask));
+      j0 = __shfl_sync(kFull, j0, __ffs(mask) - 1);
+      j = j0 + __popc(mask & ((1u << lane) - 1u));
+    }
+    if (i < n && !found) {
+      // Renderer.cpp:154-160: a miss ends the path; the colour so far is clamped and final
       if (seg == 0) {
-        p = i;
+        A.col0[p] = make_float4(0.f, 0.f, 0.f, 0.f);  // posIntersectionFound = false
       } else {
-        float4 a = qo_in[i], b = qd_in[i];
-        o = f3(a);
-        d = f3(b);
-        p = (unsigned)__float_as_int(a.w);
-      }
-      const int sl = p / (unsigned)A.npix;
-      const int pl = p - sl * A.npix;
-      const int pixel = __ldg(A.pix_map + pl);
-      const int sample = A.s0 + sl;
-      Rng g;
-      const uint64_t key =
-          stream_key(A.seed_mixed, kDomainPixel, (uint64_t)sample * ((uint64_t)A.width * A.height) + (uint64_t)pixel);
-      if (seg == 0) {
-        g.init(key, 0);
-        float sx, sy;
-        jitter_sample(g, sample, A.jitter_d, sx, sy);  // Renderer.cpp:229
-        const int y = pixel / A.width, x = pixel - y * A.width;
-        camera_ray(S.cam, x, y, sx, sy, A.width, A.height, o, d);  // Renderer.cpp:233
-      } else {
-        g.init(key, 4u + (PHOTON ? 4u : 10u) * (unsigned)seg);
-      }
-      HitRec h;
-      n_near++;
-      const bool found = trace<false>(S, o, d, stack, A.brute, h);  // h.t > 0 by construction
-      float3 c = f3(0.f, 0.f, 0.f);
-      if (found) {
-        float3 nrm, P;
-        int mesh;
-        hit_geometry(S, h, nrm, P, mesh);
-        const DMaterial m = S.mats[mesh];
-        if (PHOTON) {
-          n_knn++;
-          c = shade_photon(S, d, nrm, P, m, A.k, A.num_photons, n_visits);
-        } else {
-          c = shade_direct(S, d, nrm, P, m, g, stack, A.brute, n_shadow);
-        }
-        if (MODE == 1 && seg < 2) {
-          next_d = hsphere_uniform_sample(g, nrm);  // Renderer.cpp:164-166
-          next_o = P;
-          push = true;
-        }
-      }
-      // Renderer.cpp:143-170 unrolled: colour = c0 + (c1 + c2); a miss at depth d ends the sum there.
-      if (seg == 0) {
-        float3 out = (MODE == 0 || !found) ? normalize_color(c) : c;
-        A.col0[p] = make_float4(out.x, out.y, out.z, found ? 1.f : 0.f);
-      } else if (seg == 1) {
-        if (found) {
-          A.col1[p] = make_float4(c.x, c.y, c.z, 0.f);
-        } else {
-          float4 c0 = A.col0[p];
-          float3 out = normalize_color(f3(c0));
-          A.col0[p] = make_float4(out.x, out.y, out.z, c0.w);
-        }
-      } else {
-        float4 c0 = A.col0[p], c1 = A.col1[p];
-        float3 out = normalize_color(v_add(f3(c0), v_add(f3(c1), c)));
+        float4 c0 = A.col0[p];
+        float3 sum = f3(c0);
+        if (seg == 2) sum = v_add(sum, v_add(f3(A.col1[p]), f3(0.f, 0.f, 0.f)));
+        float3 out = normalize_color(sum);
         A.col0[p] = make_float4(out.x, out.y, out.z, c0.w);
       }
     }
-    if (MODE == 1 && seg < 2) {  // warp-aggregated push into the next segment's queue
-      const unsigned mask = __ballot_sync(0xffffffffu, push);
-      if (mask) {
-        unsigned slot0 = 0;
-        if (lane == (unsigned)(__ffs(mask) - 1)) slot0 = atomicAdd(A.q_count + seg, (unsigned)__popc(mask));
-        slot0 = __shfl_sync(0xffffffffu, slot0, __ffs(mask) - 1);
-        if (push) {
-          const unsigned slot = slot0 + __popc(mask & ((1u << lane) - 1u));
-          qo_out[slot] = make_float4(next_o.x, next_o.y, next_o.z, __int_as_float((int)p));
-          qd_out[slot] = make_float4(next_d.x, next_d.y, next_d.z, 0.f);
+    if (found) {
+      n_hit++;
+      int pixel, sample;
+      Rng g;
+      g.init(path_stream_key(A, p, pixel, sample), 4u + (PHOTON ? 4u : 10u) * (unsigned)seg);
+      float3 nrm, P;
+      int mesh;
+      hit_geometry(S, h, nrm, P, mesh);
+      const DMaterial m = S.mats[mesh];
+      A.hit_path[j] = (int)p;
+      if (PHOTON) {
+        n_knn++;
+        float3 c = shade_photon(S, d, nrm, P, m, A.k, A.num_photons, n_visits);
+        A.contrib[shadow_slot(j, 0)] = make_float4(c.x, c.y, c.z, 0.f);
+        A.occ[shadow_slot(j, 0)] = 0;
+        for (unsigned l = 1; l < (unsigned)kShadowLights; l++) A.occ[shadow_slot(j, l)] = 1;
+      } else {
+        // Renderer.cpp:49-60: per light 2 uniforms, the shadow ray, and (eagerly) radiance * bsdf
+        const float3 wo = v_neg(d);
+        for (int l = 0; l < kShadowLights; l++) {
+          const unsigned s = shadow_slot(j, l);
+          if (l < S.num_lights) {
+            const DLight& L = S.lights[l];
+            float3 to_light = v_sub(light_rand_area_position(L, g), P);
+            float3 c = v_mul(light_evaluate(L, P), evaluate_color_response(m, nrm, to_light, wo));
+            A.sh_o[s] = make_float4(P.x, P.y, P.z, 0.f);
+            A.sh_d[s] = make_float4(to_light.x, to_light.y, to_light.z, 0.f);
+            A.contrib[s] = make_float4(c.x, c.y, c.z, 0.f);
+          } else {  // fewer than 3 lights: a ray that cannot hit anything, contribution dropped by occ
+            A.sh_o[s] = make_float4(P.x, P.y, P.z, 0.f);
+            A.sh_d[s] = make_float4(0.f, 0.f, 0.f, 0.f);
+            A.contrib[s] = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
         }
+      }
+      if (MODE == 1 && seg < 2) {  // Renderer.cpp:164-166: bounce
+        float3 nd = hsphere_uniform_sample(g, nrm);
+        qo_out[j] = make_float4(P.x, P.y, P.z, __int_as_float((int)p));
+        qd_out[j] = make_float4(nd.x, nd.y, nd.z, 0.f);
       }
     }
   }
-  // counters: one atomic per warp per counter
   for (int off = 16; off > 0; off >>= 1) {
-    n_near += __shfl_xor_sync(0xffffffffu, n_near, off);
-    n_shadow += __shfl_xor_sync(0xffffffffu, n_shadow, off);
-    n_knn += __shfl_xor_sync(0xffffffffu, n_knn, off);
-    n_visits += __shfl_xor_sync(0xffffffffu, n_visits, off);
+    n_hit += __shfl_xor_sync(kFull, n_hit, off);
+    n_knn += __shfl_xor_sync(kFull, n_knn, off);
+    n_visits += __shfl_xor_sync(kFull, n_visits, off);
   }
   if (lane == 0) {
-    if (n_near) atomicAdd(A.counters + kCntNearest, (unsigned long long)n_near);
-    if (n_shadow) atomicAdd(A.counters + kCntShadow, (unsigned long long)n_shadow);
+    if (n_hit && !PHOTON) atomicAdd(A.counters + kCntShadow, (unsigned long long)n_hit * A.scene.num_lights);
     if (n_knn) atomicAdd(A.counters + kCntKnn, (unsigned long long)n_knn);
     if (n_visits) atomicAdd(A.counters + kCntKdVisits, n_visits);
   }
+  if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(A.counters + kCntNearest, (unsigned long long)n);
 }
 
-void launch_segment(const RenderArgs& a, int seg, int grid_ctas, cudaStream_t st) {
+void launch_shade(const RenderArgs& a, int seg, int grid, cudaStream_t st) {
   if (a.mode == 0) {
     if (a.photon)
-      k_segment<0, true><<<grid_ctas, kBlock, 0, st>>>(a, seg);
+      k_shade<0, true><<<grid, kBlock, 0, st>>>(a, seg);
     else
-      k_segment<0, false><<<grid_ctas, kBlock, 0, st>>>(a, seg);
+      k_shade<0, false><<<grid, kBlock, 0, st>>>(a, seg);
   } else {
     if (a.photon)
-      k_segment<1, true><<<grid_ctas, kBlock, 0, st>>>(a, seg);
+      k_shade<1, true><<<grid, kBlock, 0, st>>>(a, seg);
     else
-      k_segment<1, false><<<grid_ctas, kBlock, 0, st>>>(a, seg);
+      k_shade<1, false><<<grid, kBlock, 0, st>>>(a, seg);
   }
 }
 
-int segment_ctas_per_sm(int mode, int photon) {
-  int n = 0;
-  if (mode == 0)
-    photon ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_segment<0, true>, kBlock, 0)
-           : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_segment<0, false>, kBlock, 0);
-  else
-    photon ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_segment<1, true>, kBlock, 0)
-           : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_segment<1, false>, kBlock, 0);
-  return n < 1 ? 1 : n;
+// ----------------------------------------------------------------------------------------------
+// k_combine: colorResponse = ((0 + a0) + a1) + a2 over the unoccluded lights (Renderer.cpp:44,49-60),
+// then the path sum c0 + (c1 + c2) and the per-sample clamp (Renderer.cpp:168,254)
+// ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_combine(const RenderArgs A, const int seg) {
+  const unsigned n = A.q_count[kQHits0 + seg];
+  for (unsigned j = blockIdx.x * 256 + threadIdx.x; j < n; j += gridDim.x * 256) {
+    float3 c = f3(0.f, 0.f, 0.f);
+#pragma unroll
+    for (int l = 0; l < kShadowLights; l++) {
+      const unsigned s = shadow_slot(j, l);
+      if (A.occ[s] == 0 && (A.photon || l < A.scene.num_lights)) c = v_add(c, f3(A.contrib[s]));
+    }
+    const unsigned p = (unsigned)A.hit_path[j];
+    if (seg == 0) {
+      float3 out = A.mode == 0 ? normalize_color(c) : c;
+      A.col0[p] = make_float4(out.x, out.y, out.z, 1.f);
+    } else if (seg == 1) {
+      A.col1[p] = make_float4(c.x, c.y, c.z, 0.f);
+    } else {
+      float4 c0 = A.col0[p];
+      float3 out = normalize_color(v_add(f3(c0), v_add(f3(A.col1[p]), c)));
+      A.col0[p] = make_float4(out.x, out.y, out.z, c0.w);
+    }
+  }
 }
+void launch_combine(const RenderArgs& a, int seg, int grid, cudaStream_t st) { k_combine<<<grid, 256, 0, st>>>(a, seg); }
 
 // ----------------------------------------------------------------------------------------------
 // ordered accumulation: updateImage(x,y) += colorResponse for samples in index order
@@ -244,33 +456,6 @@ void launch_scatter(const float4* acc_rgb, const int* acc_cnt, const int* pix_ma
 // ----------------------------------------------------------------------------------------------
 // parity hooks
 // ----------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kBlock) k_trace(const DScene S, const float* __restrict__ rays6, long long n,
-                                                  int* tri, float* uvt, int brute, int any, unsigned char* occluded) {
-  __shared__ int s_stack[kStackDepth * kBlock];
-  int* stack = s_stack + threadIdx.x;
-  for (long long i = (long long)blockIdx.x * kBlock + threadIdx.x; i < n; i += (long long)gridDim.x * kBlock) {
-    float3 o = f3(rays6[6 * i], rays6[6 * i + 1], rays6[6 * i + 2]);
-    float3 d = f3(rays6[6 * i + 3], rays6[6 * i + 4], rays6[6 * i + 5]);
-    HitRec h;
-    if (any) {
-      occluded[i] = trace<true>(S, o, d, stack, brute, h) ? 1 : 0;
-    } else {
-      bool f = trace<false>(S, o, d, stack, brute, h);
-      tri[i] = f ? h.gid : -1;
-      uvt[3 * i] = f ? h.u : 0.f;
-      uvt[3 * i + 1] = f ? h.v : 0.f;
-      uvt[3 * i + 2] = f ? h.t : 0.f;
-    }
-  }
-}
-void launch_trace_rays(const DScene& s, const float* rays6, long long n, int* tri, float* uvt, int brute, int any,
-                       unsigned char* occluded, cudaStream_t st) {
-  long long blocks = (n + kBlock - 1) / kBlock;
-  if (blocks > 148 * 16) blocks = 148 * 16;
-  if (blocks < 1) blocks = 1;
-  k_trace<<<(int)blocks, kBlock, 0, st>>>(s, rays6, n, tri, uvt, brute, any, occluded);
-}
-
 __global__ void k_bsdf(DMaterial m, const float* __restrict__ in, long long n, float* out) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -337,7 +522,8 @@ __global__ void __launch_bounds__(kBlock) k_emit(const DScene S, uint64_t seed_m
       if (depth >= 20) break;  // PhotonMap.h:98: dropped
       HitRec h;
       n_rays++;
-      if (!trace<false>(S, o, d, stack, brute, h)) {  // PhotonMap.h:109-112
+      const bool f = brute ? brute_trace<false>(S, o, d, h) : bvh_traverse<false>(S, o, d, stack, kBlock, h);
+      if (!f) {  // PhotonMap.h:109-112
         stored = depth != 0;
         break;
       }
@@ -363,7 +549,7 @@ __global__ void __launch_bounds__(kBlock) k_emit(const DScene S, uint64_t seed_m
     out_a[q] = make_float4(ppos.x, ppos.y, ppos.z, weight);
     out_b[q] = make_float4(pdir.x, pdir.y, pdir.z, __int_as_float((stored ? 1 : 0) | (hist << 8)));
   }
-  for (int off = 16; off > 0; off >>= 1) n_rays += __shfl_xor_sync(0xffffffffu, n_rays, off);
+  for (int off = 16; off > 0; off >>= 1) n_rays += __shfl_xor_sync(kFull, n_rays, off);
   if ((threadIdx.x & 31) == 0 && n_rays) atomicAdd(counters + kCntPhotonRays, (unsigned long long)n_rays);
 }
 void launch_emit(const DScene& s, uint64_t seed_mixed, int per_light, float light_pdf, int first_path, int npaths,

@@ -9,6 +9,21 @@ namespace rtb {
 // Device counters (unsigned long long each)
 enum Counter { kCntNearest = 0, kCntShadow = 1, kCntKnn = 2, kCntPhotonRays = 3, kCntKdVisits = 4, kCntNum = 8 };
 
+// q_count[] slots (unsigned each): hits compacted by segment 0/1/2, then the work-fetch cursors of the
+// persistent trace kernels (nearest-hit and any-hit launch of each segment)
+enum QSlot { kQHits0 = 0, kQFetchNearest0 = 4, kQFetchAny0 = 8, kQNum = 12 };
+
+// Shadow rays / light contributions of compacted hit j live in a light-major blocked layout so that a
+// warp of the any-hit kernel gets 32 consecutive hit points aiming at ONE light (coherent rays):
+//   slot(j, l) = (j / 32) * 96 + l * 32 + (j % 32)            (3 lights per hit, kShadowLights)
+constexpr int kShadowLights = 3;
+__host__ __device__ __forceinline__ unsigned shadow_slot(unsigned j, unsigned l) {
+  return (j >> 5) * (32u * kShadowLights) + l * 32u + (j & 31u);
+}
+__host__ __device__ __forceinline__ unsigned shadow_slots_for(unsigned hits) {
+  return ((hits + 31u) >> 5) * (32u * kShadowLights);
+}
+
 // One wavefront batch = `nsamp` consecutive samples of `npix` pixels; path p = s_local*npix + pixel_local.
 struct RenderArgs {
   DScene scene;
@@ -20,30 +35,45 @@ struct RenderArgs {
   int k;            // neighbours
   int num_photons;  // REQUESTED photon count (Renderer.cpp:99)
   int brute;        // 1: O(T) scan instead of BVH
+  int stack_depth;  // traversal stack entries per ray (>= bvh depth)
   uint64_t seed_mixed;
   const int* pix_map;  // local pixel -> y*W + x
   int npix;
   int s0, nsamp;
   float4* col0;  // per path: seg-0 colour, then the final clamped colour; w = posIntersectionFound
   float4* col1;  // per path: seg-1 colour
-  float4* q_o[2];
-  float4* q_d[2];           // ray queues (origin+path id, direction)
-  unsigned int* q_count;    // [3] entries pushed by segment 0,1,2
+  float4* ray_o[2];  // ray queues, ping-pong by segment: (origin, path id) / (direction, -)
+  float4* ray_d[2];
+  float4* hit;       // per ray slot of the current segment: (t, u, v, triangle id | -1)
+  float4* sh_o;      // shadow rays, blocked layout (see shadow_slot)
+  float4* sh_d;
+  float4* contrib;   // radiance * bsdf of light l for hit j, same layout
+  unsigned char* occ;  // any-hit result, same layout
+  int* hit_path;     // compacted hit j -> path id
+  unsigned int* q_count;
   unsigned long long* counters;
 };
 
-void launch_segment(const RenderArgs& a, int seg, int grid_ctas, cudaStream_t st);
+void launch_raygen(const RenderArgs& a, cudaStream_t st);
+void launch_trace_nearest(const RenderArgs& a, int seg, int grid_ctas, cudaStream_t st);
+void launch_shade(const RenderArgs& a, int seg, int grid_ctas, cudaStream_t st);
+void launch_trace_any(const RenderArgs& a, int seg, int grid_ctas, cudaStream_t st);
+void launch_combine(const RenderArgs& a, int seg, int grid_ctas, cudaStream_t st);
+int trace_ctas_per_sm(int stack_depth);
+size_t trace_smem_bytes(int stack_depth);
+
 void launch_resolve(const float4* col0, int npix, int nsamp, float4* acc_rgb, int* acc_cnt, cudaStream_t st);
 void launch_scatter(const float4* acc_rgb, const int* acc_cnt, const int* pix_map, int npix, float* out_rgb,
                     int* out_cnt, cudaStream_t st);
-void launch_trace_rays(const DScene& s, const float* rays6, long long n, int* tri, float* uvt, int brute, int any,
-                       unsigned char* occluded, cudaStream_t st);
+// parity hooks: caller-supplied rays through the SAME persistent trace kernels the renderer uses
+void launch_trace_rays(const DScene& s, const float4* ro, const float4* rd, unsigned n, float4* hits,
+                       unsigned char* occluded, int any, int brute, int stack_depth, unsigned* fetch_counter,
+                       int grid_ctas, cudaStream_t st);
 void launch_bsdf(DMaterial m, const float* n_wi_wo, long long n, float* rgb, cudaStream_t st);
 // photon emission: path q = light*npaths + j traces path (first_path + j) of `light`
 void launch_emit(const DScene& s, uint64_t seed_mixed, int per_light, float light_pdf, int first_path, int npaths,
                  int brute, float4* out_a, float4* out_b, unsigned long long* counters, cudaStream_t st);
 void launch_knn(const DScene& s, const float* q3, long long n, int k, int* node_index, unsigned long long* counters,
                 cudaStream_t st);
-int segment_ctas_per_sm(int mode, int photon);
 
 }  // namespace rtb

@@ -194,12 +194,28 @@ RT_DI void accept_nearest(HitRec& h, float t, float u, float v, int gid) {
   }
 }
 
-// Conservative slab test against a padded box (see bvh_build.h for the padding argument).  NaNs from
+// Conservative slab test against a padded box (see host_build.h for the padding argument).  NaNs from
 // 0*inf drop out of fminf/fmaxf.  A child is visited when its interval overlaps [0, best_t].
 RT_DI bool box_hit(float3 lo, float3 hi, float3 o, float3 inv, float best_t, float& tnear) {
   float t0x = (lo.x - o.x) * inv.x, t1x = (hi.x - o.x) * inv.x;
   float t0y = (lo.y - o.y) * inv.y, t1y = (hi.y - o.y) * inv.y;
   float t0z = (lo.z - o.z) * inv.z, t1z = (hi.z - o.z) * inv.z;
+  float tmin = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fminf(t0z, t1z));
+  float tmax = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fmaxf(t0z, t1z));
+  tnear = tmin;
+  return (tmin <= tmax) && (tmax >= 0.f) && (tmin <= best_t);
+}
+
+// The same test with one fused multiply-add per plane: t = lo*inv - o*inv (oinv = o*inv precomputed per
+// ray).  The traversal only has to be conservative, not bit-exact, and the padding covers the different
+// rounding.  inv MUST come from safe_inv(): with inv = +-inf the form lo*inf - o*inf gives inf - inf = NaN
+// on ONE plane of a slab the origin is inside of, and fmin/fmax then resolve it as a miss (found by the
+// N=128 parity test: 3 of 22.6 M primary rays have an exactly-zero direction component).
+RT_DI float safe_inv(float d) { return fminf(fmaxf(1.0f / d, -1e30f), 1e30f); }
+RT_DI bool box_hit_fma(float3 lo, float3 hi, float3 inv, float3 oinv, float best_t, float& tnear) {
+  float t0x = __fmaf_rn(lo.x, inv.x, -oinv.x), t1x = __fmaf_rn(hi.x, inv.x, -oinv.x);
+  float t0y = __fmaf_rn(lo.y, inv.y, -oinv.y), t1y = __fmaf_rn(hi.y, inv.y, -oinv.y);
+  float t0z = __fmaf_rn(lo.z, inv.z, -oinv.z), t1z = __fmaf_rn(hi.z, inv.z, -oinv.z);
   float tmin = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fminf(t0z, t1z));
   float tmax = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fmaxf(t0z, t1z));
   tnear = tmin;
