@@ -151,7 +151,7 @@ def run_cpu(workload, cores, seconds_target, repeats=1, warm=0):
     jobs = [(cs["scene_file"], cs["w"], cs["h"], cs["N"], cs["mode"], 1, x0, a, x1, b, cs["samples"][0],
              cs["samples"][1], kind) for a, b in bands if b > a]
     # logical ray count of exactly this sample, from the restatement's counters (identical streams,
-    # bit-identical control flow -- tests/test_oracle_port_vs_ref.py), outside the timed region
+    # bit-identical control flow -- tests/test_oracle.py), outside the timed region
     flat = O.FlatScene.load(cs["scene_file"])
     flat.w, flat.h = cs["w"], cs["h"]
     port = O.PortOracle(flat)

@@ -183,6 +183,10 @@ int rt_get_photons(rt_ctx* ctx, rt_photon* out, int64_t capacity, int64_t* count
 int rt_knn(rt_ctx* ctx, const float* queries, int64_t n, int32_t k, int32_t* node_index);
 int rt_get_kdtree(rt_ctx* ctx, rt_photon* nodes, int32_t* left, int32_t* right, int32_t* root, int64_t capacity);
 
+/* Which pixels (y*W + x) a shard owns, in the order the wavefront processes them (pure host function,
+ * needs no device): call with out = NULL to get the count. */
+int rt_shard_pixels(const rt_params* params, int32_t* out, int64_t capacity, int64_t* count);
+
 int rt_get_stats(rt_ctx* ctx, rt_stats* out);
 int rt_reset_stats(rt_ctx* ctx);
 /* flattened BVH for inspection/tests: nodes*16 floats; returns counts through out params */

@@ -52,6 +52,7 @@ def scenes():
     # non-square camera (the CLI default 380x270) for the host-side camera test
     flat = ref.create_scene(380, 270)
     save("camera_380x270.npz", cam=flat.cam)
+    save("background.npz", rows_420=ref.background(420, 420)[:, 0, :], rows_270=ref.background(380, 270)[:, 0, :])
     # the reference's OFF loader on our own tiny fixture (quads + comment + polygon fan)
     pos, nrm, tri = ref.load_off(os.path.join(GOLD, "fixture_mixed.off"))
     save("fixture_mixed_loaded.npz", pos=pos, nrm=nrm, tri=tri)

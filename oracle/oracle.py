@@ -20,6 +20,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 PORT_LIB = os.path.join(HERE, "liboracle_port.so")
 REF_LIB = os.path.join(HERE, "_ref", "libref_cb.so")
+REF_STOCK_LIB = os.path.join(HERE, "_ref", "libref_stock.so")
 REF_BIN = os.path.join(HERE, "_ref", "RayTracer_ref")
 REF_BIN_OMP = os.path.join(HERE, "_ref", "RayTracer_ref_omp")
 REF_MESHES = os.path.join(HERE, "_ref", "meshes")
@@ -288,6 +289,14 @@ class PhotonMapHandle:
         self.o._fn("photon_map_get")(self.handle, _p(p), _p(hist))
         return p, hist
 
+    def light_counts(self, num_lights=3):
+        """(port only) particles stored per light by the emission that built this map."""
+        out = np.zeros(num_lights, np.int64)
+        fn = self.o.lib.orc_photon_map_light_counts
+        fn.restype, fn.argtypes = None, [C.c_void_p, C.c_void_p, C.c_int]
+        fn(self.handle, _p(out), num_lights)
+        return out
+
     def layout(self):
         n = self.size()
         nodes = np.zeros((n, 7), _f)
@@ -365,8 +374,9 @@ class PortOracle(_Oracle):
 class RefOracle(_Oracle):
     prefix = "ref_"
 
-    def __init__(self):
-        super().__init__(REF_LIB)
+    def __init__(self, stock_rng=False):
+        """stock_rng=True loads the build whose `gen` is the reference's own serial minstd_rand0."""
+        super().__init__(REF_STOCK_LIB if stock_rng else REF_LIB)
         lib = self.lib
         lib.ref_scene_create.restype = C.c_void_p
         lib.ref_scene_create.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_int]

@@ -16,6 +16,7 @@ struct PortPhotonMap {
   KdTree tree;
   int depth_hist[20] = {0};
   Counters counters;
+  std::vector<int64_t> per_light;
 };
 inline V3 ld3(const float* p) { return mk(p[0], p[1], p[2]); }
 inline void st3(float* p, V3 v) {
@@ -173,7 +174,7 @@ void* orc_photon_map_create(void* sp, int numPhotons, uint64_t seed, int first_p
   PortPhotonMap* pm = new PortPhotonMap();
   int p0 = first_path < 0 ? 0 : first_path;
   int p1 = num_paths < 0 ? -1 : p0 + num_paths;
-  emit_photons(s, numPhotons, seed, p0, p1, pm->list, pm->depth_hist, pm->counters);
+  emit_photons(s, numPhotons, seed, p0, p1, pm->list, pm->depth_hist, pm->counters, &pm->per_light);
   pm->tree.build(pm->list);
   return pm;
 }
@@ -186,6 +187,11 @@ void* orc_photon_map_from_list(const float* particles, int64_t n) {
 }
 void orc_photon_map_destroy(void* p) { delete static_cast<PortPhotonMap*>(p); }
 int64_t orc_photon_map_size(void* p) { return (int64_t) static_cast<PortPhotonMap*>(p)->list.size(); }
+// particles stored per light by the emission that built this map (out: one int64 per light)
+void orc_photon_map_light_counts(void* p, int64_t* out, int n) {
+  PortPhotonMap* pm = static_cast<PortPhotonMap*>(p);
+  for (int i = 0; i < n; i++) out[i] = i < (int)pm->per_light.size() ? pm->per_light[i] : 0;
+}
 uint64_t orc_photon_map_rays(void* p) { return static_cast<PortPhotonMap*>(p)->counters.rays; }
 void orc_photon_map_get(void* p, float* particles, int32_t* depth_hist) {
   PortPhotonMap* pm = static_cast<PortPhotonMap*>(p);

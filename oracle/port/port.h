@@ -4,7 +4,7 @@
 // --impl reference legs may use this code; the product (ray-tracing-engine_b200/) never links it.
 //
 // PARITY PINNING: the reference ships no tests and no golden vectors, so this
-// restatement is pinned against the reference ITSELF: tests/test_oracle_port_vs_ref.py runs every
+// restatement is pinned against the reference ITSELF: tests/test_oracle.py runs every
 // function below against the unmodified reference compiled into oracle/_ref/libref_cb.so (bit-exact
 // comparisons), and tests/golden/ holds vectors generated from that library by oracle/gen_golden.py
 // for the machines where /root/reference is absent.
@@ -461,14 +461,17 @@ static inline int photons_per_light(const Scene& s, int numPhotons) {
   return (int)((float)numPhotons * lightPdf);
 }
 static inline void emit_photons(const Scene& s, int numPhotons, uint64_t seed, int p0, int p1,
-                                std::vector<Particle>& list, int* depth_hist, Counters& c) {
+                                std::vector<Particle>& list, int* depth_hist, Counters& c,
+                                std::vector<int64_t>* per_light = nullptr) {
   if (numPhotons <= 0) return;
   float lightPdf = 1.f / (float)s.lights.size();
   int perLight = photons_per_light(s, numPhotons);
   if (p0 < 0) p0 = 0;
   if (p1 < 0 || p1 > perLight) p1 = perLight;
+  if (per_light) per_light->assign(s.lights.size(), 0);
   for (size_t li = 0; li < s.lights.size(); li++) {
     const Light& l = s.lights[li];
+    const size_t before = list.size();
     for (int i = p0; i < p1; i++) {
       Rng g(seed, RTO_DOMAIN_PHOTON, (uint64_t)li * (uint64_t)perLight + (uint64_t)i);
       V3 startPosition = light_rand_area_position(l, g);
@@ -479,6 +482,7 @@ static inline void emit_photons(const Scene& s, int numPhotons, uint64_t seed, i
       int depth = photon_path(s, startPosition, startDirection, photon, g, list, c);
       if (depth >= 0 && depth_hist) depth_hist[depth]++;
     }
+    if (per_light) (*per_light)[li] = (int64_t)(list.size() - before);
   }
 }
 

@@ -34,7 +34,11 @@
 #include <vector>
 #include <array>
 #include <assert.h>
-#include <math.h>
+// NOTE: <math.h> must NOT be included before the reference sources: libstdc++'s <math.h> wrapper pulls the
+// float overloads (std::tan(float), ...) into the global namespace, and Camera.h:16 `tan(angle / 2.f)` --
+// which the stock build resolves to ::tan(double) because Camera.h is the first header Main.cpp includes --
+// would silently become tanf and move the camera by 1-4 ulp.  Everything above is either included by
+// Main.cpp itself before Camera.h or does not declare anything the reference looks up unqualified.
 
 #include "rng_contract.h"
 
@@ -46,14 +50,18 @@
 #undef private
 #undef protected
 
-#ifndef RT_ORACLE_SHARED_RNG
-#error "build with -include ref_shim.h (shared-RNG oracle)"
-#endif
-
 // ---------------------------------------------------------------- the engine behind `gen`
+// Two builds of this file (oracle/Makefile):
+//   _ref/libref_cb.so     -include ref_shim.h: `gen` is the counter-based engine, one stream per unit of work
+//   _ref/libref_stock.so  no shim: `gen` stays the reference's std::default_random_engine (minstd_rand0,
+//                         seed 1) consumed serially; set_stream() is a no-op.  A full-frame ref_render in
+//                         the reference's loop order (sample, row, column) then reproduces the stock
+//                         binary's output.ppm byte for byte -- the test that pins this harness (include
+//                         order, restated loops, composite) against the unmodified program.
+static uint64_t g_words_drawn = 0;
+#ifdef RT_ORACLE_SHARED_RNG
 static uint64_t g_key = 0;
 static uint32_t g_ctr = 0;
-static uint64_t g_words_drawn = 0;
 std::cb_engine::result_type std::cb_engine::operator()() {
   ++g_words_drawn;
   return rto_word(g_key, g_ctr++);
@@ -62,6 +70,12 @@ static inline void set_stream(uint64_t seed, uint64_t domain, uint64_t index) {
   g_key = rto_stream_key(seed, domain, index);
   g_ctr = 0;
 }
+extern "C" int ref_shared_rng(void) { return 1; }
+#else
+static inline void set_stream(uint64_t, uint64_t, uint64_t) {}
+extern "C" int ref_shared_rng(void) { return 0; }
+extern "C" void ref_reseed(unsigned seed) { gen.seed(seed); }
+#endif
 
 namespace {
 struct RefScene {

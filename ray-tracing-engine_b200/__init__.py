@@ -85,6 +85,36 @@ class Scene:
                       self.lights_ctor, self.cam):
                 a.tofile(fh)
 
+    @classmethod
+    def build(cls, width, height, mesh_dir="../meshes", input_off=None, subdivisions=0):
+        """The scene main() assembles (source/Main.cpp:165-208), built by the C++ host code
+        (host/scene_host.cpp through lib/librt_host.so): Cornell box, 3 lights, the two meshes loaded
+        from `mesh_dir`; `input_off` replaces cube_tri.off; `subdivisions` midpoint-subdivides it."""
+        lib = _host_lib()
+        h = lib.rth_scene_create(str(mesh_dir).encode(), (input_off or "").encode(), int(subdivisions), int(width),
+                                 int(height))
+        if not h:
+            raise RuntimeError(lib.rth_last_error().decode(errors="replace"))
+        try:
+            cnt = np.zeros(4, np.int32)
+            lib.rth_scene_counts(h, _capi.ptr(cnt))
+            V, T, M, L = (int(v) for v in cnt)
+            f, i = np.float32, np.int32
+            pos, nrm, tri = np.zeros((V, 3), f), np.zeros((V, 3), f), np.zeros((T, 3), i)
+            mto, mvo = np.zeros(M + 1, i), np.zeros(M + 1, i)
+            mats, lights, cam = np.zeros((M, 8), f), np.zeros((L, 21), f), np.zeros(12, f)
+            lib.rth_scene_get(h, *[_capi.ptr(a) for a in (pos, nrm, tri, mto, mvo, mats, lights, cam)])
+        finally:
+            lib.rth_scene_destroy(h)
+        return cls(pos, nrm, tri, mto, mvo, mats, lights, cam, width, height)
+
+    def with_size(self, width, height):
+        """Same geometry, camera rebuilt for another aspect ratio (source/Main.cpp:169-170)."""
+        cam = np.zeros(12, np.float32)
+        _host_lib().rth_camera(int(width), int(height), _capi.ptr(cam))
+        return Scene(self.pos, self.nrm, self.tri, self.mesh_tri_off, self.mesh_vtx_off, self.mats, self.lights, cam,
+                     width, height, self.lights_ctor)
+
     def tri_mesh(self):
         out = np.zeros(self.T, np.int32)
         for m in range(self.M):
@@ -99,6 +129,45 @@ class Scene:
         s.materials, s.lights = _capi.ptr(self.mats), _capi.ptr(self.lights)
         C.memmove(C.byref(s.camera), self.cam.ctypes.data, 48)
         return s
+
+
+_hostlib = None
+
+
+def _host_lib():
+    """lib/librt_host.so: the C++ host code (OFF loader, scene assembly, camera) shared with bin/RayTracer."""
+    global _hostlib
+    if _hostlib is None:
+        path = os.path.join(_capi.PKG_DIR, "lib", "librt_host.so")
+        if not os.path.exists(path):
+            raise ImportError(f"{path} is missing: run make -C ray-tracing-engine_b200")
+        lib = C.CDLL(path)
+        vp = C.c_void_p
+        lib.rth_last_error.restype = C.c_char_p
+        lib.rth_scene_create.restype = vp
+        lib.rth_scene_create.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_int]
+        lib.rth_scene_destroy.argtypes = [vp]
+        lib.rth_scene_counts.argtypes = [vp, vp]
+        lib.rth_scene_get.argtypes = [vp] * 9
+        lib.rth_load_off.restype = C.c_int
+        lib.rth_load_off.argtypes = [C.c_char_p, C.c_int, vp, vp, vp, vp]
+        lib.rth_camera.argtypes = [C.c_int, C.c_int, vp]
+        lib.rth_background.argtypes = [C.c_int, C.c_int, vp]
+        lib.rth_save_ppm.argtypes = [C.c_char_p, C.c_int, C.c_int, vp]
+        _hostlib = lib
+    return _hostlib
+
+
+def load_off(path, subdivisions=0):
+    """Mesh::loadOFF (source/Mesh.h:57-90) through the C++ host: (positions, normals, triangles)."""
+    lib = _host_lib()
+    cnt = np.zeros(2, np.int32)
+    if lib.rth_load_off(str(path).encode(), int(subdivisions), _capi.ptr(cnt), None, None, None) != 0:
+        raise RuntimeError(lib.rth_last_error().decode(errors="replace"))
+    pos, nrm, tri = np.zeros((cnt[0], 3), np.float32), np.zeros((cnt[0], 3), np.float32), np.zeros((cnt[1], 3), np.int32)
+    lib.rth_load_off(str(path).encode(), int(subdivisions), _capi.ptr(cnt), _capi.ptr(pos), _capi.ptr(nrm),
+                     _capi.ptr(tri))
+    return pos, nrm, tri
 
 
 class Image:
@@ -339,3 +408,13 @@ class Renderer:
 
 def device_count():
     return _capi.load().rt_device_count()
+
+
+def shard_pixels(width, height, shard_rank, shard_count, shard_tile=16):
+    """Pixel indices (y*W + x) owned by a shard of the interleaved-tile partition (host only, no GPU)."""
+    p = _params(width, height, 1, 0, shard_rank=shard_rank, shard_count=shard_count, shard_tile=shard_tile)
+    n = C.c_int64()
+    _capi.check(_capi.load().rt_shard_pixels(C.byref(p), None, 0, C.byref(n)))
+    out = np.zeros(n.value, np.int32)
+    _capi.check(_capi.load().rt_shard_pixels(C.byref(p), _capi.ptr(out), n.value, C.byref(n)))
+    return out

@@ -87,6 +87,7 @@ SYMBOLS = {
     "rt_get_photons": (C.c_int, [_vp, _vp, _i64, _vp]),
     "rt_knn": (C.c_int, [_vp, _vp, _i64, _i32, _vp]),
     "rt_get_kdtree": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64]),
+    "rt_shard_pixels": (C.c_int, [C.POINTER(rt_params), _vp, _i64, _vp]),
     "rt_get_stats": (C.c_int, [_vp, C.POINTER(rt_stats)]),
     "rt_reset_stats": (C.c_int, [_vp]),
     "rt_get_bvh": (C.c_int, [_vp, _vp, _i64, _vp, _vp]),

@@ -894,6 +894,20 @@ int rt_knn(rt_ctx* c, const float* queries, int64_t n, int32_t k, int32_t* node_
   return RT_OK;
 }
 
+int rt_shard_pixels(const rt_params* p, int32_t* out, int64_t capacity, int64_t* count) {
+  int rc = validate_params(p);
+  if (rc) return rc;
+  if (!count) return fail(RT_ERR_INVALID, "null count");
+  std::vector<int> map;
+  build_pix_map(*p, map);
+  *count = (int64_t)map.size();
+  if (out) {
+    if (capacity < (int64_t)map.size()) return fail(RT_ERR_INVALID, "capacity too small");
+    std::memcpy(out, map.data(), map.size() * sizeof(int));
+  }
+  return RT_OK;
+}
+
 int rt_get_stats(rt_ctx* c, rt_stats* out) {
   if (!c || !out) return fail(RT_ERR_INVALID, "null argument");
   *out = c->stats;

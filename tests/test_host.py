@@ -1,0 +1,195 @@
+"""CPU tests of the boundary and the host side (no GPU, no compute calls)."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import GOLD, ROOT, scene_path
+
+import ray_tracing_engine_b200 as rt
+from ray_tracing_engine_b200 import _capi
+
+MESH_DIRS = ["/root/reference/meshes", os.path.join(ROOT, "oracle", "_ref", "meshes")]
+MESHES = next((d for d in MESH_DIRS if os.path.exists(os.path.join(d, "cube_tri.off"))), None)
+needs_meshes = pytest.mark.skipif(MESHES is None, reason="the reference's .off assets are not available here")
+
+
+def beq(a, b):
+    a, b = np.ascontiguousarray(a, np.float32), np.ascontiguousarray(b, np.float32)
+    return a.shape == b.shape and bool((a.view(np.uint32) == b.view(np.uint32)).all())
+
+
+# ----------------------------------------------------------------------------- the C ABI
+def header_functions():
+    src = open(os.path.join(ROOT, "include", "rt_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(rt_[a-z_0-9]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _capi.load()
+    declared = header_functions()
+    assert len(declared) >= 20
+    for name in declared:
+        assert hasattr(lib, name), f"{name} is declared in include/rt_b200.h but not exported"
+    assert sorted(_capi.SYMBOLS) == declared, "the ctypes table and the header disagree"
+
+
+def test_struct_layouts_match_the_header():
+    assert C.sizeof(_capi.rt_material) == 32 and C.sizeof(_capi.rt_light) == 84 and C.sizeof(_capi.rt_camera) == 48
+    assert C.sizeof(_capi.rt_params) == 64 and _capi.rt_params.seed.offset == 24
+    assert C.sizeof(_capi.rt_scene) == 16 + 7 * 8 + 48
+    assert _capi.rt_stats.device_ms.offset == 64
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device the product refuses to run (it never routes through the oracle)."""
+    if rt.device_count() > 0:
+        pytest.skip("a GPU is present")
+    scene = rt.Scene.load(scene_path("stock"))
+    with pytest.raises(rt.RtError) as e:
+        rt.Renderer(scene, 1, 0)
+    assert e.value.code == _capi.RT_ERR_NO_DEVICE
+    src = "".join(open(os.path.join(ROOT, "ray-tracing-engine_b200", f)).read()
+                  for f in ("__init__.py", "_capi.py", "distributed.py"))
+    assert "oracle" not in re.sub(r'""".*?"""', "", src, flags=re.S).replace("# ", ""), \
+        "the product package must not import the oracle"
+    out = subprocess.run(["ldd", _capi.LIB_PATH], capture_output=True, text=True).stdout
+    assert "oracle" not in out
+
+
+def test_parameter_validation():
+    lib = _capi.load()
+    scene = rt.Scene.load(scene_path("stock"))
+    cs = scene._as_c()
+    ctx = C.c_void_p()
+    for kw, text in ((dict(width=0), "width"), (dict(num_photons=10, k=0), "k must"), (dict(num_photons=10, k=65), "k must"),
+                     (dict(shard_count=2, shard_rank=2), "shard_rank"), (dict(num_rays=4, sample_first=3, sample_count=2), "sample")):
+        base = dict(width=8, height=8, num_rays=1, mode=0)
+        base.update(kw)
+        p = rt._params(**base)
+        assert lib.rt_create(C.byref(cs), C.byref(p), 0, C.byref(ctx)) == _capi.RT_ERR_INVALID
+        assert text in lib.rt_last_error().decode()
+    assert lib.rt_render(None, None) == _capi.RT_ERR_INVALID
+
+
+def test_composite_formula():
+    """rt_composite is host code: saveImage = update/N + background*(N-counter)/N (Renderer.cpp:262-265)."""
+    from oracle import oracle as O
+    g = np.random.default_rng(0)
+    s = g.uniform(0, 5, (7, 9, 3)).astype(np.float32)
+    c = g.integers(0, 6, (7, 9)).astype(np.int32)
+    bg = g.uniform(0, 1, (7, 9, 3)).astype(np.float32)
+    assert beq(rt.Renderer.composite(5, s, c, bg), O.PortOracle().composite(5, s, c, bg))
+
+
+def test_shard_pixels_partition():
+    for (w, h, n, tile) in ((420, 420, 8, 16), (100, 70, 3, 16), (33, 17, 4, 8), (5, 5, 7, 16)):
+        parts = [rt.shard_pixels(w, h, r, n, tile) for r in range(n)]
+        allpix = np.concatenate(parts)
+        assert len(allpix) == w * h and len(np.unique(allpix)) == w * h
+        for r, part in enumerate(parts):
+            x, y = part % w, part // w
+            assert ((((y // tile) * ((w + tile - 1) // tile) + x // tile) % n) == r).all()
+    assert len(rt.shard_pixels(64, 64, 0, 1)) == 64 * 64
+
+
+# ----------------------------------------------------------------------------- host mirror
+def test_scene_file_roundtrip(tmp_path):
+    s = rt.Scene.load(scene_path("lowres"))
+    p = str(tmp_path / "x.rtscene")
+    s.save(p)
+    t = rt.Scene.load(p)
+    for k in ("pos", "nrm", "mats", "lights", "cam"):
+        assert beq(getattr(s, k), getattr(t, k))
+    assert (s.tri == t.tri).all() and (s.tri_mesh() == t.tri_mesh()).all() and s.T == 1222
+
+
+@needs_meshes
+@pytest.mark.parametrize("name,off", [("stock", None), ("lowres", "example_low_res.off"), ("example", "example.off")])
+def test_host_scene_assembly_matches_reference(name, off):
+    """host/scene_host.cpp (OFF loader, normals, rotation, Cornell box, lights, camera) vs the scene the
+    reference's own main() code assembles (golden dump): every float bit-identical."""
+    g = rt.Scene.load(scene_path(name))
+    s = rt.Scene.build(420, 420, MESHES, os.path.join(MESHES, off) if off else None)
+    for k in ("pos", "nrm", "mats", "lights", "cam"):
+        assert beq(getattr(s, k), getattr(g, k)), k
+    assert (s.tri == g.tri).all() and (s.mesh_tri_off == g.mesh_tri_off).all() and (s.mesh_vtx_off == g.mesh_vtx_off).all()
+
+
+def test_camera_for_other_aspect(gold):
+    cam = rt.Scene.load(scene_path("stock")).with_size(380, 270).cam
+    assert beq(cam, gold("camera_380x270.npz")["cam"])
+    # golden values of SURVEY.md 8a-C for aspect 1
+    np.testing.assert_allclose(rt.Scene.load(scene_path("stock")).cam[3:9],
+                               [-0.379017353, -0.209387183, 1.55804682, 1.14500153, 0, -0.149348021], rtol=2e-7)
+
+
+def test_off_loader_on_own_fixture(gold, tmp_path):
+    g = gold("fixture_mixed_loaded.npz")
+    pos, nrm, tri = rt.load_off(os.path.join(GOLD, "fixture_mixed.off"))
+    assert beq(pos, g["pos"]) and beq(nrm, g["nrm"]) and (tri == g["tri"]).all()
+    assert len(tri) == 1 + 2 + 3 + 1  # triangle, quad -> 2, pentagon -> 3, triangle
+    with pytest.raises(RuntimeError) as e:
+        rt.load_off(str(tmp_path / "missing.off"))
+    assert "Error Loading OFF file: Error loading OFF file:" in str(e.value)  # Mesh.h:62-64,84-88
+    # CRLF line endings, as in the reference's example meshes (which carry no comment line: the
+    # reference's skipHashCommentLine does not step over '\r', Mesh.h:126-134, and neither do we)
+    lines = [l for l in open(os.path.join(GOLD, "fixture_mixed.off"), "rb").read().split(b"\n") if not l.startswith(b"#")]
+    crlf = tmp_path / "crlf.off"
+    crlf.write_bytes(b"\r\n".join(lines))
+    p2, n2, t2 = rt.load_off(str(crlf))
+    assert beq(p2, pos) and (t2 == tri).all()
+
+
+def test_subdivision_counts_and_midpoints():
+    pos0, _, tri0 = rt.load_off(os.path.join(GOLD, "fixture_mixed.off"))
+    pos, nrm, tri = rt.load_off(os.path.join(GOLD, "fixture_mixed.off"), subdivisions=2)
+    assert len(tri) == 16 * len(tri0)
+    assert beq(pos[:len(pos0)], pos0)
+    a, b = pos0[tri0[0][0]], pos0[tri0[0][1]]
+    assert beq(pos[len(pos0)], np.float32(0.5) * (a + b))  # first new vertex = midpoint of the first edge
+    np.testing.assert_allclose(np.linalg.norm(nrm, axis=1), 1, atol=1e-6)
+
+
+@needs_meshes
+def test_synthetic_million_triangle_scene():
+    s = rt.Scene.build(1920, 1080, MESHES, os.path.join(MESHES, "example_low_res.off"), 5)
+    assert s.T == 1200 * 4 ** 5 + 22 and s.V == 614785 + 28  # SURVEY.md 8d cfg 5
+
+
+def test_image_background_and_ppm(gold, tmp_path):
+    g = gold("background.npz")
+    assert beq(rt.Image(420, 420).fillBackground().pixels[:, 0, :], g["rows_420"])
+    assert beq(rt.Image(380, 270).fillBackground().pixels[:, 7, :], g["rows_270"])
+    img = rt.Image(3, 2)
+    img.pixels[:] = np.float32([[[0, 0.5, 1], [0.999, 0.2, 0.1], [1, 1, 1]], [[0.004, 0.0039, 0.3], [0.25, 0.75, 0.6], [0, 0, 0]]])
+    path = str(tmp_path / "a.ppm")
+    img.savePPM(path)
+    assert open(path).read() == "P3\n3 2\n255\n0 127 255 254 51 25 255 255 255 1 0 76 63 191 153 0 0 0 \n"
+    # the C++ host writer produces the same bytes
+    lib = rt._host_lib()
+    p2 = str(tmp_path / "b.ppm")
+    lib.rth_save_ppm(p2.encode(), 3, 2, _capi.ptr(img.pixels))
+    assert open(p2).read() == open(path).read()
+
+
+def test_cli_banner_and_errors(tmp_path):
+    """bin/RayTracer keeps the reference's command line (CommandLine.h:47-97): banner, defaults, errors."""
+    exe = os.path.join(ROOT, "ray-tracing-engine_b200", "bin", "RayTracer")
+    if not os.path.exists(exe):
+        pytest.skip("CLI not built")
+    r = subprocess.run([exe, "-bogus", "1"], capture_output=True, text=True, cwd=tmp_path)
+    assert r.returncode == 1 and "Unknown argument <-bogus>" in r.stderr and "USAGE:" in r.stderr
+    r = subprocess.run([exe, "-width"], capture_output=True, text=True, cwd=tmp_path)
+    assert r.returncode == 1 and "Missing argument" in r.stderr
+    r = subprocess.run([exe, "-help"], capture_output=True, text=True, cwd=tmp_path)
+    assert r.returncode == 0 and "USAGE:" in r.stderr
+    r = subprocess.run([exe, "-m", "7", "-p", "100", "-k", "3", "-meshdir", "/nonexistent"], capture_output=True,
+                       text=True, cwd=tmp_path)
+    assert "Mode: Ray tracing" in r.stdout and "Photon map ON with 100 photons. Number of searched neighbours equals 3" in r.stdout
+    assert "width: 380, height: 270" in r.stdout and "Output image filename: output.ppm" in r.stdout
+    assert r.returncode == 1 and "Error Loading OFF file: Error loading OFF file: /nonexistent/cube_tri.off" in r.stderr

@@ -1,0 +1,253 @@
+"""CPU tests of the oracles (no GPU).
+
+1. The CPU restatement (oracle/port) against the committed golden vectors of the unmodified reference.
+2. The restatement against the reference itself, live, bit for bit (needs oracle/_ref, i.e. the build
+   container or the prebuilt files that travel to the GPU box) -- on inputs the goldens do not hold.
+3. The reference harness against the stock reference binary: with the reference's own serial engine
+   the harness's re-stated loops must reproduce the binary's output.ppm byte for byte.
+"""
+import hashlib
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import GOLD, scene_path
+from oracle import oracle as O
+
+SEED = 1
+needs_ref = pytest.mark.skipif(not O.have_ref(), reason="oracle/_ref not built (no /root/reference here)")
+
+
+def beq(a, b):
+    a, b = np.ascontiguousarray(a), np.ascontiguousarray(b)
+    if a.shape != b.shape:
+        return False
+    if a.dtype.kind == "f":
+        return bool((a.view(np.uint32 if a.itemsize == 4 else np.uint64) ==
+                     b.astype(a.dtype).view(np.uint32 if a.itemsize == 4 else np.uint64)).all())
+    return bool((a == b).all())
+
+
+def port_for(name):
+    return O.PortOracle(O.FlatScene.load(scene_path(name)))
+
+
+# ------------------------------------------------------------------ 1. restatement vs golden vectors
+def test_rng_contract_golden(gold):
+    g = gold("rng.npz")
+    p = O.PortOracle()
+    for i in range(3):
+        idx = int(g[f"idx_{i}"][0])
+        assert beq(p.rng_words(SEED, O.DOMAIN_PIXEL, idx, 64), g[f"words_{i}"])
+        assert beq(p.rng_uniform_float(SEED, O.DOMAIN_PIXEL, idx, 256, -0.01, 0.01), g[f"uf_{i}"])
+        assert beq(p.rng_uniform_double(SEED, O.DOMAIN_PHOTON, idx, 256, 0.0, 1.0000000278275352), g[f"ud_{i}"])
+
+
+def test_rng_contract_by_hand():
+    """The contract restated in pure Python integers (oracle/rng_contract.h)."""
+    M = (1 << 64) - 1
+
+    def mix(z):
+        z ^= z >> 30
+        z = (z * 0xBF58476D1CE4E5B9) & M
+        z ^= z >> 27
+        z = (z * 0x94D049BB133111EB) & M
+        return z ^ (z >> 31)
+    G = 0x9E3779B97F4A7C15
+    seed, domain, index = 7, 2, 123456789
+    key = mix(mix((seed + G) & M) ^ ((domain << 56) | index))
+    want = []
+    for c in range(10):
+        pr = mix((key + ((c >> 1) + 1) * G) & M)
+        want.append((pr >> 32) if c & 1 else (pr & 0xFFFFFFFF))
+    got = O.PortOracle().rng_words(seed, domain, index, 10)
+    assert got.tolist() == want
+    # canonical float: float(w)/2^32 clamped below 1
+    f = O.PortOracle().rng_uniform_float(seed, domain, index, 10, 0.0, 1.0)
+    assert beq(f, np.minimum(np.array(want, np.uint32).astype(np.float32) / np.float32(2 ** 32),
+                             np.nextafter(np.float32(1), np.float32(0))))
+
+
+def test_sampling_golden(gold):
+    g = gold("sampling.npz")
+    p = port_for("stock")
+    assert beq(p.hsphere(SEED, O.DOMAIN_PHOTON, 1000, g["normals"]), g["hsphere"])
+    assert beq(p.jitter(SEED, O.DOMAIN_PIXEL, 0, 4096, 0, 1), g["jitter_0_1"])
+    assert beq(p.jitter(SEED, O.DOMAIN_PIXEL, 0, 4096, 77, 128), g["jitter_77_128"])
+    assert beq(p.jitter(SEED, O.DOMAIN_PIXEL, 0, 4096, 1000, 1024), g["jitter_1000_1024"])
+    # RayTracer.h:111-115 quirk kept: N=128 -> d=11, rows up to 11 => y in [1, 1.09) for the last samples
+    assert g["jitter_77_128"][:, 1].min() >= 7 / 11 and p.jitter(SEED, 1, 0, 8, 127, 128)[:, 1].min() >= 1.0
+    for l in range(3):
+        assert beq(p.light_sample(l, SEED, O.DOMAIN_PIXEL, 0, 4096), g[f"light_{l}"])
+        assert beq(p.light_eval(l, g["pts"]), g[f"light_eval_{l}"])
+    assert beq(p.camera_rays(g["cam_xy"], g["cam_shift"]), g["cam_rays"])
+
+
+def test_bsdf_golden(gold):
+    g = gold("bsdf.npz")
+    p = O.PortOracle()
+    for m in range(5):
+        out, want = p.bsdf(g["mats"][m], g["inputs"]), g[f"bsdf_{m}"]
+        nan = np.isnan(want)
+        assert (np.isnan(out) == nan).all() and beq(np.nan_to_num(out), np.nan_to_num(want))
+    # hand-checked values of SURVEY.md 8a-B (gold cube material, walls material)
+    np.testing.assert_allclose(g["bsdf_3"][0], [0.720003963, 0.623214185, 0.42272082], rtol=1e-6)
+    np.testing.assert_allclose(g["bsdf_0"][0], [0.306084782, 0.306084782, 0.286986172], rtol=1e-6)
+
+
+@pytest.mark.parametrize("name,stride", [("stock", 1), ("lowres", 2), ("example", 4)])
+def test_trace_golden(gold, name, stride):
+    g = gold(f"trace_{name}.npz")
+    h = port_for(name).trace(g["rays"][::stride])
+    assert beq(h["hit"], g["hit"][::stride]) and beq(h["mesh"], g["mesh"][::stride])
+    assert beq(h["tri3"], g["tri3"][::stride]) and beq(h["uvd"], g["uvd"][::stride])
+
+
+@pytest.mark.parametrize("case,name", [("stock_m1_N4_win", "stock"), ("lowres_m0_N1_win", "lowres"),
+                                       ("lowres_m1_N2_win", "lowres")])
+def test_render_windows_golden(gold, case, name):
+    g = gold(f"render_{case}.npz")
+    r = port_for(name).render(int(g["N"][0]), int(g["mode"][0]), SEED, window=tuple(g["window"]), want_samples=True)
+    assert beq(r["samples"], g["samples"]) and beq(r["found"], g["found"])
+    assert beq(r["sum_rgb"], g["sum_rgb"]) and beq(r["counter"], g["counter"])
+
+
+def test_render_full_frame_golden(gold):
+    g = gold("render_stock_m0_N1.npz")
+    p = port_for("stock")
+    p.counters(reset=True)
+    r = p.render(1, 0, SEED, threads=4)
+    assert beq(r["sum_rgb"], g["sum_rgb"]) and beq(r["counter"], g["counter"])
+    img = p.composite(1, r["sum_rgb"], r["counter"], p.background(420, 420))
+    assert beq((np.float32(255) * img).astype(np.uint32).astype(np.uint8), g["image8"])
+    assert p.counters(reset=True)["rays"] == 705600  # 176 400 x 4 rays
+
+
+def test_photons_kdtree_knn_golden(gold):
+    g = gold("photons.npz")
+    p = port_for("stock")
+    pm = p.photon_map_create(3000, SEED)
+    plist, hist = pm.get()
+    assert beq(plist, g["list"]) and beq(hist, g["hist"])
+    nodes, left, right, root = pm.layout()
+    assert beq(nodes, g["nodes"]) and beq(left, g["left"]) and beq(right, g["right"]) and root == int(g["root"][0])
+    for k in (1, 5, 10, 50):
+        res, visited = pm.knn(g["queries"], k)
+        assert beq(res[:, :, :3], g[f"knn_{k}"]) and beq(visited.astype(np.int32), g[f"visited_{k}"])
+    # sharded emission concatenates to the same list (the multi-GPU contract)
+    a, b = p.photon_map_create(3000, SEED, 0, 400).get()[0], p.photon_map_create(3000, SEED, 400, 600).get()[0]
+    assert len(a) + len(b) == len(plist)
+    with pytest.raises(RuntimeError):
+        pm.knn(g["queries"][:1], len(plist) + 1)  # kdtree.h:182-183
+
+
+def test_photon_render_golden(gold):
+    ph = gold("photons.npz")
+    p = port_for("stock")
+    pm = p.photon_map_from_list(ph["list"])
+    for case in ("stock_m0_p3000_k10_win", "stock_m1_p3000_k5_N2_win"):
+        g = gold(f"render_{case}.npz")
+        r = p.render(int(g["N"][0]), int(g["mode"][0]), SEED, num_photons=3000, k=int(g["k"][0]), photon_map=pm,
+                     window=tuple(g["window"]), want_samples=True)
+        assert beq(r["samples"], g["samples"]) and beq(r["found"], g["found"])
+
+
+def test_stock_md5_recorded():
+    txt = open(os.path.join(GOLD, "stock_binary_md5.txt")).read()
+    assert txt.startswith("036d13f6d213e36061f97b32db7ba3fe")
+
+
+# ------------------------------------------------------------------ 2. restatement vs the reference, live
+@needs_ref
+@pytest.mark.parametrize("w,h", [(64, 48), (33, 57)])
+def test_port_equals_reference_live(w, h):
+    ref = O.RefOracle()
+    flat = ref.create_scene(w, h)
+    port = O.PortOracle(flat)
+    g = np.random.default_rng(w * 1000 + h)
+    xy = np.stack(np.meshgrid(np.arange(w), np.arange(h)), -1).reshape(-1, 2)
+    sh = g.uniform(0, 1, (len(xy), 2)).astype(np.float32)
+    rays = ref.camera_rays(xy, sh)
+    assert beq(rays, port.camera_rays(xy, sh))
+    rays = np.concatenate([rays, np.concatenate([g.uniform(-1.5, 1.5, (4000, 3)), g.normal(size=(4000, 3))], 1)
+                           .astype(np.float32)])
+    a, b = ref.trace(rays), port.trace(rays)
+    assert all(beq(a[k], b[k]) for k in ("hit", "mesh", "tri3", "uvd"))
+    tri = g.normal(size=(20000, 15)).astype(np.float32)
+    fa, ua = ref.triangle_intersect(tri)
+    fb, ub = port.triangle_intersect(tri)
+    assert beq(fa, fb) and beq(ua, ub)  # u, v, t of misses too (Ray.cpp:17-20 writes them before the tests)
+    for mode, N in ((0, 2), (1, 3)):
+        A = ref.render(N, mode, 5, want_samples=True)
+        B = port.render(N, mode, 5, want_samples=True)
+        assert all(beq(A[k], B[k]) for k in ("samples", "found", "sum_rgb", "counter"))
+    bg = ref.background(w, h)
+    assert beq(bg, port.background(w, h))
+    assert beq(ref.composite(3, A["sum_rgb"], A["counter"], bg), port.composite(3, B["sum_rgb"], B["counter"], bg))
+    pa, pb = ref.photon_map_create(2000, 9), port.photon_map_create(2000, 9)
+    assert beq(pa.get()[0], pb.get()[0]) and beq(pa.get()[1], pb.get()[1])
+    assert all(beq(x, y) for x, y in zip(pa.layout()[:3], pb.layout()[:3]))
+    q = g.uniform(-1.5, 1.5, (500, 3)).astype(np.float32)
+    for k in (1, 7, 33):
+        (ra, va), (rb, vb) = pa.knn(q, k), pb.knn(q, k)
+        assert beq(ra, rb) and beq(va, vb)
+    for mode in (0, 1):
+        A = ref.render(2, mode, 5, num_photons=2000, k=7, photon_map=pa, want_samples=True)
+        B = port.render(2, mode, 5, num_photons=2000, k=7, photon_map=pb, want_samples=True)
+        assert beq(A["samples"], B["samples"]) and beq(A["found"], B["found"])
+
+
+@needs_ref
+def test_port_equals_reference_on_custom_mesh():
+    meshes = O.REF_MESHES if os.path.isdir(O.REF_MESHES) else "/root/reference/meshes"
+    ref = O.RefOracle()
+    flat = ref.create_scene(48, 48, custom_off=os.path.join(meshes, "example_low_res.off"), meshdir=meshes)
+    port = O.PortOracle(flat)
+    A = ref.render(1, 1, 3, window=(16, 16, 32, 32), want_samples=True)
+    B = port.render(1, 1, 3, window=(16, 16, 32, 32), want_samples=True)
+    assert beq(A["samples"], B["samples"])
+    # handing the flat scene back to the reference classes reproduces the same render
+    ref2 = O.RefOracle()
+    ref2.set_scene(flat)
+    assert beq(ref2.flatten(48, 48).lights, flat.lights), "light bases are host-recomputable from the ctor args"
+    C = ref2.render(1, 1, 3, window=(16, 16, 32, 32), want_samples=True)
+    assert beq(A["samples"], C["samples"])
+
+
+# ------------------------------------------------------------------ 3. harness vs the stock binary
+def run_stock_binary(args, tmp):
+    """The unmodified reference program; it resolves ../meshes from its cwd (Main.cpp:186-187)."""
+    build = os.path.join(tmp, "build")
+    os.makedirs(build, exist_ok=True)
+    link = os.path.join(tmp, "meshes")
+    if not os.path.exists(link):
+        os.symlink(O.REF_MESHES if os.path.isdir(O.REF_MESHES) else "/root/reference/meshes", link)
+    subprocess.run([O.REF_BIN] + args, cwd=build, check=True, stdout=subprocess.DEVNULL)
+    return open(os.path.join(build, "output.ppm"), "rb").read()
+
+
+@needs_ref
+@pytest.mark.parametrize("w,h,N,mode,p,k", [(420, 420, 1, 0, 0, 0), (64, 48, 3, 1, 0, 0), (40, 30, 2, 0, 900, 5),
+                                            (40, 30, 2, 1, 900, 7)])
+def test_harness_reproduces_stock_binary(tmp_path, w, h, N, mode, p, k):
+    """With the reference's own engine (serial minstd_rand0, seed 1) the harness's re-stated emission loop,
+    pixel loop and composite must give the stock binary's PPM byte for byte."""
+    if not os.path.exists(O.REF_STOCK_LIB) or not os.path.exists(O.REF_BIN):
+        pytest.skip("stock-RNG harness / stock binary not built")
+    args = ["-width", str(w), "-height", str(h), "-N", str(N), "-m", str(mode)]
+    if p:
+        args += ["-p", str(p), "-k", str(k)]
+    want = run_stock_binary(args, str(tmp_path))
+    if (w, h, N, mode, p) == (420, 420, 1, 0, 0):
+        assert hashlib.md5(want).hexdigest() == "036d13f6d213e36061f97b32db7ba3fe"
+    ref = O.RefOracle(stock_rng=True)
+    ref.lib.ref_reseed(1)
+    ref.create_scene(w, h)
+    pm = ref.photon_map_create(p, 0) if p else None  # Renderer.cpp:209: emission first, same engine
+    r = ref.render(N, mode, 0, num_photons=p, k=k, photon_map=pm)
+    img = ref.composite(N, r["sum_rgb"], r["counter"], ref.background(w, h))
+    out = os.path.join(str(tmp_path), "harness.ppm")
+    ref.save_ppm(img, out)
+    assert open(out, "rb").read() == want
