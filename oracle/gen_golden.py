@@ -52,6 +52,11 @@ def scenes():
     # non-square camera (the CLI default 380x270) for the host-side camera test
     flat = ref.create_scene(380, 270)
     save("camera_380x270.npz", cam=flat.cam)
+    out = {}
+    for key, f in (("cube_tri", "cube_tri.off"), ("cube_tri2", "cube_tri2.off"), ("example_low_res", "example_low_res.off")):
+        pos, nrm, tri = ref.load_off(f"{MESHES}/{f}")
+        out[key + "_pos"], out[key + "_tri"] = pos, tri
+    save("meshes_loaded.npz", **out)
     save("background.npz", rows_420=ref.background(420, 420)[:, 0, :], rows_270=ref.background(380, 270)[:, 0, :])
     # the reference's OFF loader on our own tiny fixture (quads + comment + polygon fan)
     pos, nrm, tri = ref.load_off(os.path.join(GOLD, "fixture_mixed.off"))

@@ -22,6 +22,7 @@
 // No tensor-core work exists on this path (nothing is a dense contraction): the kernels are
 // pointer-chasing traversals bounded by L1/L2 latency and the fp32/ALU issue rate.
 #include <limits.h>
+#include <stdlib.h>
 
 #include "kernels.h"
 
@@ -34,12 +35,89 @@ constexpr int kRefillBelow = 22;  // refill a warp's idle lanes when fewer lanes
 // ----------------------------------------------------------------------------------------------
 // k_trace: persistent warps, one ray per lane, lanes refilled from the queue as their rays finish.
 // Shared memory: per thread a stack of (node ref, tnear) pairs, [depth][kBlock] ints each.
+//
+// Tuning knobs (rt_set_tuning / RT_TUNING env, measured on B200 -- see DESIGN.md section 4):
+//   LEAFB  > 0: lanes that reach a leaf wait until at least LEAFB lanes of the warp hold a leaf (or no
+//               lane has an internal node left), so the Moller-Trumbore block is issued for many lanes
+//               at once instead of once per iteration for a few ("while-while" with a vote);
+//   MINB      : __launch_bounds__ minimum CTAs per SM (register cap -> occupancy).
 // ----------------------------------------------------------------------------------------------
-template <bool ANY, bool BLOCKED>
-__global__ void __launch_bounds__(kBlock)
-    k_trace(const DScene S, const float4* __restrict__ ro, const float4* __restrict__ rd, const unsigned* n_ptr,
-            unsigned n_fixed, float4* __restrict__ hits, unsigned char* __restrict__ occ, unsigned* fetch, int depth) {
-  extern __shared__ int s_dyn[];
+struct TraceLane {
+  unsigned idx;
+  float3 o, d, inv, oinv;
+  HitRec h;
+  int sp, cur;
+};
+
+template <bool ANY>
+RT_DI void trace_pop(TraceLane& L, const int* st_ref, const int* st_tn) {
+  L.cur = kDone;
+  while (L.sp > 0) {  // next entry whose box can still matter
+    L.sp--;
+    const int ref = st_ref[L.sp * kBlock];
+    if (ANY || __int_as_float(st_tn[L.sp * kBlock]) <= L.h.t) {
+      L.cur = ref;
+      break;
+    }
+  }
+}
+template <bool ANY>
+RT_DI void trace_write(const TraceLane& L, float4* __restrict__ hits, unsigned char* __restrict__ occ) {
+  if (ANY)
+    occ[L.idx] = (L.h.gid != 0x7fffffff) ? 1 : 0;
+  else
+    hits[L.idx] = make_float4(L.h.t, L.h.u, L.h.v, __int_as_float(L.h.gid != 0x7fffffff ? L.h.gid : -1));
+}
+// internal node: test both children, descend into the nearer hit one, push the other
+template <bool ANY>
+RT_DI void trace_box_step(const DScene& S, TraceLane& L, int* st_ref, int* st_tn) {
+  const float4 n0 = __ldg(S.nodes + 4 * L.cur), n1 = __ldg(S.nodes + 4 * L.cur + 1);
+  const float4 n2 = __ldg(S.nodes + 4 * L.cur + 2), n3 = __ldg(S.nodes + 4 * L.cur + 3);
+  float tn0, tn1;
+  const bool h0 = box_hit_fma(f3(n0.x, n0.y, n0.z), f3(n0.w, n1.x, n1.y), L.inv, L.oinv, L.h.t, tn0);
+  const bool h1 = box_hit_fma(f3(n1.z, n1.w, n2.x), f3(n2.y, n2.z, n2.w), L.inv, L.oinv, L.h.t, tn1);
+  const int c0 = __float_as_int(n3.x), c1 = __float_as_int(n3.y);
+  if (h0 && h1) {
+    const bool first0 = tn0 <= tn1;
+    st_ref[L.sp * kBlock] = first0 ? c1 : c0;
+    if (!ANY) st_tn[L.sp * kBlock] = __float_as_int(first0 ? tn1 : tn0);
+    L.sp++;
+    L.cur = first0 ? c0 : c1;
+  } else if (h0) {
+    L.cur = c0;
+  } else if (h1) {
+    L.cur = c1;
+  } else {
+    trace_pop<ANY>(L, st_ref, st_tn);
+  }
+}
+// leaf: one triangle.  Returns true when an any-hit ray is finished by this triangle.
+template <bool ANY>
+RT_DI void trace_leaf_step(const DScene& S, TraceLane& L, const int* st_ref, const int* st_tn) {
+  const int slot = ~L.cur;
+  const float4 A = __ldg(S.tris + 3 * slot), B = __ldg(S.tris + 3 * slot + 1), C = __ldg(S.tris + 3 * slot + 2);
+  float u, v, t;
+  bool stop = false;
+  if (mt_intersect(L.o, L.d, f3(A), f3(B), f3(C), u, v, t)) {
+    if (ANY) {
+      if (t > 0.f && t < FLT_MAX) {
+        stop = true;  // occluded: this ray is done
+        L.h.gid = 0;
+      }
+    } else {
+      accept_nearest(L.h, t, u, v, __float_as_int(A.w));
+    }
+  }
+  if (stop)
+    L.cur = kDone;
+  else
+    trace_pop<ANY>(L, st_ref, st_tn);
+}
+
+template <bool ANY, bool BLOCKED, int LEAFB>
+RT_DI void trace_body(const DScene& S, const float4* __restrict__ ro, const float4* __restrict__ rd,
+                      const unsigned* n_ptr, unsigned n_fixed, float4* __restrict__ hits,
+                      unsigned char* __restrict__ occ, unsigned* fetch, int depth, int* s_dyn) {
   int* st_ref = s_dyn + threadIdx.x;
   int* st_tn = s_dyn + depth * kBlock + threadIdx.x;
   const unsigned items = n_ptr ? *n_ptr : n_fixed;                  // rays (or hit points when BLOCKED)
@@ -47,18 +125,19 @@ __global__ void __launch_bounds__(kBlock)
   const unsigned lane = threadIdx.x & 31u;
   const unsigned lt_mask = (1u << lane) - 1u;
 
-  unsigned idx = 0;
-  float3 o = f3(0, 0, 0), d = f3(0, 0, 0), inv = f3(0, 0, 0), oinv = f3(0, 0, 0);
-  HitRec h;
-  h.t = FLT_MAX;
-  h.u = h.v = 0.f;
-  h.gid = 0x7fffffff;
-  int sp = 0, cur = kDone;
+  TraceLane L;
+  L.idx = 0;
+  L.o = L.d = L.inv = L.oinv = f3(0, 0, 0);
+  L.h.t = FLT_MAX;
+  L.h.u = L.h.v = 0.f;
+  L.h.gid = 0x7fffffff;
+  L.sp = 0;
+  L.cur = kDone;
   bool exhausted = false;  // warp-uniform
 
   for (;;) {
     // ---- refill idle lanes -------------------------------------------------------------------
-    const bool need = (cur == kDone);
+    const bool need = (L.cur == kDone);
     const unsigned need_mask = __ballot_sync(kFull, need);
     if (!exhausted && need_mask) {
       const unsigned cnt = __popc(need_mask);
@@ -72,86 +151,82 @@ __global__ void __launch_bounds__(kBlock)
         if (BLOCKED && valid) valid = ((my / 96u) * 32u + (my & 31u)) < items;
         if (valid) {
           const float4 a = __ldg(ro + my), b = __ldg(rd + my);
-          idx = my;
-          o = f3(a);
-          d = f3(b);
-          inv = f3(safe_inv(d.x), safe_inv(d.y), safe_inv(d.z));
-          oinv = f3(o.x * inv.x, o.y * inv.y, o.z * inv.z);
-          h.t = FLT_MAX;
-          h.u = h.v = 0.f;
-          h.gid = 0x7fffffff;
-          sp = 0;
-          cur = 0;  // root
+          L.idx = my;
+          L.o = f3(a);
+          L.d = f3(b);
+          L.inv = f3(safe_inv(L.d.x), safe_inv(L.d.y), safe_inv(L.d.z));
+          L.oinv = f3(L.o.x * L.inv.x, L.o.y * L.inv.y, L.o.z * L.inv.z);
+          L.h.t = FLT_MAX;
+          L.h.u = L.h.v = 0.f;
+          L.h.gid = 0x7fffffff;
+          L.sp = 0;
+          L.cur = 0;  // root
         }
       }
     }
-    if (__ballot_sync(kFull, cur != kDone) == 0) {
+    if (__ballot_sync(kFull, L.cur != kDone) == 0) {
       if (exhausted) break;
       continue;
     }
     // ---- traverse until the warp runs low on live rays ------------------------------------------
     for (;;) {
-      if (cur != kDone) {
-        bool finished = false;
-        if (cur >= 0) {  // internal node: test both children
-          const float4 n0 = __ldg(S.nodes + 4 * cur), n1 = __ldg(S.nodes + 4 * cur + 1);
-          const float4 n2 = __ldg(S.nodes + 4 * cur + 2), n3 = __ldg(S.nodes + 4 * cur + 3);
-          float tn0, tn1;
-          const bool h0 = box_hit_fma(f3(n0.x, n0.y, n0.z), f3(n0.w, n1.x, n1.y), inv, oinv, h.t, tn0);
-          const bool h1 = box_hit_fma(f3(n1.z, n1.w, n2.x), f3(n2.y, n2.z, n2.w), inv, oinv, h.t, tn1);
-          const int c0 = __float_as_int(n3.x), c1 = __float_as_int(n3.y);
-          if (h0 && h1) {
-            const bool first0 = tn0 <= tn1;
-            st_ref[sp * kBlock] = first0 ? c1 : c0;
-            if (!ANY) st_tn[sp * kBlock] = __float_as_int(first0 ? tn1 : tn0);
-            sp++;
-            cur = first0 ? c0 : c1;
-          } else if (h0) {
-            cur = c0;
-          } else if (h1) {
-            cur = c1;
-          } else {
-            cur = kDone;  // pop below
-          }
-        } else {  // leaf: one triangle
-          const int slot = ~cur;
-          const float4 A = __ldg(S.tris + 3 * slot), B = __ldg(S.tris + 3 * slot + 1), C = __ldg(S.tris + 3 * slot + 2);
-          float u, v, t;
-          if (mt_intersect(o, d, f3(A), f3(B), f3(C), u, v, t)) {
-            if (ANY) {
-              if (t > 0.f && t < FLT_MAX) {
-                finished = true;  // occluded: stop this ray
-                h.gid = 0;
-              }
-            } else {
-              accept_nearest(h, t, u, v, __float_as_int(A.w));
-            }
-          }
-          cur = kDone;  // pop below
-        }
-        if (cur == kDone && !finished) {  // pop the next entry whose box can still matter
-          while (sp > 0) {
-            sp--;
-            const int ref = st_ref[sp * kBlock];
-            if (ANY || __int_as_float(st_tn[sp * kBlock]) <= h.t) {
-              cur = ref;
-              break;
-            }
-          }
-        }
-        if (cur == kDone) {  // ray complete: write the result now, the lane becomes idle
-          if (ANY)
-            occ[idx] = (h.gid != 0x7fffffff) ? 1 : 0;
+      if (LEAFB == 0) {
+        if (L.cur != kDone) {
+          if (L.cur >= 0)
+            trace_box_step<ANY>(S, L, st_ref, st_tn);
           else
-            hits[idx] = make_float4(h.t, h.u, h.v, __int_as_float(h.gid != 0x7fffffff ? h.gid : -1));
+            trace_leaf_step<ANY>(S, L, st_ref, st_tn);
+          if (L.cur == kDone) trace_write<ANY>(L, hits, occ);  // ray complete, the lane becomes idle
+        }
+      } else {
+        if (L.cur >= 0) {
+          trace_box_step<ANY>(S, L, st_ref, st_tn);
+          if (L.cur == kDone) trace_write<ANY>(L, hits, occ);
+        }
+        const bool at_leaf = L.cur < 0 && L.cur != kDone;
+        const unsigned leaf_mask = __ballot_sync(kFull, at_leaf);
+        if (leaf_mask) {
+          const unsigned node_mask = __ballot_sync(kFull, L.cur >= 0);
+          if (__popc(leaf_mask) >= LEAFB || node_mask == 0) {
+            if (at_leaf) {
+              trace_leaf_step<ANY>(S, L, st_ref, st_tn);
+              if (L.cur == kDone) trace_write<ANY>(L, hits, occ);
+            }
+          }
         }
       }
-      const unsigned live = __ballot_sync(kFull, cur != kDone);
+      const unsigned live = __ballot_sync(kFull, L.cur != kDone);
       if (live == 0) break;
       if (!exhausted && __popc(live) < kRefillBelow) break;
     }
   }
 }
+
+#define RT_TRACE_KERNEL(NAME, LEAFB, MINB)                                                                          \
+  template <bool ANY, bool BLOCKED>                                                                                 \
+  __global__ void __launch_bounds__(kBlock, MINB)                                                                   \
+      NAME(const DScene S, const float4* __restrict__ ro, const float4* __restrict__ rd, const unsigned* n_ptr,    \
+           unsigned n_fixed, float4* __restrict__ hits, unsigned char* __restrict__ occ, unsigned* fetch, int depth) { \
+    extern __shared__ int s_dyn[];                                                                                  \
+    trace_body<ANY, BLOCKED, LEAFB>(S, ro, rd, n_ptr, n_fixed, hits, occ, fetch, depth, s_dyn);                     \
+  }
+// Measured on B200, cfg2 frame (profiles/r1_tuning.md): variant 0 37.4 ms, 1 33.6 ms, 2 34.1 ms,
+// 3 37.1 ms, 4 34.5 ms  ->  variant 1 is the default.
+RT_TRACE_KERNEL(k_trace_lb8, 8, 1)    // variant 1 (default): batch leaf tests, >= 8 lanes
+RT_TRACE_KERNEL(k_trace, 0, 1)        // variant 0: test leaves as they come
+RT_TRACE_KERNEL(k_trace_lb16, 16, 1)  // variant 2: >= 16 lanes
+RT_TRACE_KERNEL(k_trace_occ, 0, 12)   // variant 3: variant 0 capped to 40 registers (12 CTAs/SM)
+RT_TRACE_KERNEL(k_trace_lb8occ, 8, 12)  // variant 4
+
+static int g_trace_variant = -1;
+int trace_variant() {
+  if (g_trace_variant < 0) {
+    const char* e = getenv("RT_TRACE_VARIANT");
+    g_trace_variant = e ? atoi(e) : 1;
+  }
+  return g_trace_variant;
+}
+void set_trace_variant(int v) { g_trace_variant = v; }
 
 // RayTracer.h:27-53 exactly as written: every ray scans every triangle (parity hook, RT_FLAG_BRUTE_FORCE)
 template <bool ANY, bool BLOCKED>
@@ -176,7 +251,14 @@ size_t trace_smem_bytes(int stack_depth) { return (size_t)2 * stack_depth * kBlo
 
 int trace_ctas_per_sm(int stack_depth) {
   int n = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_trace<false, false>, kBlock, trace_smem_bytes(stack_depth));
+  const size_t sm = trace_smem_bytes(stack_depth);
+  switch (trace_variant()) {
+    case 0: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_trace<false, false>, kBlock, sm); break;
+    case 2: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_trace_lb16<false, false>, kBlock, sm); break;
+    case 3: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_trace_occ<false, false>, kBlock, sm); break;
+    case 4: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_trace_lb8occ<false, false>, kBlock, sm); break;
+    default: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_trace_lb8<false, false>, kBlock, sm); break;
+  }
   return n < 1 ? 1 : n;
 }
 
@@ -188,8 +270,16 @@ static void launch_trace_t(const DScene& S, const float4* ro, const float4* rd, 
     k_trace_brute<ANY, BLOCKED><<<grid, kBlock, 0, st>>>(S, ro, rd, n_ptr, n_fixed, hits, occ);
   } else {
     cudaMemsetAsync(fetch, 0, sizeof(unsigned), st);
-    k_trace<ANY, BLOCKED><<<grid, kBlock, trace_smem_bytes(depth), st>>>(S, ro, rd, n_ptr, n_fixed, hits, occ, fetch,
-                                                                         depth);
+    const size_t sm = trace_smem_bytes(depth);
+#define RT_LAUNCH(K) K<ANY, BLOCKED><<<grid, kBlock, sm, st>>>(S, ro, rd, n_ptr, n_fixed, hits, occ, fetch, depth)
+    switch (trace_variant()) {
+      case 0: RT_LAUNCH(k_trace); break;
+      case 2: RT_LAUNCH(k_trace_lb16); break;
+      case 3: RT_LAUNCH(k_trace_occ); break;
+      case 4: RT_LAUNCH(k_trace_lb8occ); break;
+      default: RT_LAUNCH(k_trace_lb8); break;
+    }
+#undef RT_LAUNCH
   }
 }
 
