@@ -31,21 +31,27 @@ int fail(int code, const std::string& msg) {
                   std::string(#call) + ": " + cudaGetErrorString(e_));                                \
   } while (0)
 
+// Device buffers come from the device's stream-ordered memory pool (cudaMallocAsync) with the release
+// threshold raised to "never": a context that is destroyed returns its multi-GB wavefront buffers to the
+// pool, and the next rt_create on that GPU gets them back without a driver allocation (the e2e path of
+// bench.py creates a context per frame).
+thread_local cudaStream_t g_alloc_stream = nullptr;
+
 template <typename T>
 struct DevBuf {
   T* p = nullptr;
   size_t n = 0;
   cudaError_t ensure(size_t count) {
     if (count <= n) return cudaSuccess;
-    if (p) cudaFree(p);
+    if (p) cudaFreeAsync(p, g_alloc_stream);
     p = nullptr;
     n = 0;
-    cudaError_t e = cudaMalloc((void**)&p, std::max<size_t>(count, 1) * sizeof(T));
+    cudaError_t e = cudaMallocAsync((void**)&p, std::max<size_t>(count, 1) * sizeof(T), g_alloc_stream);
     if (e == cudaSuccess) n = count;
     return e;
   }
   void release() {
-    if (p) cudaFree(p);
+    if (p) cudaFreeAsync(p, g_alloc_stream);
     p = nullptr;
     n = 0;
   }
@@ -87,6 +93,7 @@ struct rt_ctx {
   DevBuf<unsigned int> d_qcount;
   DevBuf<unsigned long long> d_counters;
   DevBuf<unsigned char> d_scratch;
+  size_t auto_paths = 0;  // cached batch-size decision (paths per wavefront batch)
   std::vector<cudaEvent_t> seg_events;  // pairs around every k_segment launch of the current render
   size_t seg_events_used = 0;
   rt_stats stats{};
@@ -97,6 +104,7 @@ namespace {
 int bind(rt_ctx* c) {
   if (!c) return fail(RT_ERR_INVALID, "null context");
   CU(cudaSetDevice(c->device));
+  g_alloc_stream = c->stream;
   return RT_OK;
 }
 
@@ -305,11 +313,14 @@ int render_to_device(rt_ctx* c, float* out_rgb_dev, int* out_cnt_dev) {
   // batch size: bounded by free HBM (kBytesPerPath of wavefront state per path) and by 2^30 paths
   int spb = p.samples_per_batch;
   if (spb <= 0) {
-    size_t free_b = 0, total_b = 0;
-    CU(cudaMemGetInfo(&free_b, &total_b));
-    size_t budget = std::min<size_t>(free_b / 2, (size_t)24 << 30);
-    size_t max_paths = std::min<size_t>(budget / kBytesPerPath, (size_t)1 << 30);
-    spb = (int)std::max<size_t>(1, std::min<size_t>(max_paths / std::max(c->npix, 1), 1 << 20));
+    // default: batches of <= 32 M paths (8.4 GB of wavefront state), fewer when HBM is short
+    if (c->auto_paths == 0) {
+      size_t free_b = 0, total_b = 0;
+      CU(cudaMemGetInfo(&free_b, &total_b));
+      size_t budget = std::min<size_t>(free_b / 2 + c->d_col0.n * kBytesPerPath, (size_t)32 << 30);
+      c->auto_paths = std::max<size_t>(1, std::min<size_t>(budget / kBytesPerPath, (size_t)32 << 20));
+    }
+    spb = (int)std::max<size_t>(1, std::min<size_t>(c->auto_paths / std::max(c->npix, 1), 1 << 20));
   }
   const int samp_first = p.sample_first;
   const int samp_end = p.sample_count > 0 ? p.sample_first + p.sample_count : p.num_rays;
@@ -372,6 +383,7 @@ int rt_device_count(void) {
 int rt_destroy(rt_ctx* c) {
   if (!c) return RT_OK;
   cudaSetDevice(c->device);
+  g_alloc_stream = c->stream;
   c->d_nodes.release();
   c->d_tris.release();
   c->d_pos.release();
@@ -403,7 +415,11 @@ int rt_destroy(rt_ctx* c) {
   for (cudaEvent_t e : c->seg_events) cudaEventDestroy(e);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
-  if (c->stream) cudaStreamDestroy(c->stream);
+  if (c->stream) {
+    cudaStreamSynchronize(c->stream);  // the stream-ordered frees above complete before the stream goes away
+    cudaStreamDestroy(c->stream);
+  }
+  g_alloc_stream = nullptr;
   delete c;
   return RT_OK;
 }
@@ -460,6 +476,13 @@ int rt_create(const rt_scene* s, const rt_params* p, int device, rt_ctx** out) {
   CUC(cudaGetDeviceProperties(&prop, device));
   c->num_sms = prop.multiProcessorCount;
   CUC(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  g_alloc_stream = c->stream;
+  {
+    cudaMemPool_t pool;
+    CUC(cudaDeviceGetDefaultMemPool(&pool, device));
+    uint64_t never = UINT64_MAX;
+    CUC(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &never));
+  }
   CUC(cudaEventCreate(&c->ev0));
   CUC(cudaEventCreate(&c->ev1));
 
