@@ -121,6 +121,9 @@ typedef struct rt_stats {
   double photon_ms;        /* CUDA-event time of the last photon emission                            */
   int32_t bvh_nodes, bvh_depth;
   int64_t photons_stored;
+  double create_ms;        /* host wall time of rt_create ...                                        */
+  double bvh_build_ms;     /* ... of which the host BVH build                                        */
+  double kd_build_ms;      /* host wall time of the last kd-tree build (rt_set_photons)              */
 } rt_stats;
 
 typedef struct rt_ctx rt_ctx;

@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -58,6 +59,9 @@ struct DevBuf {
 };
 
 inline float3 h3(const float* a) { return make_float3(a[0], a[1], a[2]); }
+inline double now_ms() {
+  return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
 }  // namespace
 
 struct rt_ctx {
@@ -88,6 +92,9 @@ struct rt_ctx {
   DevBuf<float4> d_hit, d_sh_o, d_sh_d, d_contrib;
   DevBuf<unsigned char> d_occ;
   DevBuf<int> d_hit_path;
+  DevBuf<unsigned int> d_perm, d_sort_hist;
+  float3 bounds_lo{0, 0, 0}, bounds_hi{0, 0, 0};
+  int sort_hits = 1;  // RT_SORT_HITS=0 disables the spatial binning of bounce segments
   DevBuf<int> d_acc_cnt, d_out_cnt;
   DevBuf<float> d_out_rgb;
   DevBuf<unsigned int> d_qcount;
@@ -151,7 +158,7 @@ int ensure_pix_map(rt_ctx* c) {
 }
 
 // bytes of wavefront state per path slot (ensure_work below)
-constexpr size_t kBytesPerPath = 16 * 2 + 32 * 2 + 16 + 3 * (32 + 16 + 1) + 4;
+constexpr size_t kBytesPerPath = 16 * 2 + 32 * 2 + 16 + 3 * (32 + 16 + 1) + 4 + 4;
 
 int ensure_work(rt_ctx* c, size_t paths, bool path_mode) {
   const size_t shadow = shadow_slots_for((unsigned)paths);
@@ -168,6 +175,8 @@ int ensure_work(rt_ctx* c, size_t paths, bool path_mode) {
     CU(c->d_col1.ensure(paths));
     CU(c->d_qo1.ensure(paths));
     CU(c->d_qd1.ensure(paths));
+    CU(c->d_perm.ensure(paths));
+    CU(c->d_sort_hist.ensure(kSortBuckets + 2));
   }
   CU(c->d_qcount.ensure(kQNum));
   CU(c->d_counters.ensure(kCntNum));
@@ -218,6 +227,12 @@ void fill_args(rt_ctx* c, RenderArgs& a, const int* pix_map, int npix, bool use_
   a.contrib = c->d_contrib.p;
   a.occ = c->d_occ.p;
   a.hit_path = c->d_hit_path.p;
+  a.perm = (c->sort_hits && p.mode == 1) ? c->d_perm.p : nullptr;
+  a.sort_hist = c->d_sort_hist.p;
+  a.sort_lo = c->bounds_lo;
+  a.sort_inv_cell = make_float3(kSortGrid / std::max(c->bounds_hi.x - c->bounds_lo.x, 1e-20f),
+                                kSortGrid / std::max(c->bounds_hi.y - c->bounds_lo.y, 1e-20f),
+                                kSortGrid / std::max(c->bounds_hi.z - c->bounds_lo.z, 1e-20f));
   a.q_count = c->d_qcount.p;
   a.counters = c->d_counters.p;
 }
@@ -249,6 +264,10 @@ int run_batch(rt_ctx* c, RenderArgs& a, int s0, int nsamp) {
     if ((rc = mark())) return rc;
     launch_trace_nearest(a, seg, grid, c->stream);
     if ((rc = mark())) return rc;
+    if (seg > 0 && a.perm) {
+      launch_sort_hits(a, seg, c->stream);
+      c->stats.kernel_launches += 3;
+    }
     launch_shade(a, seg, std::max(grid_shade, 1), c->stream);
     c->stats.kernel_launches += 2;
     if (!a.photon) {
@@ -403,6 +422,8 @@ int rt_destroy(rt_ctx* c) {
   c->d_contrib.release();
   c->d_occ.release();
   c->d_hit_path.release();
+  c->d_perm.release();
+  c->d_sort_hist.release();
   c->d_qd0.release();
   c->d_qd1.release();
   c->d_acc.release();
@@ -455,6 +476,7 @@ int rt_create(const rt_scene* s, const rt_params* p, int device, rt_ctx** out) {
     if (s->triangles[t] < 0 || s->triangles[t] >= s->num_vertices)
       return fail(RT_ERR_INVALID, "triangle vertex index out of range");
 
+  const double t_create0 = now_ms();
   rt_ctx* c = new rt_ctx();
   c->device = device;
   c->params = *p;
@@ -489,6 +511,17 @@ int rt_create(const rt_scene* s, const rt_params* p, int device, rt_ctx** out) {
   // ---- BVH (host, reference split policy) ----
   float extent = 0.f;
   for (int i = 0; i < 3 * c->V; i++) extent = std::max(extent, std::fabs(s->positions[i]));
+  if (c->V > 0) {
+    float lo[3] = {s->positions[0], s->positions[1], s->positions[2]}, hi[3] = {lo[0], lo[1], lo[2]};
+    for (int v = 0; v < c->V; v++)
+      for (int a = 0; a < 3; a++) {
+        lo[a] = std::min(lo[a], s->positions[3 * v + a]);
+        hi[a] = std::max(hi[a], s->positions[3 * v + a]);
+      }
+    c->bounds_lo = make_float3(lo[0], lo[1], lo[2]);
+    c->bounds_hi = make_float3(hi[0], hi[1], hi[2]);
+  }
+  if (const char* e = getenv("RT_SORT_HITS")) c->sort_hits = atoi(e);
   for (int l = 0; l < c->L; l++)
     for (int a = 0; a < 3; a++) extent = std::max(extent, std::fabs(s->lights[l].position[a]) + s->lights[l].side);
   for (int a = 0; a < 3; a++) extent = std::max(extent, std::fabs(s->camera.position[a]));
@@ -497,7 +530,9 @@ int rt_create(const rt_scene* s, const rt_params* p, int device, rt_ctx** out) {
     return fail(RT_ERR_INVALID, "scene coordinates must be finite and smaller than 1e8");
   }
   float pad_fraction = p->bvh_pad > 0.f ? p->bvh_pad : 1.0f / 16384.0f;
+  const double t_bvh0 = now_ms();
   build_bvh(c->V, s->positions, c->T, s->triangles, c->M, s->mesh_first_triangle, extent, pad_fraction, c->bvh);
+  c->stats.bvh_build_ms = now_ms() - t_bvh0;
   if (c->bvh.depth > kStackDepth) {
     rt_destroy(c);
     return fail(RT_ERR_INVALID, "BVH deeper than the traversal stack");
@@ -537,7 +572,7 @@ int rt_create(const rt_scene* s, const rt_params* p, int device, rt_ctx** out) {
   std::vector<DMaterial> h_mats(std::max(c->M, 1));
   for (int m = 0; m < c->M; m++) {
     const rt_material& a = s->materials[m];
-    h_mats[m] = DMaterial{a.kd, a.alpha, h3(a.albedo), h3(a.f0)};
+    h_mats[m] = make_material(a.kd, a.alpha, h3(a.albedo), h3(a.f0));
   }
   CUC(c->d_nodes.ensure(c->bvh.nodes.size() / 4));
   CUC(c->d_tris.ensure(h_tris.size()));
@@ -576,6 +611,7 @@ int rt_create(const rt_scene* s, const rt_params* p, int device, rt_ctx** out) {
   S.kd_dir = c->d_kd_dir.p;
   S.kd_count = 0;
 #undef CUC
+  c->stats.create_ms = now_ms() - t_create0;
   *out = c;
   return RT_OK;
 }
@@ -751,7 +787,7 @@ int rt_eval_bsdf(rt_ctx* c, const rt_material* m, const float* n_wi_wo, int64_t 
   if (e == cudaSuccess) e = d_out.ensure(3 * (size_t)n);
   if (e == cudaSuccess) e = cudaMemcpy(d_in.p, n_wi_wo, sizeof(float) * 9 * (size_t)n, cudaMemcpyHostToDevice);
   if (e == cudaSuccess) {
-    launch_bsdf(DMaterial{m->kd, m->alpha, h3(m->albedo), h3(m->f0)}, d_in.p, n, d_out.p, c->stream);
+    launch_bsdf(make_material(m->kd, m->alpha, h3(m->albedo), h3(m->f0)), d_in.p, n, d_out.p, c->stream);
     c->stats.kernel_launches++;
     e = cudaStreamSynchronize(c->stream);
   }
@@ -835,7 +871,9 @@ int rt_set_photons(rt_ctx* c, const rt_photon* photons, int64_t n) {
   if (n >= (1 << 28)) return fail(RT_ERR_INVALID, "too many photons");
   static_assert(sizeof(rt_photon) == 28, "rt_photon must match Particle (28 bytes)");
   c->kd_nodes7.assign((const float*)photons, (const float*)photons + 7 * n);
+  const double t_kd0 = now_ms();
   build_kdtree(c->kd_nodes7, &c->kd_height);
+  c->stats.kd_build_ms = now_ms() - t_kd0;
   if (c->kd_height > kKdStack) return fail(RT_ERR_INVALID, "kd-tree deeper than the device stack");
   std::vector<float4> hp(std::max<int64_t>(n, 1)), hd(std::max<int64_t>(n, 1));
   for (int64_t i = 0; i < n; i++) {
@@ -940,6 +978,7 @@ int rt_reset_stats(rt_ctx* c) {
   if (!c) return fail(RT_ERR_INVALID, "null context");
   int nodes = c->stats.bvh_nodes, depth = c->stats.bvh_depth;
   int64_t stored = c->stats.photons_stored;
+  const double cms = c->stats.create_ms, bms = c->stats.bvh_build_ms, kms = c->stats.kd_build_ms;
   int rc = bind(c);
   if (rc) return rc;
   CU(cudaMemset(c->d_counters.p, 0, sizeof(unsigned long long) * kCntNum));
@@ -947,6 +986,9 @@ int rt_reset_stats(rt_ctx* c) {
   c->stats.bvh_nodes = nodes;
   c->stats.bvh_depth = depth;
   c->stats.photons_stored = stored;
+  c->stats.create_ms = cms;
+  c->stats.bvh_build_ms = bms;
+  c->stats.kd_build_ms = kms;
   return RT_OK;
 }
 int rt_get_bvh(rt_ctx* c, float* nodes16, int64_t capacity_nodes, int32_t* num_nodes, int32_t* depth) {

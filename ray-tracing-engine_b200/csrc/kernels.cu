@@ -335,6 +335,106 @@ void launch_raygen(const RenderArgs& a, cudaStream_t st) {
 }
 
 // ----------------------------------------------------------------------------------------------
+// Spatial binning of a bounce segment's hit points.  After a diffuse bounce the hit points of a warp's
+// 32 rays are scattered over the scene, and so are the 3 shadow rays each of them spawns (any-hit lanes
+// 18.6 of 32 on segment 1 against 22.7 on the pixel-coherent segment 0, profiles/r1_v2b_leafbatch_full.csv).
+// A counting sort by the Morton code of the hit point's cell restores that coherence for the price of
+// three small memory-bound kernels.  The order inside a cell is whatever the atomics produce; results do
+// not depend on it (every path owns its random stream and its output slot).
+// ----------------------------------------------------------------------------------------------
+RT_DI unsigned morton3_5bit(unsigned x, unsigned y, unsigned z) {
+  auto spread = [](unsigned v) {  // 5 bits -> every third bit
+    v = (v | (v << 8)) & 0x0000F00Fu;
+    v = (v | (v << 4)) & 0x000C30C3u;
+    v = (v | (v << 2)) & 0x00249249u;
+    return v;
+  };
+  return spread(x) | (spread(y) << 1) | (spread(z) << 2);
+}
+RT_DI unsigned sort_key(const RenderArgs& A, int seg, unsigned i) {
+  const float4 hr = A.hit[i];
+  if (__float_as_int(hr.w) < 0) return (unsigned)kSortBuckets;  // misses last
+  const float4 o = A.ray_o[seg & 1][i], d = A.ray_d[seg & 1][i];
+  const float px = fmaf(hr.x, d.x, o.x), py = fmaf(hr.x, d.y, o.y), pz = fmaf(hr.x, d.z, o.z);  // ~hit point
+  const int cx = min(max((int)((px - A.sort_lo.x) * A.sort_inv_cell.x), 0), kSortGrid - 1);
+  const int cy = min(max((int)((py - A.sort_lo.y) * A.sort_inv_cell.y), 0), kSortGrid - 1);
+  const int cz = min(max((int)((pz - A.sort_lo.z) * A.sort_inv_cell.z), 0), kSortGrid - 1);
+  return morton3_5bit((unsigned)cx, (unsigned)cy, (unsigned)cz);
+}
+// One CTA of 1024 threads per SM; CTA c owns the contiguous chunk [c*chunk, (c+1)*chunk) of the ray queue in
+// BOTH passes.  Shared memory holds one counter per bucket (128 KB + 4 B): hot cells (a wall) and the miss
+// bucket are absorbed by shared-memory atomics, and each CTA touches a global counter once per non-empty bucket.
+constexpr int kSortThreads = 1024;
+constexpr int kSortCells = kSortBuckets + 1;
+constexpr size_t kSortSmem = (size_t)kSortCells * sizeof(unsigned);
+
+__global__ void __launch_bounds__(kSortThreads) k_sort_count(const RenderArgs A, const int seg) {
+  extern __shared__ unsigned s_cnt[];
+  const unsigned n = A.q_count[kQHits0 + seg - 1];
+  const unsigned chunk = (n + gridDim.x - 1) / gridDim.x;
+  const unsigned i0 = blockIdx.x * chunk, i1 = min(n, i0 + chunk);
+  for (int b = threadIdx.x; b < kSortCells; b += kSortThreads) s_cnt[b] = 0;
+  __syncthreads();
+  for (unsigned i = i0 + threadIdx.x; i < i1; i += kSortThreads) atomicAdd(s_cnt + sort_key(A, seg, i), 1u);
+  __syncthreads();
+  for (int b = threadIdx.x; b < kSortCells; b += kSortThreads)
+    if (s_cnt[b]) atomicAdd(A.sort_hist + b, s_cnt[b]);
+}
+// exclusive scan of kSortBuckets+1 counters in place (one CTA of 1024 threads, 33 counters per thread)
+__global__ void __launch_bounds__(1024) k_sort_scan(unsigned* hist) {
+  __shared__ unsigned s_part[1024];
+  constexpr int kPer = (kSortCells + 1023) / 1024;
+  unsigned local[kPer];
+  unsigned sum = 0;
+  const int first = threadIdx.x * kPer;
+  for (int k = 0; k < kPer; k++) {
+    const int b = first + k;
+    local[k] = b < kSortCells ? hist[b] : 0u;
+    sum += local[k];
+  }
+  s_part[threadIdx.x] = sum;
+  __syncthreads();
+  for (int off = 1; off < 1024; off <<= 1) {  // Hillis-Steele inclusive scan of the partials
+    unsigned v = threadIdx.x >= off ? s_part[threadIdx.x - off] : 0u;
+    __syncthreads();
+    s_part[threadIdx.x] += v;
+    __syncthreads();
+  }
+  unsigned run = s_part[threadIdx.x] - sum;
+  for (int k = 0; k < kPer; k++) {
+    const int b = first + k;
+    if (b < kSortCells) hist[b] = run;
+    run += local[k];
+  }
+}
+__global__ void __launch_bounds__(kSortThreads) k_sort_scatter(const RenderArgs A, const int seg) {
+  extern __shared__ unsigned s_cnt[];
+  const unsigned n = A.q_count[kQHits0 + seg - 1];
+  const unsigned chunk = (n + gridDim.x - 1) / gridDim.x;
+  const unsigned i0 = blockIdx.x * chunk, i1 = min(n, i0 + chunk);
+  for (int b = threadIdx.x; b < kSortCells; b += kSortThreads) s_cnt[b] = 0;
+  __syncthreads();
+  for (unsigned i = i0 + threadIdx.x; i < i1; i += kSortThreads) atomicAdd(s_cnt + sort_key(A, seg, i), 1u);
+  __syncthreads();
+  for (int b = threadIdx.x; b < kSortCells; b += kSortThreads)  // reserve this CTA's range in every bucket
+    if (s_cnt[b]) s_cnt[b] = atomicAdd(A.sort_hist + b, s_cnt[b]);
+  __syncthreads();
+  for (unsigned i = i0 + threadIdx.x; i < i1; i += kSortThreads) A.perm[atomicAdd(s_cnt + sort_key(A, seg, i), 1u)] = i;
+}
+void launch_sort_hits(const RenderArgs& a, int seg, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(k_sort_count, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSortSmem);
+    cudaFuncSetAttribute(k_sort_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSortSmem);
+    configured = true;
+  }
+  cudaMemsetAsync(a.sort_hist, 0, (kSortBuckets + 2) * sizeof(unsigned), st);
+  k_sort_count<<<148, kSortThreads, kSortSmem, st>>>(a, seg);
+  k_sort_scan<<<1, 1024, 0, st>>>(a.sort_hist);
+  k_sort_scatter<<<148, kSortThreads, kSortSmem, st>>>(a, seg);
+}
+
+// ----------------------------------------------------------------------------------------------
 // k_shade: one thread per ray of the segment
 // ----------------------------------------------------------------------------------------------
 // Renderer.cpp:63-104
@@ -359,7 +459,7 @@ RT_DI float3 shade_photon(const DScene& S, float3 dir, float3 n, float3 P, const
 }
 
 template <int MODE, bool PHOTON>
-__global__ void __launch_bounds__(kBlock) k_shade(const RenderArgs A, const int seg) {
+__global__ void __launch_bounds__(kBlock, PHOTON ? 1 : 8) k_shade(const RenderArgs A, const int seg) {
   const DScene& S = A.scene;
   const unsigned n = seg == 0 ? (unsigned)A.npix * (unsigned)A.nsamp : A.q_count[kQHits0 + seg - 1];
   const float4* qo_in = A.ray_o[seg & 1];
@@ -370,13 +470,15 @@ __global__ void __launch_bounds__(kBlock) k_shade(const RenderArgs A, const int 
   unsigned n_hit = 0, n_knn = 0;
   unsigned long long n_visits = 0;
 
+  const bool permuted = seg > 0 && A.perm != nullptr;
   for (unsigned base = blockIdx.x * kBlock; base < n; base += gridDim.x * kBlock) {
-    const unsigned i = base + threadIdx.x;
+    const unsigned slot = base + threadIdx.x;
+    const unsigned i = (permuted && slot < n) ? A.perm[slot] : slot;
     bool found = false;
     unsigned p = 0;
     float3 o = f3(0, 0, 0), d = f3(0, 0, 0);
     HitRec h;
-    if (i < n) {
+    if (slot < n) {
       const float4 a = qo_in[i], b = qd_in[i], hr = A.hit[i];
       o = f3(a);
       d = f3(b);
@@ -396,7 +498,7 @@ __global__ void __launch_bounds__(kBlock) k_shade(const RenderArgs A, const int 
       j0 = __shfl_sync(kFull, j0, __ffs(mask) - 1);
       j = j0 + __popc(mask & ((1u << lane) - 1u));
     }
-    if (i < n && !found) {
+    if (slot < n && !found) {
       // Renderer.cpp:154-160: a miss ends the path; the colour so far is clamped and final
       if (seg == 0) {
         A.col0[p] = make_float4(0.f, 0.f, 0.f, 0.f);  // posIntersectionFound = false
@@ -426,13 +528,14 @@ __global__ void __launch_bounds__(kBlock) k_shade(const RenderArgs A, const int 
         for (unsigned l = 1; l < (unsigned)kShadowLights; l++) A.occ[shadow_slot(j, l)] = 1;
       } else {
         // Renderer.cpp:49-60: per light 2 uniforms, the shadow ray, and (eagerly) radiance * bsdf
-        const float3 wo = v_neg(d);
+        const BsdfFrame bf = bsdf_frame(m, nrm, v_neg(d));
+#pragma unroll
         for (int l = 0; l < kShadowLights; l++) {
           const unsigned s = shadow_slot(j, l);
           if (l < S.num_lights) {
             const DLight& L = S.lights[l];
             float3 to_light = v_sub(light_rand_area_position(L, g), P);
-            float3 c = v_mul(light_evaluate(L, P), evaluate_color_response(m, nrm, to_light, wo));
+            float3 c = v_mul(light_evaluate(L, P), evaluate_color_response(m, bf, to_light));
             A.sh_o[s] = make_float4(P.x, P.y, P.z, 0.f);
             A.sh_d[s] = make_float4(to_light.x, to_light.y, to_light.z, 0.f);
             A.contrib[s] = make_float4(c.x, c.y, c.z, 0.f);

@@ -50,10 +50,19 @@ struct RenderArgs {
   float4* contrib;   // radiance * bsdf of light l for hit j, same layout
   unsigned char* occ;  // any-hit result, same layout
   int* hit_path;     // compacted hit j -> path id
+  // spatial binning of the hit points of a bounce segment (counting sort by Morton cell): perm[k] = ray slot
+  // processed k-th by k_shade, so that consecutive hits (and the shadow rays they spawn) are neighbours
+  unsigned int* perm;        // null: identity
+  unsigned int* sort_hist;   // kSortBuckets + 2 counters (bucket kSortBuckets = misses)
+  float3 sort_lo;            // scene bounds
+  float3 sort_inv_cell;      // kSortGrid / extent per axis
   unsigned int* q_count;
   unsigned long long* counters;
 };
 
+constexpr int kSortGrid = 32;                                   // cells per axis
+constexpr int kSortBuckets = kSortGrid * kSortGrid * kSortGrid;  // 32768 Morton cells (+1 bucket for misses)
+void launch_sort_hits(const RenderArgs& a, int seg, cudaStream_t st);  // fills a.perm for segment seg
 void launch_raygen(const RenderArgs& a, cudaStream_t st);
 void launch_trace_nearest(const RenderArgs& a, int seg, int grid_ctas, cudaStream_t st);
 void launch_shade(const RenderArgs& a, int seg, int grid_ctas, cudaStream_t st);

@@ -123,10 +123,47 @@ struct Rng {
 // ------------------------------------------------------------------------------------------------
 // device scene
 // ------------------------------------------------------------------------------------------------
-struct DMaterial {  // Material.h:62-64
-  float kd, alpha;
-  float3 albedo, f0;
+struct DMaterial {  // Material.h:62-64 + per-material constants of Material.h:25-69, precomputed by
+  float kd, alpha;    // make_material() with exactly the reference's operations (so they are bit-identical
+  float3 albedo, f0;  // to recomputing them per call, as the reference does)
+  float3 diffuse_kd;   // m_kd * (m_albedo / float(M_PI))          Material.h:27,38
+  float one_minus_kd;  // 1 - m_kd                                 Material.h:28
+  float a2, a2m1;      // alpha*alpha, alpha*alpha - 1             Material.h:47-48
+  float k, one_minus_k;  // float(alpha*sqrt(2/pi)), 1 - k         Material.h:67-68
+  float3 one_minus_f0;   // (1,1,1) - F0                           Material.h:52
 };
+__host__ __device__ inline DMaterial make_material(float kd, float alpha, float3 albedo, float3 f0) {
+  DMaterial m;
+  m.kd = kd;
+  m.alpha = alpha;
+  m.albedo = albedo;
+  m.f0 = f0;
+#ifdef __CUDA_ARCH__
+  const float pi_f = 3.14159274f;
+  m.diffuse_kd = make_float3(__fmul_rn(__fdiv_rn(albedo.x, pi_f), kd), __fmul_rn(__fdiv_rn(albedo.y, pi_f), kd),
+                             __fmul_rn(__fdiv_rn(albedo.z, pi_f), kd));
+  m.one_minus_kd = __fsub_rn(1.f, kd);
+  m.a2 = __fmul_rn(alpha, alpha);
+  m.a2m1 = __fsub_rn(m.a2, 1.f);
+  m.k = (float)__dmul_rn((double)alpha, 0.7978845608028654);
+  m.one_minus_k = __fsub_rn(1.f, m.k);
+  m.one_minus_f0 = make_float3(__fsub_rn(1.f, f0.x), __fsub_rn(1.f, f0.y), __fsub_rn(1.f, f0.z));
+#else
+  // host: x86-64 SSE2 binary32/binary64, compiled with -ffp-contract=off (volatile blocks re-association)
+  volatile float pi_f = 3.14159274f;
+  volatile float dx = albedo.x / pi_f, dy = albedo.y / pi_f, dz = albedo.z / pi_f;
+  m.diffuse_kd = make_float3(dx * kd, dy * kd, dz * kd);
+  m.one_minus_kd = 1.f - kd;
+  volatile float a2 = alpha * alpha;
+  m.a2 = a2;
+  m.a2m1 = a2 - 1.f;
+  volatile double kk = (double)alpha * 0.7978845608028654;
+  m.k = (float)kk;
+  m.one_minus_k = 1.f - m.k;
+  m.one_minus_f0 = make_float3(1.f - f0.x, 1.f - f0.y, 1.f - f0.z);
+#endif
+  return m;
+}
 struct DLight {  // LightSource.h:61-65
   float3 position, color, normal, vertical, horizontal;
   float intensity, side, ac, al, aq, factor;
@@ -355,34 +392,49 @@ RT_DI float3 light_evaluate(const DLight& l, float3 p) { return v_scl(v_scl(l.co
 // are formed by multiplication in binary64 (<= 2 ulp of binary64 from glibc's pow, invisible after
 // the rounding to binary32 that follows except with probability ~1e-8).
 // ------------------------------------------------------------------------------------------------
-RT_DI float g_schlick(float alpha, float3 w, float3 n) {
-  float k = (float)__dmul_rn((double)alpha, 0.7978845608028654);  // alpha * sqrt(2/pi)
-  float nw = v_dot(n, w);
-  return __fdiv_rn(nw, __fadd_rn(__fmul_rn(nw, __fsub_rn(1.f, k)), k));
+// Material.h:66-69 with k = float(alpha*sqrt(2/pi)) precomputed
+RT_DI float g_schlick(const DMaterial& m, float nw) {
+  return __fdiv_rn(nw, __fadd_rn(__fmul_rn(nw, m.one_minus_k), m.k));
 }
-RT_DI float3 specular_response(const DMaterial& m, float3 n, float3 wi, float3 wo) {
+// The per-hit part of evaluateColorResponse: normal and outgoing direction are re-normalised by the
+// reference on every call (Material.h:29-30); the result only depends on the hit, so we do it once.
+struct BsdfFrame {
+  float3 n, wo;   // normalize(normal), normalize(wo)
+  float n_wo;     // dot(n, wo)
+  float g_wo;     // gSchlick(wo, n)
+};
+RT_DI BsdfFrame bsdf_frame(const DMaterial& m, float3 normal, float3 wo) {
+  BsdfFrame f;
+  f.n = v_norm(normal);
+  f.wo = v_norm(wo);
+  f.n_wo = v_dot(f.n, f.wo);
+  f.g_wo = g_schlick(m, f.n_wo);
+  return f;
+}
+// Material.h:25-60 for one incoming direction wi (not yet normalised)
+RT_DI float3 evaluate_color_response(const DMaterial& m, const BsdfFrame& f, float3 wi_raw) {
   const double kPi = 3.141592653589793;
-  float3 wh = v_norm(v_add(wi, wo));
-  float a2 = __fmul_rn(m.alpha, m.alpha);
-  double nh = (double)v_dot(n, wh);
-  double inner = __dadd_rn(1.0, __dmul_rn((double)__fsub_rn(a2, 1.f), __dmul_rn(nh, nh)));
-  float D = (float)__ddiv_rn((double)a2, __dmul_rn(kPi, __dmul_rn(inner, inner)));
-  double x = __dsub_rn(1.0, fmax(0.0, (double)v_dot(wi, wh)));
-  double x2 = __dmul_rn(x, x);
-  float fr = (float)__dmul_rn(__dmul_rn(x2, x2), x);
-  float3 F = v_add(m.f0, v_scl(v_sub(f3(1.f, 1.f, 1.f), m.f0), fr));
-  float G = __fmul_rn(g_schlick(m.alpha, wi, n), g_schlick(m.alpha, wo, n));
-  float denom = (float)__dmul_rn(__dmul_rn(4.0, (double)v_dot(n, wi)), (double)v_dot(n, wo));
-  return v_dvs(v_scl(v_scl(F, D), G), denom);
-}
-RT_DI float3 evaluate_color_response(const DMaterial& m, float3 n, float3 wi, float3 wo) {
-  float3 diffuse = v_dvs(m.albedo, 3.14159274f);  // albedo / float(M_PI)
-  float3 spec = specular_response(m, v_norm(n), v_norm(wi), v_norm(wo));
-  float3 r = v_add(v_scl(diffuse, m.kd), v_scl(spec, __fsub_rn(1.f, m.kd)));
+  const float3 wi = v_norm(wi_raw);
+  const float3 wh = v_norm(v_add(wi, f.wo));
+  const double nh = (double)v_dot(f.n, wh);
+  const double inner = __dadd_rn(1.0, __dmul_rn((double)m.a2m1, __dmul_rn(nh, nh)));
+  const float D = (float)__ddiv_rn((double)m.a2, __dmul_rn(kPi, __dmul_rn(inner, inner)));
+  const double x = __dsub_rn(1.0, fmax(0.0, (double)v_dot(wi, wh)));
+  const double x2 = __dmul_rn(x, x);
+  const float fr = (float)__dmul_rn(__dmul_rn(x2, x2), x);
+  const float3 F = v_add(m.f0, v_scl(m.one_minus_f0, fr));
+  const float n_wi = v_dot(f.n, wi);
+  const float G = __fmul_rn(g_schlick(m, n_wi), f.g_wo);
+  const float denom = (float)__dmul_rn(__dmul_rn(4.0, (double)n_wi), (double)f.n_wo);
+  const float3 spec = v_dvs(v_scl(v_scl(F, D), G), denom);
+  float3 r = v_add(m.diffuse_kd, v_scl(spec, m.one_minus_kd));
   if (r.x < 0.f) r.x = 0.f;
   if (r.y < 0.f) r.y = 0.f;
   if (r.z < 0.f) r.z = 0.f;
   return r;
+}
+RT_DI float3 evaluate_color_response(const DMaterial& m, float3 n, float3 wi, float3 wo) {
+  return evaluate_color_response(m, bsdf_frame(m, n, wo), wi);
 }
 // Renderer.cpp:279-283: fmax(fmin(c,1),0) -- a NaN channel becomes 1
 RT_DI float3 normalize_color(float3 c) {
@@ -520,13 +572,20 @@ RT_DI void kd_knearest(const DScene& S, float3 q, int k, KdHeap& H, int* kst, in
       b = nb;
       e = ne;
     }
-    // unwind: first frame whose far side survives `dx*dx >= m_bestdist` (kdtree.h:105, squared vs not)
+    // unwind: first frame whose far side survives `dx*dx >= m_bestdist` (kdtree.h:105, squared vs not).
+    // Second condition: a far subtree lies entirely beyond the splitting plane, so every photon in it has
+    // d >= |dx|; when |dx| >= m_bestdist none of them can pass `d < m_bestdist` (kdtree.h:92), the visit
+    // would change neither the heap nor m_bestdist, and skipping it returns exactly the reference's result
+    // (only kdtree::visited() differs).  For m_bestdist < 1 -- the usual case in this scene -- this is the
+    // pruning an exact k-NN would do and removes ~85 % of the node visits.  The factor keeps a 2-ulp
+    // margin for sqrt(fl(a*a)) < |a|; in doubt we visit, which is what the reference does.
     bool resumed = false;
     while (sp > 0) {
       sp--;
       float dx = __int_as_float(kst[(3 * sp + 2) * ks]);
       double dx2 = __dmul_rn((double)dx, (double)dx);
       if (dx2 >= (double)best) continue;
+      if (fabsf(dx) * 0.9999995f >= best) continue;
       int fe = kst[(3 * sp + 1) * ks];
       b = kst[(3 * sp) * ks];
       axis = (fe >> 28) & 3;

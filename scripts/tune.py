@@ -17,10 +17,16 @@ if len(sys.argv) > 1 and sys.argv[1] == "--one":
         s, c = r.render_accumulate()
         st = r.stats()
         dev.append(st["device_ms"]); tr.append(st["trace_ms"])
-    print(json.dumps(dict(variant=os.environ.get("RT_TRACE_VARIANT", "0"), device_ms=min(dev), trace_ms=min(tr),
+    print(json.dumps(dict(variant=os.environ.get("RT_TRACE_VARIANT", "default"), sort=os.environ.get("RT_SORT_HITS", "default"), device_ms=min(dev), trace_ms=min(tr),
                           rays=st["rays"] // 3, grays=st["rays"] / 3 / min(dev) / 1e6, checksum=float(s.sum()), hits=int(c.sum()))))
 else:
     for v in sys.argv[1:] or ["0", "1", "2", "3", "4"]:
-        env = dict(os.environ, RT_TRACE_VARIANT=v)
+        env = dict(os.environ)
+        for kv in v.split(","):  # "1" or "1,RT_SORT_HITS=0"
+            if "=" in kv:
+                k_, v_ = kv.split("=")
+                env[k_] = v_
+            else:
+                env["RT_TRACE_VARIANT"] = kv
         out = subprocess.run([sys.executable, __file__, "--one"], env=env, capture_output=True, text=True)
         print(out.stdout.strip() or out.stderr[-500:], flush=True)
