@@ -121,6 +121,18 @@ class Scene:
             out[self.mesh_tri_off[m]:self.mesh_tri_off[m + 1]] = m
         return out
 
+    def build_bvh_host(self, pad_fraction=0.0):
+        """The host BVH builder alone (no device needed): (nodes [n,16] float32, slot_triangle [T], depth).
+        Split policy of BVH::from_triangles (source/BVH.h:100-161); layout in csrc/host_build.h."""
+        lib = _capi.load()
+        cs = self._as_c()
+        cnt, depth = np.zeros(1, np.int32), np.zeros(1, np.int32)
+        _capi.check(lib.rt_build_bvh_host(C.byref(cs), pad_fraction, None, 0, None, _capi.ptr(cnt), _capi.ptr(depth)))
+        nodes, slots = np.zeros((int(cnt[0]), 16), np.float32), np.zeros(self.T, np.int32)
+        _capi.check(lib.rt_build_bvh_host(C.byref(cs), pad_fraction, _capi.ptr(nodes), int(cnt[0]), _capi.ptr(slots),
+                                          _capi.ptr(cnt), _capi.ptr(depth)))
+        return nodes, slots, int(depth[0])
+
     def _as_c(self):
         s = _capi.rt_scene()
         s.num_vertices, s.num_triangles, s.num_meshes, s.num_lights = self.V, self.T, self.M, self.L

@@ -305,6 +305,16 @@ int photons_per_light(const rt_ctx* c, float* light_pdf_out) {
   return (int)((float)c->params.num_photons * light_pdf);
 }
 
+// largest |coordinate| of any vertex, light or the camera: scales the BVH padding (host_build.h)
+float scene_extent(const rt_scene* s) {
+  float extent = 0.f;
+  for (int64_t i = 0; i < 3 * (int64_t)s->num_vertices; i++) extent = std::max(extent, std::fabs(s->positions[i]));
+  for (int l = 0; l < s->num_lights; l++)
+    for (int a = 0; a < 3; a++) extent = std::max(extent, std::fabs(s->lights[l].position[a]) + s->lights[l].side);
+  for (int a = 0; a < 3; a++) extent = std::max(extent, std::fabs(s->camera.position[a]));
+  return extent;
+}
+
 bool use_photon_map(const rt_ctx* c) { return c->params.num_photons > 0 && c->scene.kd_count > 0; }
 
 int prepare_photons(rt_ctx* c) {
@@ -321,7 +331,8 @@ int prepare_photons(rt_ctx* c) {
 }
 
 // the whole render: batches of samples -> ordered accumulation -> scatter into full-frame buffers
-int render_to_device(rt_ctx* c, float* out_rgb_dev, int* out_cnt_dev) {
+// composite_dev != null: instead of the raw sums/counters, composite over the background it holds (rt_render)
+int render_to_device(rt_ctx* c, float* out_rgb_dev, int* out_cnt_dev, float* composite_dev = nullptr) {
   int rc = bind(c);
   if (rc) return rc;
   if ((rc = prepare_photons(c))) return rc;
@@ -361,11 +372,18 @@ int render_to_device(rt_ctx* c, float* out_rgb_dev, int* out_cnt_dev) {
       c->stats.kernel_launches++;
     }
   }
-  CU(cudaMemsetAsync(out_rgb_dev, 0, sizeof(float) * 3 * npx, c->stream));
-  CU(cudaMemsetAsync(out_cnt_dev, 0, sizeof(int) * npx, c->stream));
-  if (c->npix > 0) {
-    launch_scatter(c->d_acc.p, c->d_acc_cnt.p, c->d_pix_map.p, c->npix, out_rgb_dev, out_cnt_dev, c->stream);
-    c->stats.kernel_launches++;
+  if (composite_dev) {
+    if (c->npix > 0) {
+      launch_composite(c->d_acc.p, c->d_acc_cnt.p, c->d_pix_map.p, c->npix, p.num_rays, composite_dev, c->stream);
+      c->stats.kernel_launches++;
+    }
+  } else {
+    CU(cudaMemsetAsync(out_rgb_dev, 0, sizeof(float) * 3 * npx, c->stream));
+    CU(cudaMemsetAsync(out_cnt_dev, 0, sizeof(int) * npx, c->stream));
+    if (c->npix > 0) {
+      launch_scatter(c->d_acc.p, c->d_acc_cnt.p, c->d_pix_map.p, c->npix, out_rgb_dev, out_cnt_dev, c->stream);
+      c->stats.kernel_launches++;
+    }
   }
   CU(cudaEventRecord(c->ev1, c->stream));
   CU(cudaStreamSynchronize(c->stream));
@@ -494,9 +512,7 @@ int rt_create(const rt_scene* s, const rt_params* p, int device, rt_ctx** out) {
     }                                                                               \
   } while (0)
   CUC(cudaSetDevice(device));
-  cudaDeviceProp prop;
-  CUC(cudaGetDeviceProperties(&prop, device));
-  c->num_sms = prop.multiProcessorCount;
+  CUC(cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, device));
   CUC(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   g_alloc_stream = c->stream;
   {
@@ -509,8 +525,7 @@ int rt_create(const rt_scene* s, const rt_params* p, int device, rt_ctx** out) {
   CUC(cudaEventCreate(&c->ev1));
 
   // ---- BVH (host, reference split policy) ----
-  float extent = 0.f;
-  for (int i = 0; i < 3 * c->V; i++) extent = std::max(extent, std::fabs(s->positions[i]));
+  const float extent = scene_extent(s);
   if (c->V > 0) {
     float lo[3] = {s->positions[0], s->positions[1], s->positions[2]}, hi[3] = {lo[0], lo[1], lo[2]};
     for (int v = 0; v < c->V; v++)
@@ -522,9 +537,6 @@ int rt_create(const rt_scene* s, const rt_params* p, int device, rt_ctx** out) {
     c->bounds_hi = make_float3(hi[0], hi[1], hi[2]);
   }
   if (const char* e = getenv("RT_SORT_HITS")) c->sort_hits = atoi(e);
-  for (int l = 0; l < c->L; l++)
-    for (int a = 0; a < 3; a++) extent = std::max(extent, std::fabs(s->lights[l].position[a]) + s->lights[l].side);
-  for (int a = 0; a < 3; a++) extent = std::max(extent, std::fabs(s->camera.position[a]));
   if (!(extent < 1e8f)) {  // keeps lo * safe_inv(d) finite in the slab test (rt_device.cuh)
     rt_destroy(c);
     return fail(RT_ERR_INVALID, "scene coordinates must be finite and smaller than 1e8");
@@ -657,21 +669,14 @@ int rt_render(rt_ctx* c, float* rgb_inout) {
   const rt_params& p = c->params;
   const size_t npx = (size_t)p.width * p.height;
   if (p.num_rays < 1) return RT_OK;  // Renderer.cpp:219: no pass, image = saveImage (we leave the input)
-  std::vector<float> sum(3 * npx);
-  std::vector<int32_t> cnt(npx);
-  int rc = rt_render_accumulate(c, sum.data(), cnt.data());
+  int rc = bind(c);
   if (rc) return rc;
-  if (p.shard_count > 1) {
-    // composite only the pixels this shard owns
-    std::vector<int> map;
-    build_pix_map(p, map);
-    std::vector<float> full(rgb_inout, rgb_inout + 3 * npx);
-    rt_composite(p.width, p.height, p.num_rays, sum.data(), cnt.data(), full.data());
-    for (int px : map)
-      for (int ch = 0; ch < 3; ch++) rgb_inout[3 * (size_t)px + ch] = full[3 * (size_t)px + ch];
-    return RT_OK;
-  }
-  return rt_composite(p.width, p.height, p.num_rays, sum.data(), cnt.data(), rgb_inout);
+  // background up, the whole Renderer::render on the device (composite included), frame down
+  CU(c->d_out_rgb.ensure(3 * npx));
+  CU(cudaMemcpyAsync(c->d_out_rgb.p, rgb_inout, sizeof(float) * 3 * npx, cudaMemcpyHostToDevice, c->stream));
+  if ((rc = render_to_device(c, nullptr, nullptr, c->d_out_rgb.p))) return rc;
+  CU(cudaMemcpy(rgb_inout, c->d_out_rgb.p, sizeof(float) * 3 * npx, cudaMemcpyDeviceToHost));
+  return RT_OK;
 }
 
 int rt_render_samples(rt_ctx* c, int32_t x0, int32_t y0, int32_t x1, int32_t y1, int32_t s0, int32_t s1, float* rgb,
@@ -989,6 +994,24 @@ int rt_reset_stats(rt_ctx* c) {
   c->stats.create_ms = cms;
   c->stats.bvh_build_ms = bms;
   c->stats.kd_build_ms = kms;
+  return RT_OK;
+}
+int rt_build_bvh_host(const rt_scene* s, float pad_fraction, float* nodes16, int64_t capacity_nodes,
+                      int32_t* slot_triangle, int32_t* num_nodes, int32_t* depth) {
+  if (!s || s->num_triangles < 0 || s->num_meshes < 0) return fail(RT_ERR_INVALID, "bad scene");
+  for (int t = 0; t < 3 * s->num_triangles; t++)
+    if (s->triangles[t] < 0 || s->triangles[t] >= s->num_vertices)
+      return fail(RT_ERR_INVALID, "triangle vertex index out of range");
+  Bvh bvh;
+  build_bvh(s->num_vertices, s->positions, s->num_triangles, s->triangles, s->num_meshes, s->mesh_first_triangle,
+            scene_extent(s), pad_fraction > 0.f ? pad_fraction : 1.0f / 16384.0f, bvh);
+  const int64_t n = (int64_t)bvh.nodes.size() / 16;
+  if (num_nodes) *num_nodes = (int32_t)n;
+  if (depth) *depth = bvh.depth;
+  if (!nodes16) return RT_OK;
+  if (capacity_nodes < n) return fail(RT_ERR_INVALID, "capacity too small");
+  std::memcpy(nodes16, bvh.nodes.data(), bvh.nodes.size() * sizeof(float));
+  if (slot_triangle) std::memcpy(slot_triangle, bvh.slot_tri.data(), bvh.slot_tri.size() * sizeof(int32_t));
   return RT_OK;
 }
 int rt_get_bvh(rt_ctx* c, float* nodes16, int64_t capacity_nodes, int32_t* num_nodes, int32_t* depth) {

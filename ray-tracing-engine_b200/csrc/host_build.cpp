@@ -8,6 +8,8 @@
 #include <cstring>
 #include <limits>
 #include <thread>
+#include <utility>
+#include <vector>
 
 namespace rtb {
 namespace {
@@ -65,28 +67,59 @@ struct Builder {
     }
   }
 
-  // Subtree over idx[0..n): internal nodes [node_base, node_base+n-1), slots [slot_base, slot_base+n).
-  int32_t build(int32_t* idx, int n, int node_base, int slot_base, int depth, Box& box, int fork_levels) {
+  // Subtree over the triangles ord[a][b..e) (the same set in each of the three arrays, sorted by key[a]):
+  // internal nodes [node_base, node_base+n-1), slots [slot_base, slot_base+n).
+  //
+  // BVH.h:141-158 sorts the node's triangles by the key of the cut axis and gives the first floor(n/2) to the
+  // left child.  Sorting every node from scratch is O(T log^2 T); here the three orders are produced once and
+  // every split is a stable partition of the two other orders (O(n) per node, O(T log T) in total).  The order
+  // among equal keys differs from libstdc++'s unstable std::sort -- it is unspecified in the reference as well,
+  // and any choice gives a valid tree of the same shape (hit results do not depend on it).
+  int32_t* ord[3] = {nullptr, nullptr, nullptr};
+  int32_t* tmp = nullptr;        // partition scratch, same indexing as ord[]
+  unsigned char* side = nullptr;  // per global triangle: 1 = goes right at the split being processed
+
+  int32_t build(int b, int e, int node_base, int slot_base, int depth, Box& box, int fork_levels) {
+    const int n = e - b;
     if (n == 1) {
-      slot_tri[slot_base] = idx[0];
-      box = tri_box[idx[0]];
+      slot_tri[slot_base] = ord[0][b];
+      box = tri_box[ord[0][b]];
       note_depth(depth);
       return ~slot_base;
     }
     box.reset();
-    for (int i = 0; i < n; i++) box.grow(tri_box[idx[i]]);
-    const std::vector<float>& k = key[cut_axis(box)];
-    std::sort(idx, idx + n, [&k](int32_t a, int32_t b) { return k[a] < k[b]; });  // BVH.h:141-150
-    int nl = n / 2;                                                              // BVH.h:151-158
+    for (int i = b; i < e; i++) box.grow(tri_box[ord[0][i]]);
+    const int axis = cut_axis(box);
+    const int nl = n / 2;  // BVH.h:151-158
+    if (n > 2) {           // n == 2: every order already has one triangle per side after the marks below
+      for (int i = b; i < b + nl; i++) side[ord[axis][i]] = 0;
+      for (int i = b + nl; i < e; i++) side[ord[axis][i]] = 1;
+      for (int a = 0; a < 3; a++) {
+        if (a == axis) continue;
+        int32_t* o = ord[a];
+        int l = b, r = b + nl;
+        for (int i = b; i < e; i++) {
+          const int32_t t = o[i];
+          if (side[t]) tmp[r++] = t; else tmp[l++] = t;
+        }
+        std::memcpy(o + b, tmp + b, sizeof(int32_t) * (size_t)n);
+      }
+    } else {
+      const int32_t t0 = ord[axis][b], t1 = ord[axis][b + 1];
+      for (int a = 0; a < 3; a++) {
+        ord[a][b] = t0;
+        ord[a][b + 1] = t1;
+      }
+    }
     Box bl, br;
     int32_t rl, rr;
-    if (fork_levels > 0 && n > 32768) {
-      std::thread t([&]() { rl = build(idx, nl, node_base + 1, slot_base, depth + 1, bl, fork_levels - 1); });
-      rr = build(idx + nl, n - nl, node_base + nl, slot_base + nl, depth + 1, br, fork_levels - 1);
+    if (fork_levels > 0 && n > 4096) {
+      std::thread t([&]() { rl = build(b, b + nl, node_base + 1, slot_base, depth + 1, bl, fork_levels - 1); });
+      rr = build(b + nl, e, node_base + nl, slot_base + nl, depth + 1, br, fork_levels - 1);
       t.join();
     } else {
-      rl = build(idx, nl, node_base + 1, slot_base, depth + 1, bl, 0);
-      rr = build(idx + nl, n - nl, node_base + nl, slot_base + nl, depth + 1, br, 0);
+      rl = build(b, b + nl, node_base + 1, slot_base, depth + 1, bl, 0);
+      rr = build(b + nl, e, node_base + nl, slot_base + nl, depth + 1, br, 0);
     }
     float* node = nodes + 16 * (size_t)node_base;
     write_child(node, 0, &bl, rl);
@@ -154,8 +187,36 @@ void build_bvh(int num_vertices, const float* P, int T, const int32_t* tri, int 
   B.nodes = out.nodes.data();
   B.slot_tri = out.slot_tri.data();
 
-  std::vector<int32_t> idx(T);
-  for (int t = 0; t < T; t++) idx[t] = t;
+  // the three key orders, per mesh (a mesh's triangles are contiguous in [t0, t0+n))
+  std::vector<int32_t> ord_store[3], tmp_store(T);
+  std::vector<unsigned char> side_store(T, 0);
+  unsigned hw = std::thread::hardware_concurrency();
+  int fork_levels = hw >= 16 ? 4 : hw >= 8 ? 3 : hw >= 4 ? 2 : hw >= 2 ? 1 : 0;
+  {
+    auto sort_axis = [&](int a) {
+      std::vector<std::pair<float, int32_t>> kv(T);
+      for (int t = 0; t < T; t++) kv[t] = {B.key[a][t], t};
+      for (int m = 0; m < M; m++) {
+        int t0 = mesh_first_triangle[m], t1 = mesh_first_triangle[m + 1];
+        if (t1 - t0 > 1)
+          std::sort(kv.begin() + t0, kv.begin() + t1,
+                    [](const std::pair<float, int32_t>& x, const std::pair<float, int32_t>& y) { return x.first < y.first; });
+      }
+      ord_store[a].resize(T);
+      for (int t = 0; t < T; t++) ord_store[a][t] = kv[t].second;
+    };
+    if (T > 4096 && hw >= 3) {
+      std::thread t1([&]() { sort_axis(1); }), t2([&]() { sort_axis(2); });
+      sort_axis(0);
+      t1.join();
+      t2.join();
+    } else {
+      for (int a = 0; a < 3; a++) sort_axis(a);
+    }
+  }
+  for (int a = 0; a < 3; a++) B.ord[a] = ord_store[a].data();
+  B.tmp = tmp_store.data();
+  B.side = side_store.data();
   std::vector<Builder::Item> items;
   int node_base = std::max(nonempty - 1, 0);
   int sub_depth = 0;
@@ -164,7 +225,7 @@ void build_bvh(int num_vertices, const float* P, int T, const int32_t* tri, int 
     if (n <= 0) continue;
     Builder::Item it;
     B.max_depth = 0;
-    it.ref = B.build(idx.data() + t0, n, node_base, t0, 0, it.box, 3);
+    it.ref = B.build(t0, t0 + n, node_base, t0, 0, it.box, fork_levels);
     sub_depth = std::max(sub_depth, B.max_depth.load());
     for (int a = 0; a < 3; a++) it.key[a] = it.box.lo[a] + it.box.hi[a];
     items.push_back(it);

@@ -202,7 +202,146 @@ RT_DI void trace_body(const DScene& S, const float4* __restrict__ ro, const floa
   }
 }
 
-#define RT_TRACE_KERNEL(NAME, LEAFB, MINB)                                                                          \
+// ----------------------------------------------------------------------------------------------
+// trace_body_spec: the same persistent loop with POSTPONED leaves.  ncu on the batched-leaf body
+// (profiles/r1_v2b_leafbatch_full.csv, SASS view) showed the box step running with 24 of 32 lanes (the others
+// sit on a leaf waiting for the batch), the Moller-Trumbore block with 12, and two separate copies of the stack
+// pop loop with 3 and 8 lanes.  Here a lane that reaches a leaf parks it in `pend` and keeps traversing; the
+// triangle block runs when >= LEAFT lanes have a parked leaf (or no lane has a node left), and there is ONE pop
+// site shared by "both children missed" and "leaf parked".  The result does not depend on the order in which
+// leaves are tested (accept_nearest is order-independent; any-hit is an OR), only the culling is a little later.
+// ----------------------------------------------------------------------------------------------
+template <bool ANY, bool BLOCKED, int LEAFT>
+RT_DI void trace_body_spec(const DScene& S, const float4* __restrict__ ro, const float4* __restrict__ rd,
+                           const unsigned* n_ptr, unsigned n_fixed, float4* __restrict__ hits,
+                           unsigned char* __restrict__ occ, unsigned* fetch, int depth, int* s_dyn) {
+  int* st_ref = s_dyn + threadIdx.x;
+  int* st_tn = s_dyn + depth * kBlock + threadIdx.x;
+  const unsigned items = n_ptr ? *n_ptr : n_fixed;
+  const unsigned n = BLOCKED ? shadow_slots_for(items) : items;
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned lt_mask = (1u << lane) - 1u;
+
+  TraceLane L;
+  L.idx = 0;
+  L.o = L.d = L.inv = L.oinv = f3(0, 0, 0);
+  L.h.t = FLT_MAX;
+  L.h.u = L.h.v = 0.f;
+  L.h.gid = 0x7fffffff;
+  L.sp = 0;
+  L.cur = kDone;
+  int pend = 0;       // parked leaf reference (< 0) or 0
+  bool live = false;  // this lane owns an unfinished ray
+  bool exhausted = false;
+
+  for (;;) {
+    const unsigned need_mask = __ballot_sync(kFull, !live);
+    if (!exhausted && need_mask) {
+      const unsigned cnt = __popc(need_mask);
+      unsigned base = 0;
+      if (lane == 0) base = atomicAdd(fetch, cnt);
+      base = __shfl_sync(kFull, base, 0);
+      if (base + cnt >= n) exhausted = true;
+      if (!live) {
+        const unsigned my = base + __popc(need_mask & lt_mask);
+        bool valid = my < n;
+        if (BLOCKED && valid) valid = ((my / 96u) * 32u + (my & 31u)) < items;
+        if (valid) {
+          const float4 a = __ldg(ro + my), b = __ldg(rd + my);
+          L.idx = my;
+          L.o = f3(a);
+          L.d = f3(b);
+          L.inv = f3(safe_inv(L.d.x), safe_inv(L.d.y), safe_inv(L.d.z));
+          L.oinv = f3(L.o.x * L.inv.x, L.o.y * L.inv.y, L.o.z * L.inv.z);
+          L.h.t = FLT_MAX;
+          L.h.u = L.h.v = 0.f;
+          L.h.gid = 0x7fffffff;
+          L.sp = 0;
+          L.cur = 0;
+          pend = 0;
+          live = true;
+        }
+      }
+    }
+    if (__ballot_sync(kFull, live) == 0) {
+      if (exhausted) break;
+      continue;
+    }
+    for (;;) {
+      bool need_pop = false;
+      if (L.cur >= 0) {  // internal node: both child boxes
+        const float4 n0 = __ldg(S.nodes + 4 * L.cur), n1 = __ldg(S.nodes + 4 * L.cur + 1);
+        const float4 n2 = __ldg(S.nodes + 4 * L.cur + 2), n3 = __ldg(S.nodes + 4 * L.cur + 3);
+        float tn0, tn1;
+        const bool h0 = box_hit_fma(f3(n0.x, n0.y, n0.z), f3(n0.w, n1.x, n1.y), L.inv, L.oinv, L.h.t, tn0);
+        const bool h1 = box_hit_fma(f3(n1.z, n1.w, n2.x), f3(n2.y, n2.z, n2.w), L.inv, L.oinv, L.h.t, tn1);
+        const int c0 = __float_as_int(n3.x), c1 = __float_as_int(n3.y);
+        const bool first0 = tn0 <= tn1;
+        if (h0 && h1) {
+          st_ref[L.sp * kBlock] = first0 ? c1 : c0;
+          if (!ANY) st_tn[L.sp * kBlock] = __float_as_int(first0 ? tn1 : tn0);
+          L.sp++;
+          L.cur = first0 ? c0 : c1;
+        } else if (h0 || h1) {
+          L.cur = h0 ? c0 : c1;
+        } else {
+          need_pop = true;
+        }
+      }
+      if (!need_pop && L.cur < 0 && L.cur != kDone && pend == 0) {  // park the leaf, keep traversing
+        pend = L.cur;
+        need_pop = true;
+      }
+      if (need_pop) trace_pop<ANY>(L, st_ref, st_tn);
+
+      const unsigned pend_mask = __ballot_sync(kFull, pend != 0);
+      if (pend_mask) {
+        const unsigned node_mask = __ballot_sync(kFull, L.cur >= 0);
+        if (__popc(pend_mask) >= LEAFT || node_mask == 0) {
+          if (pend != 0) {
+            const int slot = ~pend;
+            pend = 0;
+            const float4 A = __ldg(S.tris + 3 * slot), B = __ldg(S.tris + 3 * slot + 1), C = __ldg(S.tris + 3 * slot + 2);
+            float u, v, t;
+            if (mt_intersect(L.o, L.d, f3(A), f3(B), f3(C), u, v, t)) {
+              if (ANY) {
+                if (t > 0.f && t < FLT_MAX) {
+                  L.h.gid = 0;
+                  L.cur = kDone;  // occluded: drop the rest of the traversal
+                  L.sp = 0;
+                }
+              } else {
+                accept_nearest(L.h, t, u, v, __float_as_int(A.w));
+              }
+            }
+          }
+        }
+      }
+      if (live && L.cur == kDone && pend == 0) {
+        trace_write<ANY>(L, hits, occ);
+        live = false;
+      }
+      const unsigned live_mask = __ballot_sync(kFull, live);
+      if (live_mask == 0) break;
+      if (!exhausted && __popc(live_mask) < kRefillBelow) break;
+    }
+  }
+}
+
+#define RT_TRACE_KERNEL_SPEC(NAME, LEAFT)                                                                           \
+  template <bool ANY, bool BLOCKED>                                                                                 \
+  __global__ void __launch_bounds__(kBlock, 1)                                                                      \
+      NAME(const DScene S, const float4* __restrict__ ro, const float4* __restrict__ rd, const unsigned* n_ptr,    \
+           unsigned n_fixed, float4* __restrict__ hits, unsigned char* __restrict__ occ, unsigned* fetch, int depth) { \
+    extern __shared__ int s_dyn[];                                                                                  \
+    trace_body_spec<ANY, BLOCKED, LEAFT>(S, ro, rd, n_ptr, n_fixed, hits, occ, fetch, depth, s_dyn);                \
+  }
+RT_TRACE_KERNEL_SPEC(k_trace_sp8, 8)    // variant 5
+RT_TRACE_KERNEL_SPEC(k_trace_sp12, 12)  // variant 6
+RT_TRACE_KERNEL_SPEC(k_trace_sp16, 16)  // variant 7
+RT_TRACE_KERNEL_SPEC(k_trace_sp24, 24)  // variant 8
+
+#define RT_TRACE_KERNEL(NAME, LEAFB, MINB)                                                                        \
   template <bool ANY, bool BLOCKED>                                                                                 \
   __global__ void __launch_bounds__(kBlock, MINB)                                                                   \
       NAME(const DScene S, const float4* __restrict__ ro, const float4* __restrict__ rd, const unsigned* n_ptr,    \
@@ -257,6 +396,10 @@ int trace_ctas_per_sm(int stack_depth) {
     case 2: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_trace_lb16<false, false>, kBlock, sm); break;
     case 3: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_trace_occ<false, false>, kBlock, sm); break;
     case 4: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_trace_lb8occ<false, false>, kBlock, sm); break;
+    case 5: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_trace_sp8<false, false>, kBlock, sm); break;
+    case 6: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_trace_sp12<false, false>, kBlock, sm); break;
+    case 7: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_trace_sp16<false, false>, kBlock, sm); break;
+    case 8: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_trace_sp24<false, false>, kBlock, sm); break;
     default: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_trace_lb8<false, false>, kBlock, sm); break;
   }
   return n < 1 ? 1 : n;
@@ -277,6 +420,10 @@ static void launch_trace_t(const DScene& S, const float4* ro, const float4* rd, 
       case 2: RT_LAUNCH(k_trace_lb16); break;
       case 3: RT_LAUNCH(k_trace_occ); break;
       case 4: RT_LAUNCH(k_trace_lb8occ); break;
+      case 5: RT_LAUNCH(k_trace_sp8); break;
+      case 6: RT_LAUNCH(k_trace_sp12); break;
+      case 7: RT_LAUNCH(k_trace_sp16); break;
+      case 8: RT_LAUNCH(k_trace_sp24); break;
       default: RT_LAUNCH(k_trace_lb8); break;
     }
 #undef RT_LAUNCH
@@ -644,6 +791,27 @@ __global__ void k_scatter(const float4* __restrict__ acc_rgb, const int* __restr
 void launch_scatter(const float4* acc_rgb, const int* acc_cnt, const int* pix_map, int npix, float* out_rgb,
                     int* out_cnt, cudaStream_t st) {
   k_scatter<<<(npix + 255) / 256, 256, 0, st>>>(acc_rgb, acc_cnt, pix_map, npix, out_rgb, out_cnt);
+}
+
+// Renderer.cpp:262-265 after the last pass (i + 1 == N), on the pixels this shard owns:
+//   saveImage = updateImage / float(N) + image * (N - counter) / float(N)
+__global__ void k_composite(const float4* __restrict__ acc_rgb, const int* __restrict__ acc_cnt,
+                            const int* __restrict__ pix_map, int npix, int num_rays, float* rgb_inout) {
+  int pl = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pl >= npix) return;
+  const size_t pixel = (size_t)pix_map[pl];
+  const float4 a = acc_rgb[pl];
+  const float fn = (float)num_rays, miss = (float)(num_rays - acc_cnt[pl]);
+  const float s[3] = {a.x, a.y, a.z};
+#pragma unroll
+  for (int ch = 0; ch < 3; ch++) {
+    const float bg = rgb_inout[3 * pixel + ch];
+    rgb_inout[3 * pixel + ch] = __fadd_rn(__fdiv_rn(s[ch], fn), __fdiv_rn(__fmul_rn(bg, miss), fn));
+  }
+}
+void launch_composite(const float4* acc_rgb, const int* acc_cnt, const int* pix_map, int npix, int num_rays,
+                      float* rgb_inout, cudaStream_t st) {
+  k_composite<<<(npix + 255) / 256, 256, 0, st>>>(acc_rgb, acc_cnt, pix_map, npix, num_rays, rgb_inout);
 }
 
 // ----------------------------------------------------------------------------------------------

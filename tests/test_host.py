@@ -193,3 +193,56 @@ def test_cli_banner_and_errors(tmp_path):
     assert "Mode: Ray tracing" in r.stdout and "Photon map ON with 100 photons. Number of searched neighbours equals 3" in r.stdout
     assert "width: 380, height: 270" in r.stdout and "Output image filename: output.ppm" in r.stdout
     assert r.returncode == 1 and "Error Loading OFF file: Error loading OFF file: /nonexistent/cube_tri.off" in r.stderr
+
+
+# ----------------------------------------------------------------------------- host BVH builder
+def _check_bvh_policy(scene, nodes, slots):
+    """Every internal node of every per-mesh tree obeys BVH::from_triangles (source/BVH.h:100-161):
+    leaf iff one triangle (:123); cut axis = first axis of strictly largest extent of the node's vertex box
+    (:131-140); left child = the floor(n/2) triangles with the smallest key sum_v vertex[v][axis] (:141-158;
+    ties may fall on either side, the reference's std::sort is unstable).  Child boxes contain their vertices."""
+    P, T = scene.pos.reshape(-1, 3), scene.tri.reshape(-1, 3)
+    assert sorted(slots.tolist()) == list(range(scene.T)), "every triangle sits in exactly one leaf slot"
+    tri_mesh = scene.tri_mesh()
+    refs = nodes[:, 12:14].copy().view(np.int32)
+    checked = [0]
+
+    def walk(ref):  # -> array of global triangle ids below ref
+        if ref < 0:
+            return np.array([slots[~ref]])
+        l, r = walk(refs[ref, 0]), walk(refs[ref, 1])
+        for side, tris in ((0, l), (1, r)):
+            v = P[T[tris].reshape(-1)]
+            lo, hi = nodes[ref, 6 * side:6 * side + 3], nodes[ref, 6 * side + 3:6 * side + 6]
+            assert (lo <= v.min(0)).all() and (hi >= v.max(0)).all(), "child box does not contain its triangles"
+        both = np.concatenate([l, r])
+        if len(set(tri_mesh[both].tolist())) == 1:  # a node of a per-mesh tree (not the top-level join)
+            v = P[T[both].reshape(-1)]
+            ext = v.max(0) - v.min(0)
+            axis, longest = 0, np.float32(0)
+            for a in range(3):
+                if ext[a] > longest:
+                    axis, longest = a, ext[a]
+            key = lambda ids: (P[T[ids, 0], axis] + P[T[ids, 1], axis]) + P[T[ids, 2], axis]
+            assert len(l) == len(both) // 2, "left child must hold floor(n/2) triangles"
+            assert key(l).max() <= key(r).min(), f"node {ref}: not a median split on axis {axis}"
+            checked[0] += 1
+        return both
+
+    assert len(walk(0)) == scene.T
+    return checked[0]
+
+
+@pytest.mark.parametrize("name", ["stock", "lowres", "example"])
+def test_host_bvh_follows_the_reference_split_policy(name):
+    path = scene_path(name)
+    if not os.path.exists(path):
+        pytest.skip(f"{name} scene fixture not present")
+    scene = rt.Scene.load(path)
+    nodes, slots, depth = scene.build_bvh_host()
+    nonempty = int((np.diff(scene.mesh_tri_off) > 0).sum())
+    assert nodes.shape[0] == scene.T - 1, "a full binary tree with one-triangle leaves has T-1 internal nodes"
+    n_checked = _check_bvh_policy(scene, nodes, slots)
+    assert n_checked == scene.T - nonempty
+    biggest = int(np.diff(scene.mesh_tri_off).max())
+    assert depth >= int(np.ceil(np.log2(biggest))) and depth <= int(np.ceil(np.log2(biggest))) + 5
