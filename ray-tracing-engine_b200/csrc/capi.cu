@@ -175,6 +175,8 @@ int ensure_work(rt_ctx* c, size_t paths, bool path_mode) {
     CU(c->d_col1.ensure(paths));
     CU(c->d_qo1.ensure(paths));
     CU(c->d_qd1.ensure(paths));
+  }
+  if (path_mode || c->params.num_photons > 0) {
     CU(c->d_perm.ensure(paths));
     CU(c->d_sort_hist.ensure(kSortBuckets + 2));
   }
@@ -209,6 +211,7 @@ void fill_args(rt_ctx* c, RenderArgs& a, const int* pix_map, int npix, bool use_
   a.mode = p.mode == 1 ? 1 : 0;                // CommandLine.h:84-87: anything else is ray tracing
   a.photon = use_photons ? 1 : 0;
   a.k = p.k;
+  a.kd_frames = c->kd_height + 1;
   a.num_photons = p.num_photons;
   a.brute = (p.flags & RT_FLAG_BRUTE_FORCE) ? 1 : 0;
   a.seed_mixed = mix64(p.seed + kGolden);
@@ -227,7 +230,7 @@ void fill_args(rt_ctx* c, RenderArgs& a, const int* pix_map, int npix, bool use_
   a.contrib = c->d_contrib.p;
   a.occ = c->d_occ.p;
   a.hit_path = c->d_hit_path.p;
-  a.perm = (c->sort_hits && p.mode == 1) ? c->d_perm.p : nullptr;
+  a.perm = (c->sort_hits && (p.mode == 1 || use_photons)) ? c->d_perm.p : nullptr;
   a.sort_hist = c->d_sort_hist.p;
   a.sort_lo = c->bounds_lo;
   a.sort_inv_cell = make_float3(kSortGrid / std::max(c->bounds_hi.x - c->bounds_lo.x, 1e-20f),
@@ -264,7 +267,7 @@ int run_batch(rt_ctx* c, RenderArgs& a, int s0, int nsamp) {
     if ((rc = mark())) return rc;
     launch_trace_nearest(a, seg, grid, c->stream);
     if ((rc = mark())) return rc;
-    if (seg > 0 && a.perm) {
+    if ((seg > 0 || a.photon) && a.perm) {  // spatial order: shadow-ray coherence / k-NN traversal coherence
       launch_sort_hits(a, seg, c->stream);
       c->stats.kernel_launches += 3;
     }
@@ -949,7 +952,7 @@ int rt_knn(rt_ctx* c, const float* queries, int64_t n, int32_t k, int32_t* node_
   if (e == cudaSuccess) e = d_idx.ensure((size_t)n * k);
   if (e == cudaSuccess) e = cudaMemcpy(d_q.p, queries, sizeof(float) * 3 * (size_t)n, cudaMemcpyHostToDevice);
   if (e == cudaSuccess) {
-    launch_knn(c->scene, d_q.p, n, k, d_idx.p, c->d_counters.p, c->stream);
+    launch_knn(c->scene, d_q.p, n, k, c->kd_height + 1, d_idx.p, c->d_counters.p, c->stream);
     c->stats.kernel_launches++;
     e = cudaStreamSynchronize(c->stream);
   }

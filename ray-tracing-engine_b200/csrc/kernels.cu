@@ -517,7 +517,7 @@ constexpr size_t kSortSmem = (size_t)kSortCells * sizeof(unsigned);
 
 __global__ void __launch_bounds__(kSortThreads) k_sort_count(const RenderArgs A, const int seg) {
   extern __shared__ unsigned s_cnt[];
-  const unsigned n = A.q_count[kQHits0 + seg - 1];
+  const unsigned n = seg == 0 ? (unsigned)A.npix * (unsigned)A.nsamp : A.q_count[kQHits0 + seg - 1];
   const unsigned chunk = (n + gridDim.x - 1) / gridDim.x;
   const unsigned i0 = blockIdx.x * chunk, i1 = min(n, i0 + chunk);
   for (int b = threadIdx.x; b < kSortCells; b += kSortThreads) s_cnt[b] = 0;
@@ -556,7 +556,7 @@ __global__ void __launch_bounds__(1024) k_sort_scan(unsigned* hist) {
 }
 __global__ void __launch_bounds__(kSortThreads) k_sort_scatter(const RenderArgs A, const int seg) {
   extern __shared__ unsigned s_cnt[];
-  const unsigned n = A.q_count[kQHits0 + seg - 1];
+  const unsigned n = seg == 0 ? (unsigned)A.npix * (unsigned)A.nsamp : A.q_count[kQHits0 + seg - 1];
   const unsigned chunk = (n + gridDim.x - 1) / gridDim.x;
   const unsigned i0 = blockIdx.x * chunk, i1 = min(n, i0 + chunk);
   for (int b = threadIdx.x; b < kSortCells; b += kSortThreads) s_cnt[b] = 0;
@@ -585,28 +585,43 @@ void launch_sort_hits(const RenderArgs& a, int seg, cudaStream_t st) {
 // k_shade: one thread per ray of the segment
 // ----------------------------------------------------------------------------------------------
 // Renderer.cpp:63-104
-RT_DI float3 shade_photon(const DScene& S, float3 dir, float3 n, float3 P, const DMaterial& m, int k, int num_photons,
-                          unsigned long long& visits) {
+// A query in which two candidates tied (see kd_knearest_sorted): repeat it with the literal heap restatement,
+// whose element moves are libstdc++'s, and hand the result back in the caller's arrays.  Rare by construction.
+__device__ __noinline__ void knn_exact_redo(const DScene& S, float3 q, int k, float* sd, int* si, int ks) {
   float hd[kMaxK];
   int hi[kMaxK];
   int kst[3 * kKdStack];
   KdHeap H{hd, hi, 1};
-  kd_knearest(S, P, k, H, kst, 1, visits);
-  float r = H.d(k - 1);  // farthest of the k (result is sorted ascending)
+  unsigned long long visits = 0;
+  kd_knearest(S, q, k, H, kst, 1, visits);
+  for (int j = 0; j < k; j++) {
+    sd[j * ks] = hd[j];
+    si[j * ks] = hi[j];
+  }
+}
+
+RT_DI float3 shade_photon(const DScene& S, float3 dir, float3 n, float3 P, const DMaterial& m, int k, int num_photons,
+                          float* sd, int* si, int* kst, unsigned long long& visits) {
+  if (kd_knearest_sorted(S, P, k, sd, si, kst, kBlock, visits)) knn_exact_redo(S, P, k, sd, si, kBlock);
+  float r = sd[(k - 1) * kBlock];  // farthest of the k (candidates are in ascending distance)
   float area = (float)__dmul_rn(__dmul_rn(3.141592653589793, (double)r), (double)r);
   float3 avg = f3(0.f, 0.f, 0.f);
   float cnt = 0.f;
   for (int j = 0; j < k; j++) {
-    avg = v_add(avg, f3(__ldg(S.kd_dir + H.i(j))));
+    avg = v_add(avg, f3(__ldg(S.kd_dir + si[j * kBlock])));
     cnt = __fadd_rn(cnt, 1.f);
   }
   float rad = __fmul_rn(__fdiv_rn(__fdiv_rn(cnt, area), (float)num_photons), 100.f);
   float3 bsdf = evaluate_color_response(m, n, v_norm(avg), v_neg(dir));
   return v_scl(bsdf, rad);
 }
+// dynamic shared memory of the kernels that run kd_knearest_sorted: k candidate (distance, index) pairs and
+// `frames` stack frames of 3 ints per thread
+size_t knn_smem_bytes(int k, int frames) { return (size_t)(2 * k + 3 * frames) * kBlock * sizeof(int); }
 
 template <int MODE, bool PHOTON>
 __global__ void __launch_bounds__(kBlock, PHOTON ? 1 : 8) k_shade(const RenderArgs A, const int seg) {
+  extern __shared__ int s_knn[];  // PHOTON only: [2k + 3*frames][kBlock]
   const DScene& S = A.scene;
   const unsigned n = seg == 0 ? (unsigned)A.npix * (unsigned)A.nsamp : A.q_count[kQHits0 + seg - 1];
   const float4* qo_in = A.ray_o[seg & 1];
@@ -617,7 +632,7 @@ __global__ void __launch_bounds__(kBlock, PHOTON ? 1 : 8) k_shade(const RenderAr
   unsigned n_hit = 0, n_knn = 0;
   unsigned long long n_visits = 0;
 
-  const bool permuted = seg > 0 && A.perm != nullptr;
+  const bool permuted = (seg > 0 || PHOTON) && A.perm != nullptr;
   for (unsigned base = blockIdx.x * kBlock; base < n; base += gridDim.x * kBlock) {
     const unsigned slot = base + threadIdx.x;
     const unsigned i = (permuted && slot < n) ? A.perm[slot] : slot;
@@ -669,7 +684,8 @@ __global__ void __launch_bounds__(kBlock, PHOTON ? 1 : 8) k_shade(const RenderAr
       A.hit_path[j] = (int)p;
       if (PHOTON) {
         n_knn++;
-        float3 c = shade_photon(S, d, nrm, P, m, A.k, A.num_photons, n_visits);
+        float3 c = shade_photon(S, d, nrm, P, m, A.k, A.num_photons, (float*)s_knn + threadIdx.x,
+                                s_knn + A.k * kBlock + threadIdx.x, s_knn + 2 * A.k * kBlock + threadIdx.x, n_visits);
         A.contrib[shadow_slot(j, 0)] = make_float4(c.x, c.y, c.z, 0.f);
         A.occ[shadow_slot(j, 0)] = 0;
         for (unsigned l = 1; l < (unsigned)kShadowLights; l++) A.occ[shadow_slot(j, l)] = 1;
@@ -714,14 +730,19 @@ __global__ void __launch_bounds__(kBlock, PHOTON ? 1 : 8) k_shade(const RenderAr
 }
 
 void launch_shade(const RenderArgs& a, int seg, int grid, cudaStream_t st) {
+  const size_t sm = a.photon ? knn_smem_bytes(a.k, a.kd_frames) : 0;
+  if (a.photon) {
+    cudaFuncSetAttribute(k_shade<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    cudaFuncSetAttribute(k_shade<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+  }
   if (a.mode == 0) {
     if (a.photon)
-      k_shade<0, true><<<grid, kBlock, 0, st>>>(a, seg);
+      k_shade<0, true><<<grid, kBlock, sm, st>>>(a, seg);
     else
       k_shade<0, false><<<grid, kBlock, 0, st>>>(a, seg);
   } else {
     if (a.photon)
-      k_shade<1, true><<<grid, kBlock, 0, st>>>(a, seg);
+      k_shade<1, true><<<grid, kBlock, sm, st>>>(a, seg);
     else
       k_shade<1, false><<<grid, kBlock, 0, st>>>(a, seg);
   }
@@ -832,21 +853,24 @@ void launch_bsdf(DMaterial m, const float* n_wi_wo, long long n, float* rgb, cud
 
 __global__ void __launch_bounds__(kBlock) k_knn(const DScene S, const float* __restrict__ q3, long long n, int k,
                                                 int* node_index, unsigned long long* counters) {
+  extern __shared__ int s_knn[];
   long long i = (long long)blockIdx.x * kBlock + threadIdx.x;
   if (i >= n) return;
-  float hd[kMaxK];
-  int hi[kMaxK];
-  int kst[3 * kKdStack];
-  KdHeap H{hd, hi, 1};
+  float* sd = (float*)s_knn + threadIdx.x;
+  int* si = s_knn + k * kBlock + threadIdx.x;
   unsigned long long visits = 0;
-  kd_knearest(S, f3(q3[3 * i], q3[3 * i + 1], q3[3 * i + 2]), k, H, kst, 1, visits);
-  for (int j = 0; j < k; j++) node_index[i * k + j] = H.i(j);
+  const float3 q = f3(q3[3 * i], q3[3 * i + 1], q3[3 * i + 2]);
+  if (kd_knearest_sorted(S, q, k, sd, si, s_knn + 2 * k * kBlock + threadIdx.x, kBlock, visits))
+    knn_exact_redo(S, q, k, sd, si, kBlock);
+  for (int j = 0; j < k; j++) node_index[i * k + j] = si[j * kBlock];
   atomicAdd(counters + kCntKdVisits, visits);
   atomicAdd(counters + kCntKnn, 1ull);
 }
-void launch_knn(const DScene& s, const float* q3, long long n, int k, int* node_index, unsigned long long* counters,
-                cudaStream_t st) {
-  k_knn<<<(int)((n + kBlock - 1) / kBlock), kBlock, 0, st>>>(s, q3, n, k, node_index, counters);
+void launch_knn(const DScene& s, const float* q3, long long n, int k, int kd_frames, int* node_index,
+                unsigned long long* counters, cudaStream_t st) {
+  const size_t sm = knn_smem_bytes(k, kd_frames);
+  cudaFuncSetAttribute(k_knn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+  k_knn<<<(int)((n + kBlock - 1) / kBlock), kBlock, sm, st>>>(s, q3, n, k, node_index, counters);
 }
 
 // ----------------------------------------------------------------------------------------------

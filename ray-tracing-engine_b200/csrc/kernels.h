@@ -33,6 +33,7 @@ struct RenderArgs {
   int mode;         // 0 ray, 1 path
   int photon;       // 1: gather from the photon map instead of direct lighting
   int k;            // neighbours
+  int kd_frames;    // kd-tree height + 1: stack frames per thread of kd_knearest_sorted
   int num_photons;  // REQUESTED photon count (Renderer.cpp:99)
   int brute;        // 1: O(T) scan instead of BVH
   int stack_depth;  // traversal stack entries per ray (>= bvh depth)
@@ -85,7 +86,7 @@ void launch_bsdf(DMaterial m, const float* n_wi_wo, long long n, float* rgb, cud
 // photon emission: path q = light*npaths + j traces path (first_path + j) of `light`
 void launch_emit(const DScene& s, uint64_t seed_mixed, int per_light, float light_pdf, int first_path, int npaths,
                  int brute, float4* out_a, float4* out_b, unsigned long long* counters, cudaStream_t st);
-void launch_knn(const DScene& s, const float* q3, long long n, int k, int* node_index, unsigned long long* counters,
-                cudaStream_t st);
+void launch_knn(const DScene& s, const float* q3, long long n, int k, int kd_frames, int* node_index,
+                unsigned long long* counters, cudaStream_t st);
 
 }  // namespace rtb

@@ -598,4 +598,97 @@ RT_DI void kd_knearest(const DScene& S, float3 q, int k, KdHeap& H, int* kst, in
   H.sort(k);
 }
 
+// ------------------------------------------------------------------------------------------------
+// kd_knearest_sorted: the same query (kdtree.h:87-107,180-195, quirks included) restated for SIMT.
+//
+// ncu on the heap version inside k_shade (profiles/r1_photon_k_shade_full.csv): 4.9-8.8 of 32 lanes active and
+// 26-32 % of the issue slots spent in the LSU on the local-memory heap and recursion stack.  What the reference
+// computes only depends on the candidate SET and its two largest distances:
+//     if (d < best) { evict the largest; best = largest of what is left (BEFORE the insertion); insert }
+// (for k = 1 "what is left" is empty and libstdc++'s front() still returns the evicted element, kdtree.h:93-96),
+// and sort_heap returns the set in ascending distance.  So the candidates live in an ascending array (an
+// insertion is one predictable shift loop, the result needs no final sort), array and stack sit in shared
+// memory ([slot][thread], conflict-free for any per-thread index), and the recursion is one loop in which every
+// iteration visits exactly one node.
+// Ties: two candidates at exactly the same binary32 distance (0.03 % of the queries at k = 50 / 357 k photons;
+// also a seed node that is visited again while it is still a candidate) are ordered -- and, when they tie for
+// the largest, evicted -- by libstdc++'s heap mechanics.  The function returns true when it has seen such a tie
+// and the caller repeats that query with kd_knearest, the literal heap restatement; otherwise the result is
+// exactly the reference's (tests: test_kdtree_and_knn_match_reference, test_knn_parity_at_scale).
+// sd/si: k slots, kst: 3 ints per frame, all with stride ks between a thread's consecutive slots.
+// ------------------------------------------------------------------------------------------------
+RT_DI bool kd_knearest_sorted(const DScene& S, float3 q, int k, float* sd, int* si, int* kst, int ks,
+                              unsigned long long& visits) {
+  bool tie = false;
+  for (int j = 0; j < k; j++) {  // kdtree.h:186: the first k nodes of the array seed the candidates
+    const float dj = v_dist(f3(__ldg(S.kd_pos + j)), q);
+    int m = j - 1;
+    while (m >= 0 && sd[m * ks] > dj) {
+      sd[(m + 1) * ks] = sd[m * ks];
+      si[(m + 1) * ks] = si[m * ks];
+      m--;
+    }
+    if (m >= 0 && sd[m * ks] == dj) tie = true;
+    sd[(m + 1) * ks] = dj;
+    si[(m + 1) * ks] = j;
+  }
+  float best = sd[(k - 1) * ks];  // m_bestdist (a distance, not squared)
+  int sp = 0, b = 0, e = S.kd_count, axis = 0;
+  unsigned nv = 0;
+  while (e > b) {
+    const int n = b + (e - b) / 2;
+    nv++;
+    const float4 p = __ldg(S.kd_pos + n);
+    const float dnode = v_dist(f3(p), q);
+    if (dnode < best) {
+      best = sd[(k > 1 ? k - 2 : 0) * ks];  // k == 1: front() is the evicted candidate itself
+      int m = k - 2;
+      while (m >= 0 && sd[m * ks] > dnode) {
+        sd[(m + 1) * ks] = sd[m * ks];
+        si[(m + 1) * ks] = si[m * ks];
+        m--;
+      }
+      // a tie with the evicted largest (old slot k-1) cannot matter: dnode < best <= it
+      if (m >= 0 && sd[m * ks] == dnode) tie = true;
+      sd[(m + 1) * ks] = dnode;
+      si[(m + 1) * ks] = n;
+    }
+    int nb = b, ne = b;  // empty
+    if (best != 0.f) {   // kdtree.h:101: best == 0 returns without visiting the children
+      const float pa = axis == 0 ? p.x : (axis == 1 ? p.y : p.z);
+      const float qa = axis == 0 ? q.x : (axis == 1 ? q.y : q.z);
+      const float dx = __fsub_rn(pa, qa);
+      int fb, fe;
+      if (dx > 0.f) {
+        nb = b, ne = n, fb = n + 1, fe = e;
+      } else {
+        nb = n + 1, ne = e, fb = b, fe = n;
+      }
+      axis = axis == 2 ? 0 : axis + 1;
+      if (fe > fb) {  // an empty far side has nothing to visit
+        kst[(3 * sp) * ks] = fb;
+        kst[(3 * sp + 1) * ks] = fe | (axis << 28);
+        kst[(3 * sp + 2) * ks] = __float_as_int(dx);
+        sp++;
+      }
+    }
+    b = nb;
+    e = ne;
+    // near side empty: resume at the newest frame whose far side survives `dx*dx >= m_bestdist` (kdtree.h:105,
+    // squared against not squared) and the exact plane-distance bound (see kd_knearest)
+    while (e <= b && sp > 0) {
+      sp--;
+      const float dx = __int_as_float(kst[(3 * sp + 2) * ks]);
+      if (__dmul_rn((double)dx, (double)dx) >= (double)best) continue;
+      if (fabsf(dx) * 0.9999995f >= best) continue;
+      const int fe = kst[(3 * sp + 1) * ks];
+      b = kst[(3 * sp) * ks];
+      axis = (fe >> 28) & 3;
+      e = fe & 0x0fffffff;
+    }
+  }
+  visits += nv;
+  return tie;
+}
+
 }  // namespace rtb

@@ -234,6 +234,30 @@ def test_kdtree_and_knn_match_reference(rt, gold):
         assert beq(got, g[f"knn_{k}"]), f"k={k}: the k photons or their order differ from kdtree::knearest"
 
 
+
+def test_knn_parity_at_scale(rt, O):
+    """The SIMT k-NN (sorted candidates + tie fallback) against kdtree::knearest restated on the CPU, on photon
+    maps the GPU emitted: 35 k photons / k=10 and 357 k photons / k=50, queries near and exactly on photons
+    (distance 0, ties).  Indices AND order must be identical for every query."""
+    scene = rt.Scene.load(scene_path("stock"))
+    port = O.PortOracle(O.FlatScene.load(scene_path("stock")))
+    g = np.random.default_rng(5)
+    for photons, k, nq in ((50000, 10, 20000), (500000, 50, 6000)):
+        r = rt.Renderer(scene, 1, 0, None, photons, k, seed=1)
+        plist = r.emit_photons()[0]
+        r.set_photons(plist)
+        nodes, left, right, root = r.kdtree()
+        pm = port.photon_map_from_list(plist)
+        on, ol, orr, oroot = pm.layout()
+        assert beq(on, nodes) and (ol == left).all() and (orr == right).all() and oroot == root
+        q = nodes[g.integers(0, len(nodes), nq), :3] + g.normal(size=(nq, 3)).astype(np.float32) * np.float32(0.02)
+        q[: nq // 4] = nodes[g.integers(0, len(nodes), nq // 4), :3]
+        idx = r.knearest(q, k)
+        out, visited, oidx = pm.knn(q, k, want_index=True)
+        assert (idx == oidx).all(), f"p={photons} k={k}: {(idx != oidx).any(axis=1).sum()} of {nq} queries differ"
+        r.close()
+
+
 def test_knn_errors(rt, gold):
     g = gold("photons.npz")
     r = make_renderer(rt, "stock")
