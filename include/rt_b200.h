@@ -124,6 +124,8 @@ typedef struct rt_stats {
   double create_ms;        /* host wall time of rt_create ...                                        */
   double bvh_build_ms;     /* ... of which the host BVH build                                        */
   double kd_build_ms;      /* host wall time of the last kd-tree build (rt_set_photons)              */
+  uint64_t kd_visits;      /* kd-tree nodes visited by the k-NN queries: kdtree::visited() summed, minus
+                              the visits the exact plane-distance bound skips                        */
 } rt_stats;
 
 typedef struct rt_ctx rt_ctx;

@@ -62,7 +62,7 @@ class rt_stats(C.Structure):
                 ("samples", C.c_uint64), ("kernel_launches", C.c_uint64), ("device_ms", C.c_double),
                 ("trace_ms", C.c_double), ("photon_ms", C.c_double), ("bvh_nodes", C.c_int32),
                 ("bvh_depth", C.c_int32), ("photons_stored", C.c_int64), ("create_ms", C.c_double),
-                ("bvh_build_ms", C.c_double), ("kd_build_ms", C.c_double)]
+                ("bvh_build_ms", C.c_double), ("kd_build_ms", C.c_double), ("kd_visits", C.c_uint64)]
 
 
 # every symbol include/rt_b200.h declares: name -> (restype, argtypes)

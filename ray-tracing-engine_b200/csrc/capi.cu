@@ -293,6 +293,7 @@ int pull_counters(rt_ctx* c) {
   s.shadow_rays = h[kCntShadow];
   s.photon_rays = h[kCntPhotonRays];
   s.knn_queries = h[kCntKnn];
+  s.kd_visits = h[kCntKdVisits];
   uint64_t nearest = h[kCntNearest];
   s.bounce_rays = nearest >= s.samples ? nearest - s.samples : 0;
   s.primary_rays = nearest - s.bounce_rays;

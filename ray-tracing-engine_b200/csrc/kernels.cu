@@ -587,28 +587,25 @@ void launch_sort_hits(const RenderArgs& a, int seg, cudaStream_t st) {
 // Renderer.cpp:63-104
 // A query in which two candidates tied (see kd_knearest_sorted): repeat it with the literal heap restatement,
 // whose element moves are libstdc++'s, and hand the result back in the caller's arrays.  Rare by construction.
-__device__ __noinline__ void knn_exact_redo(const DScene& S, float3 q, int k, float* sd, int* si, int ks) {
+__device__ __noinline__ void knn_exact_redo(const DScene& S, float3 q, int k, unsigned long long* sc, int ks) {
   float hd[kMaxK];
   int hi[kMaxK];
   int kst[3 * kKdStack];
   KdHeap H{hd, hi, 1};
   unsigned long long visits = 0;
   kd_knearest(S, q, k, H, kst, 1, visits);
-  for (int j = 0; j < k; j++) {
-    sd[j * ks] = hd[j];
-    si[j * ks] = hi[j];
-  }
+  for (int j = 0; j < k; j++) sc[j * ks] = kd_pack(hd[j], hi[j]);
 }
 
 RT_DI float3 shade_photon(const DScene& S, float3 dir, float3 n, float3 P, const DMaterial& m, int k, int num_photons,
-                          float* sd, int* si, int* kst, unsigned long long& visits) {
-  if (kd_knearest_sorted(S, P, k, sd, si, kst, kBlock, visits)) knn_exact_redo(S, P, k, sd, si, kBlock);
-  float r = sd[(k - 1) * kBlock];  // farthest of the k (candidates are in ascending distance)
+                          unsigned long long* sc, int* kst, unsigned long long& visits) {
+  if (kd_knearest_sorted(S, P, k, sc, kst, kBlock, visits)) knn_exact_redo(S, P, k, sc, kBlock);
+  float r = kd_dist_of(sc[(k - 1) * kBlock]);  // farthest of the k (candidates are in ascending distance)
   float area = (float)__dmul_rn(__dmul_rn(3.141592653589793, (double)r), (double)r);
   float3 avg = f3(0.f, 0.f, 0.f);
   float cnt = 0.f;
   for (int j = 0; j < k; j++) {
-    avg = v_add(avg, f3(__ldg(S.kd_dir + si[j * kBlock])));
+    avg = v_add(avg, f3(__ldg(S.kd_dir + kd_index_of(sc[j * kBlock]))));
     cnt = __fadd_rn(cnt, 1.f);
   }
   float rad = __fmul_rn(__fdiv_rn(__fdiv_rn(cnt, area), (float)num_photons), 100.f);
@@ -620,8 +617,8 @@ RT_DI float3 shade_photon(const DScene& S, float3 dir, float3 n, float3 P, const
 size_t knn_smem_bytes(int k, int frames) { return (size_t)(2 * k + 3 * frames) * kBlock * sizeof(int); }
 
 template <int MODE, bool PHOTON>
-__global__ void __launch_bounds__(kBlock, PHOTON ? 1 : 8) k_shade(const RenderArgs A, const int seg) {
-  extern __shared__ int s_knn[];  // PHOTON only: [2k + 3*frames][kBlock]
+__global__ void __launch_bounds__(kBlock, PHOTON ? 6 : 8) k_shade(const RenderArgs A, const int seg) {
+  extern __shared__ unsigned long long s_knn[];  // PHOTON only: k 64-bit candidate rows, then 3*frames int rows
   const DScene& S = A.scene;
   const unsigned n = seg == 0 ? (unsigned)A.npix * (unsigned)A.nsamp : A.q_count[kQHits0 + seg - 1];
   const float4* qo_in = A.ray_o[seg & 1];
@@ -684,8 +681,8 @@ __global__ void __launch_bounds__(kBlock, PHOTON ? 1 : 8) k_shade(const RenderAr
       A.hit_path[j] = (int)p;
       if (PHOTON) {
         n_knn++;
-        float3 c = shade_photon(S, d, nrm, P, m, A.k, A.num_photons, (float*)s_knn + threadIdx.x,
-                                s_knn + A.k * kBlock + threadIdx.x, s_knn + 2 * A.k * kBlock + threadIdx.x, n_visits);
+        float3 c = shade_photon(S, d, nrm, P, m, A.k, A.num_photons, s_knn + threadIdx.x,
+                                (int*)(s_knn + A.k * kBlock) + threadIdx.x, n_visits);
         A.contrib[shadow_slot(j, 0)] = make_float4(c.x, c.y, c.z, 0.f);
         A.occ[shadow_slot(j, 0)] = 0;
         for (unsigned l = 1; l < (unsigned)kShadowLights; l++) A.occ[shadow_slot(j, l)] = 1;
@@ -853,16 +850,15 @@ void launch_bsdf(DMaterial m, const float* n_wi_wo, long long n, float* rgb, cud
 
 __global__ void __launch_bounds__(kBlock) k_knn(const DScene S, const float* __restrict__ q3, long long n, int k,
                                                 int* node_index, unsigned long long* counters) {
-  extern __shared__ int s_knn[];
+  extern __shared__ unsigned long long s_knn[];
   long long i = (long long)blockIdx.x * kBlock + threadIdx.x;
   if (i >= n) return;
-  float* sd = (float*)s_knn + threadIdx.x;
-  int* si = s_knn + k * kBlock + threadIdx.x;
+  unsigned long long* sc = s_knn + threadIdx.x;
   unsigned long long visits = 0;
   const float3 q = f3(q3[3 * i], q3[3 * i + 1], q3[3 * i + 2]);
-  if (kd_knearest_sorted(S, q, k, sd, si, s_knn + 2 * k * kBlock + threadIdx.x, kBlock, visits))
-    knn_exact_redo(S, q, k, sd, si, kBlock);
-  for (int j = 0; j < k; j++) node_index[i * k + j] = si[j * kBlock];
+  if (kd_knearest_sorted(S, q, k, sc, (int*)(s_knn + k * kBlock) + threadIdx.x, kBlock, visits))
+    knn_exact_redo(S, q, k, sc, kBlock);
+  for (int j = 0; j < k; j++) node_index[i * k + j] = kd_index_of(sc[j * kBlock]);
   atomicAdd(counters + kCntKdVisits, visits);
   atomicAdd(counters + kCntKnn, 1ull);
 }

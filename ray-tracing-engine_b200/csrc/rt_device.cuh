@@ -617,22 +617,29 @@ RT_DI void kd_knearest(const DScene& S, float3 q, int k, KdHeap& H, int* kst, in
 // exactly the reference's (tests: test_kdtree_and_knn_match_reference, test_knn_parity_at_scale).
 // sd/si: k slots, kst: 3 ints per frame, all with stride ks between a thread's consecutive slots.
 // ------------------------------------------------------------------------------------------------
-RT_DI bool kd_knearest_sorted(const DScene& S, float3 q, int k, float* sd, int* si, int* kst, int ks,
+RT_DI unsigned long long kd_pack(float d, int idx) {  // distances are >= 0: their bit patterns order like the values
+  return ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)idx;
+}
+RT_DI float kd_dist_of(unsigned long long c) { return __uint_as_float((unsigned)(c >> 32)); }
+RT_DI int kd_index_of(unsigned long long c) { return (int)(unsigned)c; }
+
+// sc: k candidate slots (distance bits << 32 | node index, one 64-bit shared-memory access per move),
+// kst: 3 ints per frame (far begin, far end | next axis << 28, threshold bits); stride ks between a thread's slots.
+RT_DI bool kd_knearest_sorted(const DScene& S, float3 q, int k, unsigned long long* sc, int* kst, int ks,
                               unsigned long long& visits) {
   bool tie = false;
   for (int j = 0; j < k; j++) {  // kdtree.h:186: the first k nodes of the array seed the candidates
-    const float dj = v_dist(f3(__ldg(S.kd_pos + j)), q);
+    const unsigned dj = __float_as_uint(v_dist(f3(__ldg(S.kd_pos + j)), q));
     int m = j - 1;
-    while (m >= 0 && sd[m * ks] > dj) {
-      sd[(m + 1) * ks] = sd[m * ks];
-      si[(m + 1) * ks] = si[m * ks];
+    unsigned long long w = 0;
+    while (m >= 0 && (unsigned)((w = sc[m * ks]) >> 32) > dj) {
+      sc[(m + 1) * ks] = w;
       m--;
     }
-    if (m >= 0 && sd[m * ks] == dj) tie = true;
-    sd[(m + 1) * ks] = dj;
-    si[(m + 1) * ks] = j;
+    if (m >= 0 && (unsigned)(w >> 32) == dj) tie = true;
+    sc[(m + 1) * ks] = ((unsigned long long)dj << 32) | (unsigned)j;
   }
-  float best = sd[(k - 1) * ks];  // m_bestdist (a distance, not squared)
+  float best = kd_dist_of(sc[(k - 1) * ks]);  // m_bestdist (a distance, not squared)
   int sp = 0, b = 0, e = S.kd_count, axis = 0;
   unsigned nv = 0;
   while (e > b) {
@@ -641,46 +648,57 @@ RT_DI bool kd_knearest_sorted(const DScene& S, float3 q, int k, float* sd, int* 
     const float4 p = __ldg(S.kd_pos + n);
     const float dnode = v_dist(f3(p), q);
     if (dnode < best) {
-      best = sd[(k > 1 ? k - 2 : 0) * ks];  // k == 1: front() is the evicted candidate itself
+      // evict the largest; m_bestdist = the largest of the rest BEFORE the insertion (k == 1: libstdc++'s
+      // front() after pop_heap is the evicted candidate itself), kdtree.h:93-96
+      best = kd_dist_of(sc[(k > 1 ? k - 2 : 0) * ks]);
+      const unsigned dn = __float_as_uint(dnode);
       int m = k - 2;
-      while (m >= 0 && sd[m * ks] > dnode) {
-        sd[(m + 1) * ks] = sd[m * ks];
-        si[(m + 1) * ks] = si[m * ks];
+      unsigned long long w = 0;
+      while (m >= 0 && (unsigned)((w = sc[m * ks]) >> 32) > dn) {
+        sc[(m + 1) * ks] = w;
         m--;
       }
       // a tie with the evicted largest (old slot k-1) cannot matter: dnode < best <= it
-      if (m >= 0 && sd[m * ks] == dnode) tie = true;
-      sd[(m + 1) * ks] = dnode;
-      si[(m + 1) * ks] = n;
+      if (m >= 0 && (unsigned)(w >> 32) == dn) tie = true;
+      sc[(m + 1) * ks] = ((unsigned long long)dn << 32) | (unsigned)n;
     }
     int nb = b, ne = b;  // empty
     if (best != 0.f) {   // kdtree.h:101: best == 0 returns without visiting the children
-      const float pa = axis == 0 ? p.x : (axis == 1 ? p.y : p.z);
-      const float qa = axis == 0 ? q.x : (axis == 1 ? q.y : q.z);
+      float pa = p.x, qa = q.x;
+      if (axis == 1) pa = p.y, qa = q.y;
+      if (axis == 2) pa = p.z, qa = q.z;
       const float dx = __fsub_rn(pa, qa);
-      int fb, fe;
-      if (dx > 0.f) {
-        nb = b, ne = n, fb = n + 1, fe = e;
-      } else {
-        nb = n + 1, ne = e, fb = b, fe = n;
-      }
+      const bool left_near = dx > 0.f;
+      nb = left_near ? b : n + 1;
+      ne = left_near ? n : e;
+      const int fb = left_near ? n + 1 : b, fe = left_near ? e : n;
       axis = axis == 2 ? 0 : axis + 1;
       if (fe > fb) {  // an empty far side has nothing to visit
-        kst[(3 * sp) * ks] = fb;
-        kst[(3 * sp + 1) * ks] = fe | (axis << 28);
-        kst[(3 * sp + 2) * ks] = __float_as_int(dx);
-        sp++;
+        // The far side is skipped when `dx*dx >= m_bestdist` (kdtree.h:105: a square against a distance, in
+        // binary64, where the square of a binary32 is exact) or when |dx| >= m_bestdist (every photon behind the
+        // plane is at least |dx| away, none can pass `d < m_bestdist`, so the visit would change nothing; the
+        // factor keeps a 2-ulp margin for sqrt(fl(a*a)) < |a|).  Both are "m_bestdist <= a number known now":
+        // the largest binary32 <= dx*dx, and fl(|dx| * 0.9999995) -- so one threshold is stored and the pop
+        // costs one comparison.
+        // For k >= 2 m_bestdist never grows (it is the second largest candidate and candidates only get
+        // closer), so a far side that is already skippable now is not pushed at all.  (k == 1: m_bestdist is
+        // the distance of the candidate evicted LAST, which can go up again.)
+        const float t_sq = __double2float_rd(__dmul_rn((double)dx, (double)dx));
+        const float t_pl = __fmul_rn(fabsf(dx), 0.9999995f);
+        const float thr = fmaxf(t_sq, t_pl);
+        if (best > thr || k == 1) {
+          kst[(3 * sp) * ks] = fb;
+          kst[(3 * sp + 1) * ks] = fe | (axis << 28);
+          kst[(3 * sp + 2) * ks] = __float_as_int(thr);
+          sp++;
+        }
       }
     }
     b = nb;
     e = ne;
-    // near side empty: resume at the newest frame whose far side survives `dx*dx >= m_bestdist` (kdtree.h:105,
-    // squared against not squared) and the exact plane-distance bound (see kd_knearest)
-    while (e <= b && sp > 0) {
+    while (e <= b && sp > 0) {  // near side empty: resume at the newest frame whose far side survives
       sp--;
-      const float dx = __int_as_float(kst[(3 * sp + 2) * ks]);
-      if (__dmul_rn((double)dx, (double)dx) >= (double)best) continue;
-      if (fabsf(dx) * 0.9999995f >= best) continue;
+      if (best <= __int_as_float(kst[(3 * sp + 2) * ks])) continue;
       const int fe = kst[(3 * sp + 1) * ks];
       b = kst[(3 * sp) * ks];
       axis = (fe >> 28) & 3;

@@ -9,4 +9,4 @@ for (N, mode, p, k) in ((128, 1, 50000, 10), (1, 0, 500000, 50)):
     s, c = r.render_accumulate(); r.reset_stats()
     s, c = r.render_accumulate(); st = r.stats()
     print(f"-m {mode} -N {N} -p {p} -k {k}: photon map {tb*1e3:.0f} ms (emit kernel {st0['photon_ms']:.1f} ms, kd build {st0['kd_build_ms']:.0f} ms, stored {st0['photons_stored']}); "
-          f"render device {st['device_ms']:.1f} ms, rays {st['rays']}, queries {st['knn_queries']}, checksum {float(s.sum()):.3f}", flush=True)
+          f"render device {st['device_ms']:.1f} ms, rays {st['rays']}, queries {st['knn_queries']} ({st['kd_visits']/max(st['knn_queries'],1):.1f} node visits each), trace {st['trace_ms']:.1f} ms, checksum {float(s.sum()):.3f}", flush=True)
