@@ -81,7 +81,8 @@ typedef struct rt_params {
   int32_t shard_rank, shard_count, shard_tile;
   /* sharding by sample index: render samples [sample_first, sample_first + sample_count) of the
    * num_rays-sample frame (sample_count <= 0: all of them).  The stratum of a sample depends on its
-   * GLOBAL index (source/RayTracer.h:111-115), so num_rays stays the global N on every rank. */
+   * GLOBAL index (source/RayTracer.h:111-115), so num_rays stays the global N on every rank.
+   * sample_first == num_rays with sample_count == 0 is the empty range (a rank with no share). */
   int32_t sample_first, sample_count;
   /* samples traced per wavefront batch; 0 = choose from free HBM */
   int32_t samples_per_batch;

@@ -157,6 +157,11 @@ int ensure_pix_map(rt_ctx* c) {
   return RT_OK;
 }
 
+// stack entries a traversal can need: the whole tree from node 0 (k_emit), or the root list plus one mesh's tree
+int trace_stack_depth(const rt_ctx* c) {
+  return std::max(std::max(c->bvh.depth, c->scene.num_roots > 0 ? c->bvh.mesh_depth + c->scene.num_roots : 0), 1);
+}
+
 // bytes of wavefront state per path slot (ensure_work below)
 constexpr size_t kBytesPerPath = 16 * 2 + 32 * 2 + 16 + 3 * (32 + 16 + 1) + 4 + 4;
 
@@ -217,7 +222,7 @@ void fill_args(rt_ctx* c, RenderArgs& a, const int* pix_map, int npix, bool use_
   a.seed_mixed = mix64(p.seed + kGolden);
   a.pix_map = pix_map;
   a.npix = npix;
-  a.stack_depth = std::max(c->bvh.depth, 1);
+  a.stack_depth = trace_stack_depth(c);
   a.col0 = c->d_col0.p;
   a.col1 = c->d_col1.p;
   a.ray_o[0] = c->d_qo0.p;
@@ -549,7 +554,7 @@ int rt_create(const rt_scene* s, const rt_params* p, int device, rt_ctx** out) {
   const double t_bvh0 = now_ms();
   build_bvh(c->V, s->positions, c->T, s->triangles, c->M, s->mesh_first_triangle, extent, pad_fraction, c->bvh);
   c->stats.bvh_build_ms = now_ms() - t_bvh0;
-  if (c->bvh.depth > kStackDepth) {
+  if (std::max(c->bvh.depth, c->bvh.mesh_depth + kMaxRoots) > kStackDepth) {
     rt_destroy(c);
     return fail(RT_ERR_INVALID, "BVH deeper than the traversal stack");
   }
@@ -626,6 +631,13 @@ int rt_create(const rt_scene* s, const rt_params* p, int device, rt_ctx** out) {
   S.kd_pos = c->d_kd_pos.p;
   S.kd_dir = c->d_kd_dir.p;
   S.kd_count = 0;
+  const int nroots = (int)(c->bvh.roots.size() / 7);
+  S.num_roots = (nroots >= 2 && nroots <= kMaxRoots && !getenv("RT_NO_ROOT_LIST")) ? nroots : 0;
+  for (int r = 0; r < S.num_roots; r++) {
+    const float* q = c->bvh.roots.data() + 7 * r;
+    S.root_lo[r] = make_float4(q[0], q[1], q[2], 0.f);
+    S.root_hi[r] = make_float4(q[3], q[4], q[5], q[6]);
+  }
 #undef CUC
   c->stats.create_ms = now_ms() - t_create0;
   *out = c;
@@ -747,7 +759,7 @@ static int trace_common(rt_ctx* c, const rt_ray* rays, int64_t n, rt_hit* hits, 
   if (e == cudaSuccess) e = cudaMemcpy(d_o.p, ho.data(), sizeof(float4) * (size_t)n, cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMemcpy(d_d.p, hd.data(), sizeof(float4) * (size_t)n, cudaMemcpyHostToDevice);
   if (e == cudaSuccess) {
-    const int depth = std::max(c->bvh.depth, 1);
+    const int depth = trace_stack_depth(c);
     const int persistent = c->num_sms * trace_ctas_per_sm(depth);
     int grid = (int)std::min<int64_t>((n + kBlock - 1) / kBlock, persistent);
     launch_trace_rays(c->scene, d_o.p, d_d.p, (unsigned)n, d_h.p, d_occ.p, occluded ? 1 : 0,

@@ -231,6 +231,15 @@ void build_bvh(int num_vertices, const float* P, int T, const int32_t* tri, int 
     items.push_back(it);
     node_base += n - 1;
   }
+  out.mesh_depth = sub_depth + 1;
+  out.roots.clear();
+  for (const Builder::Item& it : items) {  // before build_top reorders them
+    for (int a = 0; a < 3; a++) out.roots.push_back(it.box.lo[a] - B.pad);
+    for (int a = 0; a < 3; a++) out.roots.push_back(it.box.hi[a] + B.pad);
+    float ref_bits;
+    std::memcpy(&ref_bits, &it.ref, 4);
+    out.roots.push_back(ref_bits);
+  }
   B.max_depth = sub_depth;
   if (items.empty()) {
     B.write_child(B.nodes, 0, nullptr, -1);

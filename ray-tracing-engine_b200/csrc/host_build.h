@@ -34,6 +34,11 @@ struct Bvh {
   std::vector<int32_t> slot_tri;   // slot -> global triangle index
   int depth = 0;                   // longest root-to-leaf path in nodes (stack bound)
   float pad = 0.f;
+  // The per-mesh roots in mesh order, 7 floats each: padded lo[3], hi[3], ref (int bits).  The reference keeps
+  // one BVH per Mesh and loops over the meshes (source/RayTracer.h:56-85); a traversal may start from this list
+  // instead of the top-level tree (6 root-box tests in a row instead of 6 dependent node visits).
+  std::vector<float> roots;
+  int mesh_depth = 0;              // longest root-to-leaf path inside one mesh's tree
 };
 
 void build_bvh(int num_vertices, const float* positions, int num_triangles, const int32_t* triangles, int num_meshes,

@@ -68,6 +68,41 @@ RT_DI void trace_write(const TraceLane& L, float4* __restrict__ hits, unsigned c
   else
     hits[L.idx] = make_float4(L.h.t, L.h.u, L.h.v, __int_as_float(L.h.gid != 0x7fffffff ? L.h.gid : -1));
 }
+// A new ray enters the scene through the list of per-mesh roots (the reference loops over the meshes,
+// RayTracer.h:56-85): all root boxes are tested back to back, the nearest hit one becomes the cursor and the others
+// go on the stack with their entry distance.  ncu on the version that entered through the top-level tree showed
+// 12.1 node visits per shadow ray, about 6 of them in the top-level tree whose wall-sized boxes almost never cull.
+template <bool ANY>
+RT_DI void trace_start(const DScene& S, TraceLane& L, int* st_ref, int* st_tn) {
+  L.sp = 0;
+  if (S.num_roots == 0) {
+    L.cur = 0;
+    return;
+  }
+  L.cur = kDone;
+  float tcur = 0.f;
+  for (int r = 0; r < S.num_roots; r++) {
+    const float4 lo = S.root_lo[r], hi = S.root_hi[r];
+    float tn;
+    if (box_hit_fma(f3(lo), f3(hi), L.inv, L.oinv, FLT_MAX, tn)) {
+      const int ref = __float_as_int(hi.w);
+      if (L.cur == kDone) {
+        L.cur = ref;
+        tcur = tn;
+      } else {
+        const bool nearer = !ANY && tn < tcur;
+        st_ref[L.sp * kBlock] = nearer ? L.cur : ref;
+        if (!ANY) st_tn[L.sp * kBlock] = __float_as_int(nearer ? tcur : tn);
+        L.sp++;
+        if (nearer) {
+          L.cur = ref;
+          tcur = tn;
+        }
+      }
+    }
+  }
+}
+
 // internal node: test both children, descend into the nearer hit one, push the other
 template <bool ANY>
 RT_DI void trace_box_step(const DScene& S, TraceLane& L, int* st_ref, int* st_tn) {
@@ -159,8 +194,8 @@ RT_DI void trace_body(const DScene& S, const float4* __restrict__ ro, const floa
           L.h.t = FLT_MAX;
           L.h.u = L.h.v = 0.f;
           L.h.gid = 0x7fffffff;
-          L.sp = 0;
-          L.cur = 0;  // root
+          trace_start<ANY>(S, L, st_ref, st_tn);
+          if (L.cur == kDone) trace_write<ANY>(L, hits, occ);  // no mesh box hit: a miss
         }
       }
     }
@@ -256,8 +291,7 @@ RT_DI void trace_body_spec(const DScene& S, const float4* __restrict__ ro, const
           L.h.t = FLT_MAX;
           L.h.u = L.h.v = 0.f;
           L.h.gid = 0x7fffffff;
-          L.sp = 0;
-          L.cur = 0;
+          trace_start<ANY>(S, L, st_ref, st_tn);
           pend = 0;
           live = true;
         }
@@ -336,7 +370,7 @@ RT_DI void trace_body_spec(const DScene& S, const float4* __restrict__ ro, const
     extern __shared__ int s_dyn[];                                                                                  \
     trace_body_spec<ANY, BLOCKED, LEAFT>(S, ro, rd, n_ptr, n_fixed, hits, occ, fetch, depth, s_dyn);                \
   }
-RT_TRACE_KERNEL_SPEC(k_trace_sp8, 8)    // variant 5
+RT_TRACE_KERNEL_SPEC(k_trace_sp8, 8)    // variant 5 (default since the root-list entry: 29.6 ms/frame vs 30.2 for variant 1)
 RT_TRACE_KERNEL_SPEC(k_trace_sp12, 12)  // variant 6
 RT_TRACE_KERNEL_SPEC(k_trace_sp16, 16)  // variant 7
 RT_TRACE_KERNEL_SPEC(k_trace_sp24, 24)  // variant 8
@@ -351,7 +385,7 @@ RT_TRACE_KERNEL_SPEC(k_trace_sp24, 24)  // variant 8
   }
 // Measured on B200, cfg2 frame (profiles/r1_tuning.md): variant 0 37.4 ms, 1 33.6 ms, 2 34.1 ms,
 // 3 37.1 ms, 4 34.5 ms  ->  variant 1 is the default.
-RT_TRACE_KERNEL(k_trace_lb8, 8, 1)    // variant 1 (default): batch leaf tests, >= 8 lanes
+RT_TRACE_KERNEL(k_trace_lb8, 8, 1)    // variant 1: batch leaf tests, >= 8 lanes
 RT_TRACE_KERNEL(k_trace, 0, 1)        // variant 0: test leaves as they come
 RT_TRACE_KERNEL(k_trace_lb16, 16, 1)  // variant 2: >= 16 lanes
 RT_TRACE_KERNEL(k_trace_occ, 0, 12)   // variant 3: variant 0 capped to 40 registers (12 CTAs/SM)
@@ -361,7 +395,7 @@ static int g_trace_variant = -1;
 int trace_variant() {
   if (g_trace_variant < 0) {
     const char* e = getenv("RT_TRACE_VARIANT");
-    g_trace_variant = e ? atoi(e) : 1;
+    g_trace_variant = e ? atoi(e) : 5;
   }
   return g_trace_variant;
 }
@@ -396,11 +430,11 @@ int trace_ctas_per_sm(int stack_depth) {
     case 2: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_trace_lb16<false, false>, kBlock, sm); break;
     case 3: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_trace_occ<false, false>, kBlock, sm); break;
     case 4: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_trace_lb8occ<false, false>, kBlock, sm); break;
-    case 5: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_trace_sp8<false, false>, kBlock, sm); break;
     case 6: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_trace_sp12<false, false>, kBlock, sm); break;
     case 7: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_trace_sp16<false, false>, kBlock, sm); break;
     case 8: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_trace_sp24<false, false>, kBlock, sm); break;
-    default: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_trace_lb8<false, false>, kBlock, sm); break;
+    case 1: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_trace_lb8<false, false>, kBlock, sm); break;
+    default: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_trace_sp8<false, false>, kBlock, sm); break;
   }
   return n < 1 ? 1 : n;
 }
@@ -413,18 +447,24 @@ static void launch_trace_t(const DScene& S, const float4* ro, const float4* rd, 
     k_trace_brute<ANY, BLOCKED><<<grid, kBlock, 0, st>>>(S, ro, rd, n_ptr, n_fixed, hits, occ);
   } else {
     cudaMemsetAsync(fetch, 0, sizeof(unsigned), st);
-    const size_t sm = trace_smem_bytes(depth);
-#define RT_LAUNCH(K) K<ANY, BLOCKED><<<grid, kBlock, sm, st>>>(S, ro, rd, n_ptr, n_fixed, hits, occ, fetch, depth)
+    // any-hit keeps no tnear column: half the stack, and the rest of the SM's 256 KB stays L1 for the BVH
+    const size_t sm = ANY ? trace_smem_bytes(depth) / 2 : trace_smem_bytes(depth);
+    static const int carve = getenv("RT_CARVEOUT") ? atoi(getenv("RT_CARVEOUT")) : -1;
+#define RT_LAUNCH(K)                                                                                          \
+  do {                                                                                                        \
+    if (carve >= 0) cudaFuncSetAttribute(K<ANY, BLOCKED>, cudaFuncAttributePreferredSharedMemoryCarveout, carve); \
+    K<ANY, BLOCKED><<<grid, kBlock, sm, st>>>(S, ro, rd, n_ptr, n_fixed, hits, occ, fetch, depth);           \
+  } while (0)
     switch (trace_variant()) {
       case 0: RT_LAUNCH(k_trace); break;
       case 2: RT_LAUNCH(k_trace_lb16); break;
       case 3: RT_LAUNCH(k_trace_occ); break;
       case 4: RT_LAUNCH(k_trace_lb8occ); break;
-      case 5: RT_LAUNCH(k_trace_sp8); break;
       case 6: RT_LAUNCH(k_trace_sp12); break;
       case 7: RT_LAUNCH(k_trace_sp16); break;
       case 8: RT_LAUNCH(k_trace_sp24); break;
-      default: RT_LAUNCH(k_trace_lb8); break;
+      case 1: RT_LAUNCH(k_trace_lb8); break;
+      default: RT_LAUNCH(k_trace_sp8); break;
     }
 #undef RT_LAUNCH
   }

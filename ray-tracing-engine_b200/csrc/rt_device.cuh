@@ -173,6 +173,7 @@ struct DCamera {  // Camera.h:34-40
 };
 
 constexpr int kMaxLights = 8;
+constexpr int kMaxRoots = 16;    // scenes with more meshes than this enter through the top-level tree
 constexpr int kStackDepth = 40;  // BVH traversal stack entries per ray (host checks bvh depth <= this)
 constexpr int kBlock = 128;      // threads per CTA of the wavefront kernels
 constexpr int kMaxK = 64;
@@ -189,6 +190,9 @@ struct DScene {
   int num_lights;
   int num_tris;
   DCamera cam;
+  // per-mesh BVH roots (mesh order): lo.xyz, hi.xyz, hi.w = node/leaf reference; 0 roots = start at node 0
+  int num_roots;
+  float4 root_lo[kMaxRoots], root_hi[kMaxRoots];
   // photon map: kd-tree in the array order of kdtree::make_tree (kdtree.h:60-69), links implicit
   const float4* __restrict__ kd_pos;  // xyz = position, w = weight
   const float4* __restrict__ kd_dir;  // xyz = incomeDirection

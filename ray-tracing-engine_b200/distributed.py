@@ -30,6 +30,16 @@ def sample_range(num_rays: int, rank: int, world: int):
     return first, num_rays * (rank + 1) // world - first
 
 
+def sample_shard_kwargs(num_rays: int, rank: int, world: int) -> dict:
+    """Renderer keyword arguments for `rank`'s share of the sample indices.  rt_params treats
+    sample_count <= 0 as "all samples", so a rank whose share is empty (more ranks than samples) is
+    given the empty range that starts at num_rays."""
+    first, count = sample_range(num_rays, rank, world)
+    if count <= 0:
+        return dict(sample_first=num_rays, sample_count=0)
+    return dict(sample_first=first, sample_count=count)
+
+
 def gather_photons(local_photons: np.ndarray, per_light_counts: np.ndarray, device=None, group=None) -> np.ndarray:
     """All-gather the shards of the photon list and splice them into (light, path) order.
 
@@ -93,8 +103,7 @@ def render_distributed(scene, num_rays, mode, num_photons=0, k=5, *, background,
     if shard == "tile":
         kw.update(shard_rank=rank, shard_count=world)
     else:
-        first, count = sample_range(num_rays, rank, world)
-        kw.update(sample_first=first, sample_count=count)
+        kw.update(sample_shard_kwargs(num_rays, rank, world))
     r = Renderer(scene, num_rays, mode, None, num_photons, k, **kw)
     if num_photons > 0:
         build_photon_map_distributed(r, device=device, group=group)

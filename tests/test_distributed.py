@@ -94,3 +94,19 @@ def test_ranges_cover_everything():
         assert rs[0][0] == 0 and sum(c for _, c in rs) == total
         assert all(rs[i][0] + rs[i][1] == rs[i + 1][0] for i in range(world - 1))
         assert [D.sample_range(total, r, world) for r in range(world)] == rs
+
+
+def test_empty_sample_shards_render_nothing():
+    """More ranks than samples: rt_params reads sample_count <= 0 as "all samples", so an empty share must be
+    expressed as the empty range at num_rays (found by the 8-GPU run of scripts/dist_check.py with N = 2)."""
+    sys.path.insert(0, ROOT)
+    from ray_tracing_engine_b200 import distributed as D
+    for total, world in ((2, 8), (5, 8), (128, 8), (1, 2)):
+        covered = []
+        for r in range(world):
+            kw = D.sample_shard_kwargs(total, r, world)
+            if kw["sample_count"] == 0:
+                assert kw["sample_first"] == total, "an empty share must not collapse to 'all samples'"
+            else:
+                covered += list(range(kw["sample_first"], kw["sample_first"] + kw["sample_count"]))
+        assert covered == list(range(total))

@@ -352,3 +352,11 @@ def test_batching_does_not_change_the_result(rt):
     a = rt.Renderer(scene, 7, 1, seed=2, width=64, height=64).render_accumulate()
     b = rt.Renderer(scene, 7, 1, seed=2, width=64, height=64, samples_per_batch=2).render_accumulate()
     assert beq(a[0], b[0]) and (a[1] == b[1]).all()
+
+
+def test_empty_sample_range_renders_nothing(rt):
+    """sample_first == num_rays, sample_count == 0: the share of a rank that has no samples (distributed.py)."""
+    scene = rt.Scene.load(scene_path("stock"))
+    r = rt.Renderer(scene, 4, 1, seed=2, width=48, height=32, sample_first=4, sample_count=0)
+    s, c = r.render_accumulate()
+    assert not s.any() and not c.any() and r.stats()["rays"] == 0
