@@ -93,6 +93,7 @@ struct rt_ctx {
   DevBuf<unsigned char> d_occ;
   DevBuf<int> d_hit_path;
   DevBuf<unsigned int> d_perm, d_sort_hist;
+  DevBuf<float4> d_sorted;
   float3 bounds_lo{0, 0, 0}, bounds_hi{0, 0, 0};
   int sort_hits = 1;  // RT_SORT_HITS=0 disables the spatial binning of bounce segments
   DevBuf<int> d_acc_cnt, d_out_cnt;
@@ -163,7 +164,7 @@ int trace_stack_depth(const rt_ctx* c) {
 }
 
 // bytes of wavefront state per path slot (ensure_work below)
-constexpr size_t kBytesPerPath = 16 * 2 + 32 * 2 + 16 + 3 * (32 + 16 + 1) + 4 + 4;
+constexpr size_t kBytesPerPath = 16 * 2 + 32 * 2 + 16 + 3 * (32 + 16 + 1) + 4 + 32;
 
 int ensure_work(rt_ctx* c, size_t paths, bool path_mode) {
   const size_t shadow = shadow_slots_for((unsigned)paths);
@@ -182,7 +183,8 @@ int ensure_work(rt_ctx* c, size_t paths, bool path_mode) {
     CU(c->d_qd1.ensure(paths));
   }
   if (path_mode || c->params.num_photons > 0) {
-    CU(c->d_perm.ensure(paths));
+    CU(c->d_perm.ensure(1));
+    CU(c->d_sorted.ensure(2 * paths));
     CU(c->d_sort_hist.ensure(kSortBuckets + 2));
   }
   CU(c->d_qcount.ensure(kQNum));
@@ -237,6 +239,7 @@ void fill_args(rt_ctx* c, RenderArgs& a, const int* pix_map, int npix, bool use_
   a.hit_path = c->d_hit_path.p;
   a.perm = (c->sort_hits && (p.mode == 1 || use_photons)) ? c->d_perm.p : nullptr;
   a.sort_hist = c->d_sort_hist.p;
+  a.sorted = c->d_sorted.p;
   a.sort_lo = c->bounds_lo;
   a.sort_inv_cell = make_float3(kSortGrid / std::max(c->bounds_hi.x - c->bounds_lo.x, 1e-20f),
                                 kSortGrid / std::max(c->bounds_hi.y - c->bounds_lo.y, 1e-20f),
@@ -450,6 +453,7 @@ int rt_destroy(rt_ctx* c) {
   c->d_occ.release();
   c->d_hit_path.release();
   c->d_perm.release();
+  c->d_sorted.release();
   c->d_sort_hist.release();
   c->d_qd0.release();
   c->d_qd1.release();

@@ -606,7 +606,16 @@ __global__ void __launch_bounds__(kSortThreads) k_sort_scatter(const RenderArgs 
   for (int b = threadIdx.x; b < kSortCells; b += kSortThreads)  // reserve this CTA's range in every bucket
     if (s_cnt[b]) s_cnt[b] = atomicAdd(A.sort_hist + b, s_cnt[b]);
   __syncthreads();
-  for (unsigned i = i0 + threadIdx.x; i < i1; i += kSortThreads) A.perm[atomicAdd(s_cnt + sort_key(A, seg, i), 1u)] = i;
+  // The payload k_shade needs (hit record, ray direction, path id) moves to its sorted slot here, where it has
+  // just been read in queue order for the key: random 16-byte WRITES that nobody waits for, instead of random
+  // reads in k_shade (ncu, profiles/r1c_cfg2_frame_full.csv: 7.3 GB of DRAM reads and 47 % issue activity in the
+  // gathering k_shade of a bounce segment against 1.1 GB / 68 % on the pixel-ordered segment 0).
+  for (unsigned i = i0 + threadIdx.x; i < i1; i += kSortThreads) {
+    const unsigned dst = atomicAdd(s_cnt + sort_key(A, seg, i), 1u);
+    const float4 o = A.ray_o[seg & 1][i], d = A.ray_d[seg & 1][i];
+    A.sorted[2 * (size_t)dst] = A.hit[i];  // one full 32-byte sector per ray
+    A.sorted[2 * (size_t)dst + 1] = make_float4(d.x, d.y, d.z, o.w);
+  }
 }
 void launch_sort_hits(const RenderArgs& a, int seg, cudaStream_t st) {
   static bool configured = false;
@@ -672,16 +681,22 @@ __global__ void __launch_bounds__(kBlock, PHOTON ? 6 : 8) k_shade(const RenderAr
   const bool permuted = (seg > 0 || PHOTON) && A.perm != nullptr;
   for (unsigned base = blockIdx.x * kBlock; base < n; base += gridDim.x * kBlock) {
     const unsigned slot = base + threadIdx.x;
-    const unsigned i = (permuted && slot < n) ? A.perm[slot] : slot;
     bool found = false;
     unsigned p = 0;
-    float3 o = f3(0, 0, 0), d = f3(0, 0, 0);
+    float3 d = f3(0, 0, 0);
     HitRec h;
     if (slot < n) {
-      const float4 a = qo_in[i], b = qd_in[i], hr = A.hit[i];
-      o = f3(a);
+      float4 b, hr;
+      if (permuted) {  // sorted payload written by k_sort_scatter: direction + path id, hit record
+        hr = A.sorted[2 * (size_t)slot];
+        b = A.sorted[2 * (size_t)slot + 1];
+        p = (unsigned)__float_as_int(b.w);
+      } else {
+        b = qd_in[slot];
+        hr = A.hit[slot];
+        p = (unsigned)__float_as_int(qo_in[slot].w);
+      }
       d = f3(b);
-      p = (unsigned)__float_as_int(a.w);
       h.t = hr.x;
       h.u = hr.y;
       h.v = hr.z;
