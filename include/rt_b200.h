@@ -149,6 +149,14 @@ int rt_set_params(rt_ctx* ctx, const rt_params* params); /* new size / N / mode 
  * rest are returned unchanged. */
 int rt_render(rt_ctx* ctx, float* rgb_inout);
 
+/* rt_render with the reference's progressive preview (source/Renderer.cpp:262-269: after pass i the image
+ * `updateImage/(i+1) + background*(i+1-counter)/(i+1)` is written to update.ppm).  `fn` is called after every
+ * `every` sample passes (and after the last one) with that composite over the whole frame; the snapshot buffer
+ * belongs to the library and is valid only during the call.  The samples are accumulated in index order whatever
+ * `every` is, so the final image is bit-identical to rt_render's.  every <= 0 or fn == NULL: plain rt_render. */
+typedef void (*rt_progress_fn)(void* user, int32_t samples_done, int32_t num_rays, const float* rgb_snapshot);
+int rt_render_progressive(rt_ctx* ctx, float* rgb_inout, int32_t every, rt_progress_fn fn, void* user);
+
 /* The same work without the composite: per-pixel sums of the clamped sample colours
  * (`updateImage`, source/Renderer.cpp:254-258) and hit counters (`counter`, :255-257), W*H*3 floats
  * and W*H int32, row-major.  Pixels owned by other shards are written as zero so that a sum-reduce

@@ -272,12 +272,24 @@ class Renderer:
     height = property(lambda s: s.params.height)
 
     # ---- the path: Renderer::render --------------------------------------------------------------
-    def render(self, image: Image) -> Image:
-        """source/Renderer.cpp:203-272: image holds the background on entry, the render on exit."""
+    def render(self, image: Image, every: int = 0, on_update=None) -> Image:
+        """source/Renderer.cpp:203-272: image holds the background on entry, the render on exit.
+
+        on_update(samples_done, num_rays, pixels[H,W,3]) is the reference's per-pass `update.ppm`
+        (Renderer.cpp:262-269), called every `every` sample passes and after the last one."""
         if image.width != self.width or image.height != self.height:
             raise ValueError("image size differs from the renderer's")
         buf = np.ascontiguousarray(image.pixels, np.float32)
-        _capi.check(self.lib.rt_render(self._ctx, _capi.ptr(buf)))
+        if on_update is not None and every > 0:
+            H, W = self.height, self.width
+
+            def trampoline(_user, done, total, ptr):
+                on_update(int(done), int(total), np.ctypeslib.as_array(ptr, shape=(H, W, 3)).copy())
+
+            cb = _capi.PROGRESS_FN(trampoline)
+            _capi.check(self.lib.rt_render_progressive(self._ctx, _capi.ptr(buf), int(every), cb, None))
+        else:
+            _capi.check(self.lib.rt_render(self._ctx, _capi.ptr(buf)))
         image.pixels = buf
         return image
 

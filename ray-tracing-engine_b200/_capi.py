@@ -65,6 +65,8 @@ class rt_stats(C.Structure):
                 ("bvh_build_ms", C.c_double), ("kd_build_ms", C.c_double), ("kd_visits", C.c_uint64)]
 
 
+PROGRESS_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_float))
+
 # every symbol include/rt_b200.h declares: name -> (restype, argtypes)
 _vp, _i32, _i64 = C.c_void_p, C.c_int32, C.c_int64
 SYMBOLS = {
@@ -74,6 +76,7 @@ SYMBOLS = {
     "rt_destroy": (C.c_int, [_vp]),
     "rt_set_params": (C.c_int, [_vp, C.POINTER(rt_params)]),
     "rt_render": (C.c_int, [_vp, _vp]),
+    "rt_render_progressive": (C.c_int, [_vp, _vp, _i32, _vp, _vp]),
     "rt_render_accumulate": (C.c_int, [_vp, _vp, _vp]),
     "rt_render_accumulate_device": (C.c_int, [_vp, _vp, _vp]),
     "rt_composite": (C.c_int, [_i32, _i32, _i32, _vp, _vp, _vp]),

@@ -344,7 +344,13 @@ int prepare_photons(rt_ctx* c) {
 
 // the whole render: batches of samples -> ordered accumulation -> scatter into full-frame buffers
 // composite_dev != null: instead of the raw sums/counters, composite over the background it holds (rt_render)
-int render_to_device(rt_ctx* c, float* out_rgb_dev, int* out_cnt_dev, float* composite_dev = nullptr) {
+struct Progress {
+  int every = 0;
+  rt_progress_fn fn = nullptr;
+  void* user = nullptr;
+};
+int render_to_device(rt_ctx* c, float* out_rgb_dev, int* out_cnt_dev, float* composite_dev = nullptr,
+                     const Progress* progress = nullptr) {
   int rc = bind(c);
   if (rc) return rc;
   if ((rc = prepare_photons(c))) return rc;
@@ -366,7 +372,14 @@ int render_to_device(rt_ctx* c, float* out_rgb_dev, int* out_cnt_dev, float* com
   }
   const int samp_first = p.sample_first;
   const int samp_end = p.sample_count > 0 ? p.sample_first + p.sample_count : p.num_rays;
+  const bool preview = progress && progress->fn && progress->every > 0 && composite_dev;
+  if (preview) spb = std::min(spb, progress->every);  // a snapshot needs a batch boundary
   spb = std::max(1, std::min(spb, std::max(samp_end - samp_first, 1)));
+  std::vector<float> snapshot;
+  if (preview) {
+    snapshot.resize(3 * npx);
+    CU(c->d_scratch.ensure(sizeof(float) * 3 * npx));
+  }
   if ((rc = ensure_work(c, (size_t)c->npix * spb, path_mode))) return rc;
   CU(c->d_acc.ensure(c->npix));
   CU(c->d_acc_cnt.ensure(c->npix));
@@ -382,11 +395,23 @@ int render_to_device(rt_ctx* c, float* out_rgb_dev, int* out_cnt_dev, float* com
       if ((rc = run_batch(c, a, s0, ns))) return rc;
       launch_resolve(c->d_col0.p, c->npix, ns, c->d_acc.p, c->d_acc_cnt.p, c->stream);
       c->stats.kernel_launches++;
+      const int done = s0 + ns - samp_first;
+      if (preview && s0 + ns < samp_end && done / progress->every != (done - ns) / progress->every) {
+        // Renderer.cpp:262-269 after pass i = done-1: the composite of the first `done` samples
+        float* snap_dev = reinterpret_cast<float*>(c->d_scratch.p);
+        CU(cudaMemcpyAsync(snap_dev, composite_dev, sizeof(float) * 3 * npx, cudaMemcpyDeviceToDevice, c->stream));
+        launch_composite(c->d_acc.p, c->d_acc_cnt.p, c->d_pix_map.p, c->npix, done, composite_dev, snap_dev, c->stream);
+        c->stats.kernel_launches++;
+        CU(cudaMemcpyAsync(snapshot.data(), snap_dev, sizeof(float) * 3 * npx, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        progress->fn(progress->user, done, samp_end - samp_first, snapshot.data());
+      }
     }
   }
   if (composite_dev) {
     if (c->npix > 0) {
-      launch_composite(c->d_acc.p, c->d_acc_cnt.p, c->d_pix_map.p, c->npix, p.num_rays, composite_dev, c->stream);
+      launch_composite(c->d_acc.p, c->d_acc_cnt.p, c->d_pix_map.p, c->npix, p.num_rays, composite_dev, composite_dev,
+                       c->stream);
       c->stats.kernel_launches++;
     }
   } else {
@@ -684,7 +709,9 @@ int rt_composite(int32_t width, int32_t height, int32_t num_rays, const float* s
   return RT_OK;
 }
 
-int rt_render(rt_ctx* c, float* rgb_inout) {
+int rt_render(rt_ctx* c, float* rgb_inout) { return rt_render_progressive(c, rgb_inout, 0, nullptr, nullptr); }
+
+int rt_render_progressive(rt_ctx* c, float* rgb_inout, int32_t every, rt_progress_fn fn, void* user) {
   if (!c || !rgb_inout) return fail(RT_ERR_INVALID, "null argument");
   const rt_params& p = c->params;
   const size_t npx = (size_t)p.width * p.height;
@@ -694,8 +721,10 @@ int rt_render(rt_ctx* c, float* rgb_inout) {
   // background up, the whole Renderer::render on the device (composite included), frame down
   CU(c->d_out_rgb.ensure(3 * npx));
   CU(cudaMemcpyAsync(c->d_out_rgb.p, rgb_inout, sizeof(float) * 3 * npx, cudaMemcpyHostToDevice, c->stream));
-  if ((rc = render_to_device(c, nullptr, nullptr, c->d_out_rgb.p))) return rc;
+  Progress progress{every, fn, user};
+  if ((rc = render_to_device(c, nullptr, nullptr, c->d_out_rgb.p, &progress))) return rc;
   CU(cudaMemcpy(rgb_inout, c->d_out_rgb.p, sizeof(float) * 3 * npx, cudaMemcpyDeviceToHost));
+  if (fn && every > 0) fn(user, p.num_rays, p.num_rays, rgb_inout);  // the last pass: update.ppm == the result
   return RT_OK;
 }
 

@@ -869,7 +869,8 @@ void launch_scatter(const float4* acc_rgb, const int* acc_cnt, const int* pix_ma
 // Renderer.cpp:262-265 after the last pass (i + 1 == N), on the pixels this shard owns:
 //   saveImage = updateImage / float(N) + image * (N - counter) / float(N)
 __global__ void k_composite(const float4* __restrict__ acc_rgb, const int* __restrict__ acc_cnt,
-                            const int* __restrict__ pix_map, int npix, int num_rays, float* rgb_inout) {
+                            const int* __restrict__ pix_map, int npix, int num_rays, const float* background,
+                            float* out) {
   int pl = blockIdx.x * blockDim.x + threadIdx.x;
   if (pl >= npix) return;
   const size_t pixel = (size_t)pix_map[pl];
@@ -878,13 +879,14 @@ __global__ void k_composite(const float4* __restrict__ acc_rgb, const int* __res
   const float s[3] = {a.x, a.y, a.z};
 #pragma unroll
   for (int ch = 0; ch < 3; ch++) {
-    const float bg = rgb_inout[3 * pixel + ch];
-    rgb_inout[3 * pixel + ch] = __fadd_rn(__fdiv_rn(s[ch], fn), __fdiv_rn(__fmul_rn(bg, miss), fn));
+    const float bg = background[3 * pixel + ch];
+    out[3 * pixel + ch] = __fadd_rn(__fdiv_rn(s[ch], fn), __fdiv_rn(__fmul_rn(bg, miss), fn));
   }
 }
+// background and out may be the same buffer (rt_render composites in place)
 void launch_composite(const float4* acc_rgb, const int* acc_cnt, const int* pix_map, int npix, int num_rays,
-                      float* rgb_inout, cudaStream_t st) {
-  k_composite<<<(npix + 255) / 256, 256, 0, st>>>(acc_rgb, acc_cnt, pix_map, npix, num_rays, rgb_inout);
+                      const float* background, float* out, cudaStream_t st) {
+  k_composite<<<(npix + 255) / 256, 256, 0, st>>>(acc_rgb, acc_cnt, pix_map, npix, num_rays, background, out);
 }
 
 // ----------------------------------------------------------------------------------------------

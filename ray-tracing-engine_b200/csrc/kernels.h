@@ -79,7 +79,7 @@ void launch_scatter(const float4* acc_rgb, const int* acc_cnt, const int* pix_ma
                     int* out_cnt, cudaStream_t st);
 // the final composite over the background on the device (rt_render): rgb_inout holds the background on entry
 void launch_composite(const float4* acc_rgb, const int* acc_cnt, const int* pix_map, int npix, int num_rays,
-                      float* rgb_inout, cudaStream_t st);
+                      const float* background, float* out, cudaStream_t st);
 // parity hooks: caller-supplied rays through the SAME persistent trace kernels the renderer uses
 void launch_trace_rays(const DScene& s, const float4* ro, const float4* rd, unsigned n, float4* hits,
                        unsigned char* occluded, int any, int brute, int stack_depth, unsigned* fetch_counter,

@@ -1,6 +1,7 @@
 // command_line.h -- the reference's command line (source/CommandLine.h:9-102): same flags, defaults,
 // banner and error texts.  Additive options (absent = stock behaviour): -i/-input <file.off> replaces
-// ../meshes/cube_tri.off, -meshdir <dir>, -subdiv <n>, -seed <n>, -device <n>, -brute.
+// ../meshes/cube_tri.off, -meshdir <dir>, -subdiv <n>, -seed <n>, -device <n>, -brute, -update <n> (rewrite
+// update.ppm every n sample passes as the reference does after every pass, Renderer.cpp:268-269; 0 = at the end).
 #pragma once
 #include <cstdlib>
 #include <iostream>
@@ -12,7 +13,7 @@ struct CommandLine {
   std::string outputFilename = "output.ppm";
   // additive
   std::string input, meshDir = "../meshes";
-  int subdiv = 0, device = 0;
+  int subdiv = 0, device = 0, update = 0;
   unsigned long long seed = 1;
   bool brute = false;
 
@@ -24,7 +25,7 @@ struct CommandLine {
                  "tracing)>][-p/-numPhotons <number of photons for a photon map. If "
                  "defined, photon map-based rendering is used.>][-k <number of "
                  "neighbours in photon mapping. Use only with -p/-numPhotons>]"
-                 "[-i/-input <mesh.off>][-meshdir <dir>][-subdiv <n>][-seed <n>][-device <n>][-brute 1]"
+                 "[-i/-input <mesh.off>][-meshdir <dir>][-subdiv <n>][-seed <n>][-device <n>][-brute 1][-update <n>]"
               << std::endl;
   }
 
@@ -51,6 +52,7 @@ struct CommandLine {
       else if (a == "-seed") seed = std::strtoull(argv[++i], nullptr, 10);
       else if (a == "-device") device = std::atoi(argv[++i]);
       else if (a == "-brute") brute = std::atoi(argv[++i]) != 0;
+      else if (a == "-update") update = std::atoi(argv[++i]);
       else throw std::runtime_error("Unknown argument <" + a + ">");
     }
     // CommandLine.h:78-96

@@ -87,12 +87,22 @@ int main(int argc, char** argv) {
   }
 
   printProgressBar(0.f);
-  if ((rc = rt_render(ctx, image.data()))) die(rc);  // Main.cpp:224
+  // Renderer.cpp:262-269 rewrites update.ppm (and the bar) after every sample pass; -update n does it every n
+  // passes from a device-side composite of the samples so far, 0 only once at the end (same final file).
+  struct Preview {
+    int w, h;
+  } preview{(int)args.width, (int)args.height};
+  auto on_update = [](void* user, int32_t done, int32_t total, const float* rgb) {
+    const Preview* pv = static_cast<const Preview*>(user);
+    std::vector<float> snap(rgb, rgb + 3 * (size_t)pv->w * pv->h);
+    rth::save_ppm("update.ppm", pv->w, pv->h, snap);
+    printProgressBar(total > 0 ? (float)done / (float)total : 1.f);
+  };
+  if ((rc = rt_render_progressive(ctx, image.data(), args.update > 0 ? args.update : (int)args.numRays + 1, on_update,
+                                  &preview)))
+    die(rc);  // Main.cpp:224
   printProgressBar(1.f);
   std::cout << std::endl;
-
-  // Renderer.cpp:268-269 rewrites update.ppm after every sample pass; the final pass equals the result
-  rth::save_ppm("update.ppm", (int)args.width, (int)args.height, image);
   rth::save_ppm(args.outputFilename, (int)args.width, (int)args.height, image);  // Main.cpp:227
 
   rt_stats st{};

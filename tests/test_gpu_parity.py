@@ -360,3 +360,26 @@ def test_empty_sample_range_renders_nothing(rt):
     r = rt.Renderer(scene, 4, 1, seed=2, width=48, height=32, sample_first=4, sample_count=0)
     s, c = r.render_accumulate()
     assert not s.any() and not c.any() and r.stats()["rays"] == 0
+
+
+def test_progressive_updates_match_the_per_pass_composite(rt):
+    """rt_render_progressive: the snapshot after `done` passes is Renderer.cpp:262-265 evaluated with i+1 = done
+    (sums of the first `done` samples / done + background * (done - counter) / done), and the final image is
+    bit-identical to the plain rt_render."""
+    scene = rt.Scene.load(scene_path("stock"))
+    W, H, N = 64, 48, 5
+    bg = rt.Image(W, H).fillBackground()
+    for mode in (0, 1):
+        r = rt.Renderer(scene, N, mode, seed=4, width=W, height=H)
+        want = r.render(rt.Image(W, H).fillBackground()).pixels
+        snaps = []
+        got = r.render(rt.Image(W, H).fillBackground(), every=2, on_update=lambda d, t, px: snaps.append((d, t, px))).pixels
+        assert beq(got, want)
+        assert [d for d, _, _ in snaps] == [2, 4, 5] and all(t == N for _, t, _ in snaps)
+        assert beq(snaps[-1][2], want)
+        for done, _, px in snaps[:-1]:
+            part = rt.Renderer(scene, N, mode, seed=4, width=W, height=H, sample_first=0, sample_count=done)
+            s, c = part.render_accumulate()
+            assert beq(px, rt.Renderer.composite(done, s, c, bg.pixels)), f"snapshot after {done} passes"
+            part.close()
+        r.close()
