@@ -205,6 +205,8 @@ int rt_get_stats(rt_ctx* ctx, rt_stats* out);
 int rt_reset_stats(rt_ctx* ctx);
 /* flattened BVH for inspection/tests: nodes*16 floats; returns counts through out params */
 int rt_get_bvh(rt_ctx* ctx, float* nodes16, int64_t capacity_nodes, int32_t* num_nodes, int32_t* depth);
+/* leaf slot -> global triangle index of the context's BVH (num_triangles ints) */
+int rt_get_bvh_slots(rt_ctx* ctx, int32_t* slot_triangle, int64_t capacity);
 /* The host-side BVH builder alone (pure host function, needs no device): the split policy of
  * BVH::from_triangles (source/BVH.h:100-161) per mesh plus the top-level join, exactly what rt_create uploads.
  * nodes16: capacity_nodes*16 floats (layout in csrc/host_build.h); slot_triangle: num_triangles ints

@@ -422,6 +422,12 @@ class Renderer:
     def reset_stats(self):
         _capi.check(self.lib.rt_reset_stats(self._ctx))
 
+    def bvh_slots(self):
+        """leaf slot -> global triangle index of this context's BVH"""
+        out = np.zeros(self.scene.T, np.int32)
+        _capi.check(self.lib.rt_get_bvh_slots(self._ctx, _capi.ptr(out), len(out)))
+        return out
+
     def bvh(self):
         n, d = C.c_int32(), C.c_int32()
         _capi.check(self.lib.rt_get_bvh(self._ctx, None, 0, C.byref(n), C.byref(d)))

@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "../../include/rt_b200.h"
+#include "bvh_build.h"
 #include "host_build.h"
 #include "kernels.h"
 
@@ -77,6 +78,7 @@ struct rt_ctx {
   DevBuf<DMaterial> d_mats;
   DScene scene{};
   Bvh bvh;
+  bool bvh_on_device = false;  // built by csrc/bvh_build.cu: bvh.nodes holds only the top-level join on the host
   // photon map
   std::vector<float> kd_nodes7;
   DevBuf<float4> d_kd_pos, d_kd_dir;
@@ -580,18 +582,9 @@ int rt_create(const rt_scene* s, const rt_params* p, int device, rt_ctx** out) {
     return fail(RT_ERR_INVALID, "scene coordinates must be finite and smaller than 1e8");
   }
   float pad_fraction = p->bvh_pad > 0.f ? p->bvh_pad : 1.0f / 16384.0f;
-  const double t_bvh0 = now_ms();
-  build_bvh(c->V, s->positions, c->T, s->triangles, c->M, s->mesh_first_triangle, extent, pad_fraction, c->bvh);
-  c->stats.bvh_build_ms = now_ms() - t_bvh0;
-  if (std::max(c->bvh.depth, c->bvh.mesh_depth + kMaxRoots) > kStackDepth) {
-    rt_destroy(c);
-    return fail(RT_ERR_INVALID, "BVH deeper than the traversal stack");
-  }
-  c->stats.bvh_nodes = (int)(c->bvh.nodes.size() / 16);
-  c->stats.bvh_depth = c->bvh.depth;
 
-  // ---- upload ----
-  std::vector<float4> h_pos(std::max(c->V, 1)), h_nrm(std::max(c->V, 1)), h_tris(3 * (size_t)std::max(c->T, 1));
+  // ---- shading data up first: the device BVH builder reads positions and triangle indices from HBM ----
+  std::vector<float4> h_pos(std::max(c->V, 1)), h_nrm(std::max(c->V, 1));
   std::vector<int4> h_vidx(std::max(c->T, 1));
   for (int v = 0; v < c->V; v++) {
     h_pos[v] = make_float4(s->positions[3 * v], s->positions[3 * v + 1], s->positions[3 * v + 2], 0.f);
@@ -604,38 +597,73 @@ int rt_create(const rt_scene* s, const rt_params* p, int device, rt_ctx** out) {
       h_vidx[t] = make_int4(s->triangles[3 * t], s->triangles[3 * t + 1], s->triangles[3 * t + 2], m);
     }
   }
-  for (int slot = 0; slot < c->T; slot++) {
-    int gid = c->bvh.slot_tri[slot];
-    const float* p0 = s->positions + 3 * (size_t)s->triangles[3 * gid];
-    const float* p1 = s->positions + 3 * (size_t)s->triangles[3 * gid + 1];
-    const float* p2 = s->positions + 3 * (size_t)s->triangles[3 * gid + 2];
-    // Ray.cpp:11: edge1 = p1 - p0, edge2 = p2 - p0 (binary32 subtractions, done once here)
-    volatile float e1x = p1[0] - p0[0], e1y = p1[1] - p0[1], e1z = p1[2] - p0[2];
-    volatile float e2x = p2[0] - p0[0], e2y = p2[1] - p0[1], e2z = p2[2] - p0[2];
-    int gid_bits = gid;
-    float gid_f;
-    std::memcpy(&gid_f, &gid_bits, 4);
-    h_tris[3 * (size_t)slot] = make_float4(p0[0], p0[1], p0[2], gid_f);
-    h_tris[3 * (size_t)slot + 1] = make_float4(e1x, e1y, e1z, 0.f);
-    h_tris[3 * (size_t)slot + 2] = make_float4(e2x, e2y, e2z, 0.f);
-  }
   std::vector<DMaterial> h_mats(std::max(c->M, 1));
   for (int m = 0; m < c->M; m++) {
     const rt_material& a = s->materials[m];
     h_mats[m] = make_material(a.kd, a.alpha, h3(a.albedo), h3(a.f0));
   }
-  CUC(c->d_nodes.ensure(c->bvh.nodes.size() / 4));
-  CUC(c->d_tris.ensure(h_tris.size()));
   CUC(c->d_pos.ensure(h_pos.size()));
   CUC(c->d_nrm.ensure(h_nrm.size()));
   CUC(c->d_tri_vidx.ensure(h_vidx.size()));
   CUC(c->d_mats.ensure(h_mats.size()));
-  CUC(cudaMemcpy(c->d_nodes.p, c->bvh.nodes.data(), c->bvh.nodes.size() * sizeof(float), cudaMemcpyHostToDevice));
-  CUC(cudaMemcpy(c->d_tris.p, h_tris.data(), h_tris.size() * sizeof(float4), cudaMemcpyHostToDevice));
   CUC(cudaMemcpy(c->d_pos.p, h_pos.data(), h_pos.size() * sizeof(float4), cudaMemcpyHostToDevice));
   CUC(cudaMemcpy(c->d_nrm.p, h_nrm.data(), h_nrm.size() * sizeof(float4), cudaMemcpyHostToDevice));
   CUC(cudaMemcpy(c->d_tri_vidx.p, h_vidx.data(), h_vidx.size() * sizeof(int4), cudaMemcpyHostToDevice));
   CUC(cudaMemcpy(c->d_mats.p, h_mats.data(), h_mats.size() * sizeof(DMaterial), cudaMemcpyHostToDevice));
+
+  // ---- BVH (reference split policy): on the device for large scenes, on the host otherwise ----
+  const double t_bvh0 = now_ms();
+  {
+    const char* e = getenv("RT_BVH_BUILD");  // "gpu" | "host"; default: gpu from 8192 triangles
+    const bool want_gpu = e ? std::string(e) == "gpu" : c->T >= 8192;
+    if (want_gpu && c->T >= 2) {
+      int nonempty = 0;
+      for (int m = 0; m < c->M; m++) nonempty += s->mesh_first_triangle[m + 1] > s->mesh_first_triangle[m] ? 1 : 0;
+      const size_t num_nodes = (size_t)(c->T - nonempty) + (size_t)std::max(nonempty - 1, 0);
+      CUC(c->d_nodes.ensure(4 * std::max<size_t>(num_nodes, 1)));
+      CUC(c->d_tris.ensure(3 * (size_t)c->T));
+      std::string err;
+      long long launches = 0;
+      if (build_bvh_device(c->d_pos.p, c->d_tri_vidx.p, c->T, c->M, s->mesh_first_triangle, extent * pad_fraction,
+                           c->d_nodes.p, c->d_tris.p, c->stream, c->bvh, &launches, err)) {
+        c->bvh_on_device = true;
+        c->stats.kernel_launches += (uint64_t)launches;
+      } else if (e) {  // explicitly requested: report instead of silently building on the host
+        rt_destroy(c);
+        return fail(RT_ERR_CUDA, "device BVH build failed: " + err);
+      }
+    }
+  }
+  if (!c->bvh_on_device) {
+    build_bvh(c->V, s->positions, c->T, s->triangles, c->M, s->mesh_first_triangle, extent, pad_fraction, c->bvh);
+    std::vector<float4> h_tris(3 * (size_t)std::max(c->T, 1));
+    for (int slot = 0; slot < c->T; slot++) {
+      int gid = c->bvh.slot_tri[slot];
+      const float* p0 = s->positions + 3 * (size_t)s->triangles[3 * gid];
+      const float* p1 = s->positions + 3 * (size_t)s->triangles[3 * gid + 1];
+      const float* p2 = s->positions + 3 * (size_t)s->triangles[3 * gid + 2];
+      // Ray.cpp:11: edge1 = p1 - p0, edge2 = p2 - p0 (binary32 subtractions, done once here)
+      volatile float e1x = p1[0] - p0[0], e1y = p1[1] - p0[1], e1z = p1[2] - p0[2];
+      volatile float e2x = p2[0] - p0[0], e2y = p2[1] - p0[1], e2z = p2[2] - p0[2];
+      int gid_bits = gid;
+      float gid_f;
+      std::memcpy(&gid_f, &gid_bits, 4);
+      h_tris[3 * (size_t)slot] = make_float4(p0[0], p0[1], p0[2], gid_f);
+      h_tris[3 * (size_t)slot + 1] = make_float4(e1x, e1y, e1z, 0.f);
+      h_tris[3 * (size_t)slot + 2] = make_float4(e2x, e2y, e2z, 0.f);
+    }
+    CUC(c->d_nodes.ensure(c->bvh.nodes.size() / 4));
+    CUC(c->d_tris.ensure(h_tris.size()));
+    CUC(cudaMemcpy(c->d_nodes.p, c->bvh.nodes.data(), c->bvh.nodes.size() * sizeof(float), cudaMemcpyHostToDevice));
+    CUC(cudaMemcpy(c->d_tris.p, h_tris.data(), h_tris.size() * sizeof(float4), cudaMemcpyHostToDevice));
+  }
+  c->stats.bvh_build_ms = now_ms() - t_bvh0;
+  if (std::max(c->bvh.depth, c->bvh.mesh_depth + kMaxRoots) > kStackDepth) {
+    rt_destroy(c);
+    return fail(RT_ERR_INVALID, "BVH deeper than the traversal stack");
+  }
+  c->stats.bvh_nodes = (int)c->bvh.num_nodes;
+  c->stats.bvh_depth = c->bvh.depth;
   CUC(c->d_counters.ensure(kCntNum));
   CUC(cudaMemset(c->d_counters.p, 0, sizeof(unsigned long long) * kCntNum));
   CUC(c->d_kd_pos.ensure(1));
@@ -1063,14 +1091,26 @@ int rt_build_bvh_host(const rt_scene* s, float pad_fraction, float* nodes16, int
   if (slot_triangle) std::memcpy(slot_triangle, bvh.slot_tri.data(), bvh.slot_tri.size() * sizeof(int32_t));
   return RT_OK;
 }
+int rt_get_bvh_slots(rt_ctx* c, int32_t* slot_triangle, int64_t capacity) {
+  if (!c || !slot_triangle) return fail(RT_ERR_INVALID, "null argument");
+  if (capacity < (int64_t)c->bvh.slot_tri.size()) return fail(RT_ERR_INVALID, "capacity too small");
+  std::memcpy(slot_triangle, c->bvh.slot_tri.data(), c->bvh.slot_tri.size() * sizeof(int32_t));
+  return RT_OK;
+}
 int rt_get_bvh(rt_ctx* c, float* nodes16, int64_t capacity_nodes, int32_t* num_nodes, int32_t* depth) {
   if (!c) return fail(RT_ERR_INVALID, "null context");
-  int n = (int)(c->bvh.nodes.size() / 16);
+  int n = (int)c->bvh.num_nodes;
   if (num_nodes) *num_nodes = n;
   if (depth) *depth = c->bvh.depth;
   if (nodes16) {
     if (capacity_nodes < n) return fail(RT_ERR_INVALID, "capacity too small");
-    std::memcpy(nodes16, c->bvh.nodes.data(), c->bvh.nodes.size() * sizeof(float));
+    if (c->bvh_on_device) {
+      int rc = bind(c);
+      if (rc) return rc;
+      CU(cudaMemcpy(nodes16, c->d_nodes.p, c->bvh.num_nodes * 16 * sizeof(float), cudaMemcpyDeviceToHost));
+    } else {
+      std::memcpy(nodes16, c->bvh.nodes.data(), c->bvh.nodes.size() * sizeof(float));
+    }
   }
   return RT_OK;
 }

@@ -183,6 +183,7 @@ void build_bvh(int num_vertices, const float* P, int T, const int32_t* tri, int 
   size_t num_nodes = (size_t)std::max(T - nonempty, 0) + (size_t)std::max(nonempty - 1, 0);
   if (num_nodes == 0) num_nodes = 1;  // T <= 1: a root with at most one leaf child
   out.nodes.assign(16 * num_nodes, 0.f);
+  out.num_nodes = num_nodes;
   out.slot_tri.assign(T, 0);
   B.nodes = out.nodes.data();
   B.slot_tri = out.slot_tri.data();
@@ -276,6 +277,37 @@ int32_t link_tree(size_t begin, size_t end, int32_t* left, int32_t* right) {
   return (int32_t)n;
 }
 }  // namespace
+
+void build_top_level(int n_roots, const float* boxes6, const int32_t* refs, float pad, int mesh_depth, Bvh& out) {
+  Builder B;
+  B.pad = pad;
+  out.pad = pad;
+  B.nodes = out.nodes.data();
+  std::vector<Builder::Item> items((size_t)n_roots);
+  out.roots.clear();
+  for (int r = 0; r < n_roots; r++) {
+    Builder::Item& it = items[r];
+    it.ref = refs[r];
+    for (int a = 0; a < 3; a++) {
+      it.box.lo[a] = boxes6[6 * r + a];
+      it.box.hi[a] = boxes6[6 * r + 3 + a];
+      it.key[a] = it.box.lo[a] + it.box.hi[a];
+    }
+    for (int a = 0; a < 3; a++) out.roots.push_back(it.box.lo[a] - pad);
+    for (int a = 0; a < 3; a++) out.roots.push_back(it.box.hi[a] + pad);
+    float ref_bits;
+    std::memcpy(&ref_bits, &it.ref, 4);
+    out.roots.push_back(ref_bits);
+  }
+  const int sub_depth = mesh_depth - 1;
+  out.mesh_depth = mesh_depth;
+  B.max_depth = sub_depth;
+  if (n_roots > 1) {
+    Box root;
+    B.build_top(items.data(), n_roots, 0, 0, root, sub_depth);
+  }
+  out.depth = B.max_depth.load() + 1;
+}
 
 void build_kdtree(std::vector<float>& photons7, int* height_out) {
   static_assert(sizeof(KdItem) == 28, "Particle is 28 bytes");

@@ -30,7 +30,8 @@ namespace rtb {
 // is ~50x that bound and also dominates the rounding of the slab arithmetic (<= 2^-22 * extent *
 // |1/d| against pad * |1/d|), so a triangle the brute force accepts is never culled.
 struct Bvh {
-  std::vector<float> nodes;        // 16 per node
+  std::vector<float> nodes;        // 16 per node (device-built trees: only the top-level join, see bvh_build.h)
+  size_t num_nodes = 0;            // nodes of the whole tree
   std::vector<int32_t> slot_tri;   // slot -> global triangle index
   int depth = 0;                   // longest root-to-leaf path in nodes (stack bound)
   float pad = 0.f;
@@ -43,6 +44,12 @@ struct Bvh {
 
 void build_bvh(int num_vertices, const float* positions, int num_triangles, const int32_t* triangles, int num_meshes,
                const int32_t* mesh_first_triangle, float extent, float pad_fraction, Bvh& out);
+
+// The top-level join alone, for a tree whose per-mesh subtrees were built elsewhere (csrc/bvh_build.cu): n_roots
+// exact (unpadded) mesh boxes lo[3],hi[3] and their references, mesh_depth = nodes on the longest root-to-leaf path
+// inside one mesh.  out.nodes must already hold >= max(n_roots-1, 1) nodes; the join is written to nodes
+// [0, n_roots-1); out.roots / out.depth / out.mesh_depth / out.pad are filled.
+void build_top_level(int n_roots, const float* boxes6, const int32_t* refs, float pad, int mesh_depth, Bvh& out);
 
 // Photon kd-tree exactly as kdtree::make_tree builds it (source/kdtree.h:60-69,119-126): in-place,
 // node at begin+(end-begin)/2 after std::nth_element on the cycling axis; the array ends in the

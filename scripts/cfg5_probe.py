@@ -9,7 +9,11 @@ t = time.time(); scene = rt.Scene.build(1920, 1080, meshes, os.path.join(meshes,
 N = int(os.environ.get("RT_N", "16"))
 t = time.time(); r = rt.Renderer(scene, N, 1, seed=1); t_create = time.time() - t
 nodes, depth = r.bvh()
-print(f"scene V={scene.V} T={scene.T} build {t_scene:.2f}s; rt_create (BVH build + upload) {t_create:.2f}s; bvh nodes {len(nodes)} depth {depth}", flush=True)
+st = r.stats()
+print(f"scene V={scene.V} T={scene.T} build {t_scene:.2f}s; rt_create {t_create:.2f}s (library {st['create_ms']:.0f} ms, of which BVH build "
+      f"{st['bvh_build_ms']:.0f} ms, RT_BVH_BUILD={os.environ.get('RT_BVH_BUILD', 'default')}); bvh nodes {len(nodes)} depth {depth}", flush=True)
+t = time.time(); r2 = rt.Renderer(scene, N, 1, seed=1); st2 = r2.stats(); r2.close()
+print(f"second rt_create {time.time() - t:.3f}s (library {st2['create_ms']:.0f} ms, BVH build {st2['bvh_build_ms']:.0f} ms)", flush=True)
 # parity at scale: BVH vs brute force on primary + secondary rays
 g = np.random.default_rng(3)
 n = 40000

@@ -383,3 +383,32 @@ def test_progressive_updates_match_the_per_pass_composite(rt):
             assert beq(px, rt.Renderer.composite(done, s, c, bg.pixels)), f"snapshot after {done} passes"
             part.close()
         r.close()
+
+
+# ----------------------------------------------------------------------------- device BVH build
+@pytest.mark.parametrize("name", ["stock", "lowres", "example"])
+def test_device_bvh_build_follows_the_policy_and_traces_identically(rt, gold, name, monkeypatch):
+    """csrc/bvh_build.cu: the level-synchronous GPU build obeys the same split-policy checker as the host builder
+    (tests/test_host.py), has the same shape (node count, depth), and tracing through it returns the reference's
+    golden hits bit for bit."""
+    from test_host import _check_bvh_policy
+    scene = rt.Scene.load(scene_path(name))
+    monkeypatch.setenv("RT_BVH_BUILD", "host")
+    rh = rt.Renderer(scene, 1, 0, seed=SEED)
+    monkeypatch.setenv("RT_BVH_BUILD", "gpu")
+    rg = rt.Renderer(scene, 1, 0, seed=SEED)
+    nodes_h, depth_h = rh.bvh()
+    nodes_g, depth_g = rg.bvh()
+    assert nodes_g.shape == nodes_h.shape and depth_g == depth_h
+    nonempty = int((np.diff(scene.mesh_tri_off) > 0).sum())
+    assert _check_bvh_policy(scene, nodes_g, rg.bvh_slots()) == scene.T - nonempty
+    g = gold(f"trace_{name}.npz")
+    h = rg.rayTrace(g["rays"])
+    assert (h["hit"] == g["hit"]).all() and (h["tri3"] == g["tri3"]).all() and beq(h["uvd"], g["uvd"])
+    assert (rg.occluded(g["rays"]) == g["hit"]).all()
+    # a frame through either tree is the same frame
+    monkeypatch.setenv("RT_BVH_BUILD", "host")
+    a = rt.Renderer(scene, 2, 1, seed=3, width=96, height=64).render_accumulate()
+    monkeypatch.setenv("RT_BVH_BUILD", "gpu")
+    b = rt.Renderer(scene, 2, 1, seed=3, width=96, height=64).render_accumulate()
+    assert beq(a[0], b[0]) and (a[1] == b[1]).all()
