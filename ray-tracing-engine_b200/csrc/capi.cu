@@ -185,7 +185,7 @@ int ensure_work(rt_ctx* c, size_t paths, bool path_mode) {
     CU(c->d_qd1.ensure(paths));
   }
   if (path_mode || c->params.num_photons > 0) {
-    CU(c->d_perm.ensure(1));
+    CU(c->d_perm.ensure(paths));
     CU(c->d_sorted.ensure(2 * paths));
     CU(c->d_sort_hist.ensure(kSortBuckets + 2));
   }

@@ -562,7 +562,11 @@ __global__ void __launch_bounds__(kSortThreads) k_sort_count(const RenderArgs A,
   const unsigned i0 = blockIdx.x * chunk, i1 = min(n, i0 + chunk);
   for (int b = threadIdx.x; b < kSortCells; b += kSortThreads) s_cnt[b] = 0;
   __syncthreads();
-  for (unsigned i = i0 + threadIdx.x; i < i1; i += kSortThreads) atomicAdd(s_cnt + sort_key(A, seg, i), 1u);
+  for (unsigned i = i0 + threadIdx.x; i < i1; i += kSortThreads) {
+    const unsigned key = sort_key(A, seg, i);
+    A.perm[i] = key;  // the scatter pass reads 4 bytes per ray instead of recomputing the key from 48
+    atomicAdd(s_cnt + key, 1u);
+  }
   __syncthreads();
   for (int b = threadIdx.x; b < kSortCells; b += kSortThreads)
     if (s_cnt[b]) atomicAdd(A.sort_hist + b, s_cnt[b]);
@@ -601,7 +605,7 @@ __global__ void __launch_bounds__(kSortThreads) k_sort_scatter(const RenderArgs 
   const unsigned i0 = blockIdx.x * chunk, i1 = min(n, i0 + chunk);
   for (int b = threadIdx.x; b < kSortCells; b += kSortThreads) s_cnt[b] = 0;
   __syncthreads();
-  for (unsigned i = i0 + threadIdx.x; i < i1; i += kSortThreads) atomicAdd(s_cnt + sort_key(A, seg, i), 1u);
+  for (unsigned i = i0 + threadIdx.x; i < i1; i += kSortThreads) atomicAdd(s_cnt + A.perm[i], 1u);
   __syncthreads();
   for (int b = threadIdx.x; b < kSortCells; b += kSortThreads)  // reserve this CTA's range in every bucket
     if (s_cnt[b]) s_cnt[b] = atomicAdd(A.sort_hist + b, s_cnt[b]);
@@ -611,7 +615,7 @@ __global__ void __launch_bounds__(kSortThreads) k_sort_scatter(const RenderArgs 
   // reads in k_shade (ncu, profiles/r1c_cfg2_frame_full.csv: 7.3 GB of DRAM reads and 47 % issue activity in the
   // gathering k_shade of a bounce segment against 1.1 GB / 68 % on the pixel-ordered segment 0).
   for (unsigned i = i0 + threadIdx.x; i < i1; i += kSortThreads) {
-    const unsigned dst = atomicAdd(s_cnt + sort_key(A, seg, i), 1u);
+    const unsigned dst = atomicAdd(s_cnt + A.perm[i], 1u);
     const float4 o = A.ray_o[seg & 1][i], d = A.ray_d[seg & 1][i];
     A.sorted[2 * (size_t)dst] = A.hit[i];  // one full 32-byte sector per ray
     A.sorted[2 * (size_t)dst + 1] = make_float4(d.x, d.y, d.z, o.w);

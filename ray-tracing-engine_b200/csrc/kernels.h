@@ -53,7 +53,8 @@ struct RenderArgs {
   int* hit_path;     // compacted hit j -> path id
   // spatial binning of the hit points of a bounce segment (counting sort by Morton cell): perm[k] = ray slot
   // processed k-th by k_shade, so that consecutive hits (and the shadow rays they spawn) are neighbours
-  unsigned int* perm;        // non-null: the bounce segments (and photon gathers) are processed in sorted order
+  unsigned int* perm;        // non-null: the bounce segments (and photon gathers) are processed in sorted order;
+                             // holds the Morton cell of every ray between k_sort_count and k_sort_scatter
   float4* sorted;            // sorted payload, 32 B per ray: [2k] hit record, [2k+1] direction (xyz) + path id (w)
                              // of the ray processed k-th by k_shade
   unsigned int* sort_hist;   // kSortBuckets + 2 counters (bucket kSortBuckets = misses)
