@@ -336,8 +336,11 @@ class Renderer:
         tri = hits["tri"].astype(np.int32)
         hit = (tri >= 0).astype(np.int32)
         safe = np.where(tri >= 0, tri, 0)
-        mesh = np.where(tri >= 0, self.scene.tri_mesh()[safe] if self.scene.T else 0, 0).astype(np.int32)
-        tri3 = np.where((tri >= 0)[:, None], self.scene.tri[safe] - self.scene.mesh_vtx_off[mesh][:, None], 0)
+        if self.scene.T:
+            mesh = np.where(tri >= 0, self.scene.tri_mesh()[safe], 0).astype(np.int32)
+            tri3 = np.where((tri >= 0)[:, None], self.scene.tri[safe] - self.scene.mesh_vtx_off[mesh][:, None], 0)
+        else:  # an empty scene: every ray misses
+            mesh, tri3 = np.zeros(n, np.int32), np.zeros((n, 3), np.int32)
         uvd = np.stack([hits["u"], hits["v"], hits["t"]], 1).astype(np.float32)
         return dict(hit=hit, mesh=mesh, tri3=tri3.astype(np.int32), uvd=uvd, tri_index=tri)
 

@@ -246,7 +246,7 @@ RT_DI void trace_body(const DScene& S, const float4* __restrict__ ro, const floa
 // site shared by "both children missed" and "leaf parked".  The result does not depend on the order in which
 // leaves are tested (accept_nearest is order-independent; any-hit is an OR), only the culling is a little later.
 // ----------------------------------------------------------------------------------------------
-template <bool ANY, bool BLOCKED, int LEAFT>
+template <bool ANY, bool BLOCKED, int LEAFT, int UNROLL = 1>
 RT_DI void trace_body_spec(const DScene& S, const float4* __restrict__ ro, const float4* __restrict__ rd,
                            const unsigned* n_ptr, unsigned n_fixed, float4* __restrict__ hits,
                            unsigned char* __restrict__ occ, unsigned* fetch, int depth, int* s_dyn) {
@@ -302,6 +302,8 @@ RT_DI void trace_body_spec(const DScene& S, const float4* __restrict__ ro, const
       continue;
     }
     for (;;) {
+#pragma unroll
+     for (int u = 0; u < UNROLL; u++) {  // UNROLL node steps per round of votes (the votes cost ~26 issue slots)
       bool need_pop = false;
       if (L.cur >= 0) {  // internal node: both child boxes
         const float4 n0 = __ldg(S.nodes + 4 * L.cur), n1 = __ldg(S.nodes + 4 * L.cur + 1);
@@ -327,6 +329,7 @@ RT_DI void trace_body_spec(const DScene& S, const float4* __restrict__ ro, const
         need_pop = true;
       }
       if (need_pop) trace_pop<ANY>(L, st_ref, st_tn);
+     }
 
       const unsigned pend_mask = __ballot_sync(kFull, pend != 0);
       if (pend_mask) {
@@ -362,18 +365,24 @@ RT_DI void trace_body_spec(const DScene& S, const float4* __restrict__ ro, const
   }
 }
 
-#define RT_TRACE_KERNEL_SPEC(NAME, LEAFT)                                                                           \
+#define RT_TRACE_KERNEL_SPEC(NAME, LEAFT, UNROLL)                                                                           \
   template <bool ANY, bool BLOCKED>                                                                                 \
   __global__ void __launch_bounds__(kBlock, 1)                                                                      \
       NAME(const DScene S, const float4* __restrict__ ro, const float4* __restrict__ rd, const unsigned* n_ptr,    \
            unsigned n_fixed, float4* __restrict__ hits, unsigned char* __restrict__ occ, unsigned* fetch, int depth) { \
     extern __shared__ int s_dyn[];                                                                                  \
-    trace_body_spec<ANY, BLOCKED, LEAFT>(S, ro, rd, n_ptr, n_fixed, hits, occ, fetch, depth, s_dyn);                \
+    trace_body_spec<ANY, BLOCKED, LEAFT, UNROLL>(S, ro, rd, n_ptr, n_fixed, hits, occ, fetch, depth, s_dyn);                \
   }
-RT_TRACE_KERNEL_SPEC(k_trace_sp8, 8)    // variant 5 (default since the root-list entry: 29.6 ms/frame vs 30.2 for variant 1)
-RT_TRACE_KERNEL_SPEC(k_trace_sp12, 12)  // variant 6
-RT_TRACE_KERNEL_SPEC(k_trace_sp16, 16)  // variant 7
-RT_TRACE_KERNEL_SPEC(k_trace_sp24, 24)  // variant 8
+RT_TRACE_KERNEL_SPEC(k_trace_sp8, 8, 1)    // variant 5 (default since the root-list entry: 29.6 ms/frame vs 30.2 for variant 1)
+RT_TRACE_KERNEL_SPEC(k_trace_sp12, 12, 1)  // variant 6
+RT_TRACE_KERNEL_SPEC(k_trace_sp16, 16, 1)  // variant 7
+RT_TRACE_KERNEL_SPEC(k_trace_sp24, 24, 1)  // variant 8
+RT_TRACE_KERNEL_SPEC(k_trace_sp8u2, 8, 2)  // variant 9: two node steps per round of votes
+RT_TRACE_KERNEL_SPEC(k_trace_sp8u3, 8, 3)  // variant 10 (default): 26.2 ms/frame; u2 26.7, u4 26.8, u6 27.7, u1 28.1
+RT_TRACE_KERNEL_SPEC(k_trace_sp12u2, 12, 2)  // variant 11
+RT_TRACE_KERNEL_SPEC(k_trace_sp8u4, 8, 4)    // variant 12
+RT_TRACE_KERNEL_SPEC(k_trace_sp8u6, 8, 6)    // variant 13
+RT_TRACE_KERNEL_SPEC(k_trace_sp12u4, 12, 4)  // variant 14
 
 #define RT_TRACE_KERNEL(NAME, LEAFB, MINB)                                                                        \
   template <bool ANY, bool BLOCKED>                                                                                 \
@@ -395,7 +404,7 @@ static int g_trace_variant = -1;
 int trace_variant() {
   if (g_trace_variant < 0) {
     const char* e = getenv("RT_TRACE_VARIANT");
-    g_trace_variant = e ? atoi(e) : 5;
+    g_trace_variant = e ? atoi(e) : 10;
   }
   return g_trace_variant;
 }
@@ -433,8 +442,14 @@ int trace_ctas_per_sm(int stack_depth) {
     case 6: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_trace_sp12<false, false>, kBlock, sm); break;
     case 7: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_trace_sp16<false, false>, kBlock, sm); break;
     case 8: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_trace_sp24<false, false>, kBlock, sm); break;
+    case 9: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_trace_sp8u2<false, false>, kBlock, sm); break;
+    case 11: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_trace_sp12u2<false, false>, kBlock, sm); break;
+    case 12: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_trace_sp8u4<false, false>, kBlock, sm); break;
+    case 13: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_trace_sp8u6<false, false>, kBlock, sm); break;
+    case 14: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_trace_sp12u4<false, false>, kBlock, sm); break;
     case 1: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_trace_lb8<false, false>, kBlock, sm); break;
-    default: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_trace_sp8<false, false>, kBlock, sm); break;
+    case 5: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_trace_sp8<false, false>, kBlock, sm); break;
+    default: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_trace_sp8u3<false, false>, kBlock, sm); break;
   }
   return n < 1 ? 1 : n;
 }
@@ -463,8 +478,14 @@ static void launch_trace_t(const DScene& S, const float4* ro, const float4* rd, 
       case 6: RT_LAUNCH(k_trace_sp12); break;
       case 7: RT_LAUNCH(k_trace_sp16); break;
       case 8: RT_LAUNCH(k_trace_sp24); break;
+      case 9: RT_LAUNCH(k_trace_sp8u2); break;
+      case 11: RT_LAUNCH(k_trace_sp12u2); break;
+      case 12: RT_LAUNCH(k_trace_sp8u4); break;
+      case 13: RT_LAUNCH(k_trace_sp8u6); break;
+      case 14: RT_LAUNCH(k_trace_sp12u4); break;
       case 1: RT_LAUNCH(k_trace_lb8); break;
-      default: RT_LAUNCH(k_trace_sp8); break;
+      case 5: RT_LAUNCH(k_trace_sp8); break;
+      default: RT_LAUNCH(k_trace_sp8u3); break;
     }
 #undef RT_LAUNCH
   }

@@ -202,6 +202,7 @@ def test_render_matches_port_oracle_other_seed_and_size(rt, O):
     port = O.PortOracle(flat)
     scene = rt.Scene.load(scene_path("stock"))
     for mode, N in ((0, 3), (1, 5)):
+        port.counters(reset=True)  # the port's counters are process-wide
         want = port.render(N, mode, 99, want_samples=True)
         r = rt.Renderer(scene, N, mode, seed=99, width=96, height=64)
         rgb, found = r.render_samples()
