@@ -30,7 +30,9 @@ namespace rtb {
 
 constexpr unsigned kFull = 0xffffffffu;
 constexpr int kDone = INT_MIN;    // traversal cursor value: no work (never a valid ~slot)
-constexpr int kRefillBelow = 22;  // refill a warp's idle lanes when fewer lanes than this are live
+constexpr int kRefillBelowDefault = 14;  // refill a warp's idle lanes when fewer lanes than this are live
+__constant__ int c_refill_below = kRefillBelowDefault;
+#define kRefillBelow c_refill_below
 
 // ----------------------------------------------------------------------------------------------
 // k_trace: persistent warps, one ray per lane, lanes refilled from the queue as their rays finish.
@@ -462,6 +464,12 @@ static void launch_trace_t(const DScene& S, const float4* ro, const float4* rd, 
     k_trace_brute<ANY, BLOCKED><<<grid, kBlock, 0, st>>>(S, ro, rd, n_ptr, n_fixed, hits, occ);
   } else {
     cudaMemsetAsync(fetch, 0, sizeof(unsigned), st);
+    static const int refill = getenv("RT_REFILL_BELOW") ? atoi(getenv("RT_REFILL_BELOW")) : -1;
+    static bool refill_set = false;
+    if (refill >= 0 && !refill_set) {
+      cudaMemcpyToSymbol(c_refill_below, &refill, sizeof(int));
+      refill_set = true;
+    }
     // any-hit keeps no tnear column: half the stack, and the rest of the SM's 256 KB stays L1 for the BVH
     const size_t sm = ANY ? trace_smem_bytes(depth) / 2 : trace_smem_bytes(depth);
     static const int carve = getenv("RT_CARVEOUT") ? atoi(getenv("RT_CARVEOUT")) : -1;
