@@ -141,6 +141,12 @@ int rt_create(const rt_scene* scene, const rt_params* params, int device, rt_ctx
 int rt_destroy(rt_ctx* ctx);
 int rt_set_params(rt_ctx* ctx, const rt_params* params); /* new size / N / mode / k / seed / shard */
 
+/* rt_composite on the device: sum_rgb_device / counter_device are full-frame device buffers (e.g. the result of
+ * the NCCL reduce of every rank's rt_render_accumulate_device), rgb_inout a HOST buffer holding the background on
+ * entry and the composite on exit.  Same arithmetic as rt_composite, bit for bit. */
+int rt_composite_device(rt_ctx* ctx, int32_t num_rays, const float* sum_rgb_device, const int32_t* counter_device,
+                        float* rgb_inout);
+
 /* Replaces `renderer.render(image)` (source/Main.cpp:224; source/Renderer.cpp:203-272).
  * rgb_inout: W*H*3 floats, row-major, y = 0 is the top row (source/Image.h:23-29).  In: the
  * background (Image::fillBackground, source/Image.cpp:12-21).  Out: the final composite

@@ -313,6 +313,13 @@ class Renderer:
                                               _capi.ptr(_capi.i32(counter)), _capi.ptr(out)))
         return out
 
+    def composite_device(self, num_rays, sum_rgb_ptr: int, counter_ptr: int, background):
+        """Renderer.cpp:262-265 on full-frame DEVICE sums/counters (after the multi-GPU reduce); returns [H,W,3]."""
+        out = np.ascontiguousarray(background, np.float32).copy()
+        _capi.check(self.lib.rt_composite_device(self._ctx, int(num_rays), C.c_void_p(sum_rgb_ptr),
+                                                 C.c_void_p(counter_ptr), _capi.ptr(out)))
+        return out
+
     def render_samples(self, window=None, samples=None):
         """Clamped per-sample colours [ns,h,w,3] and posIntersectionFound [ns,h,w] over a window."""
         x0, y0, x1, y1 = window if window else (0, 0, self.width, self.height)

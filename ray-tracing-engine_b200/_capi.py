@@ -80,6 +80,7 @@ SYMBOLS = {
     "rt_render_accumulate": (C.c_int, [_vp, _vp, _vp]),
     "rt_render_accumulate_device": (C.c_int, [_vp, _vp, _vp]),
     "rt_composite": (C.c_int, [_i32, _i32, _i32, _vp, _vp, _vp]),
+    "rt_composite_device": (C.c_int, [_vp, _i32, _vp, _vp, _vp]),
     "rt_render_samples": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
     "rt_trace_rays": (C.c_int, [_vp, _vp, _i64, _vp, _i32]),
     "rt_occluded": (C.c_int, [_vp, _vp, _i64, _vp, _i32]),

@@ -737,6 +737,21 @@ int rt_composite(int32_t width, int32_t height, int32_t num_rays, const float* s
   return RT_OK;
 }
 
+int rt_composite_device(rt_ctx* c, int32_t num_rays, const float* sum_rgb_device, const int32_t* counter_device,
+                        float* rgb_inout) {
+  if (!c || !sum_rgb_device || !counter_device || !rgb_inout) return fail(RT_ERR_INVALID, "null argument");
+  int rc = bind(c);
+  if (rc) return rc;
+  const size_t npx = (size_t)c->params.width * c->params.height;
+  CU(c->d_out_rgb.ensure(3 * npx));
+  CU(cudaMemcpyAsync(c->d_out_rgb.p, rgb_inout, sizeof(float) * 3 * npx, cudaMemcpyHostToDevice, c->stream));
+  launch_composite_frame(sum_rgb_device, counter_device, (long long)npx, num_rays, c->d_out_rgb.p, c->stream);
+  c->stats.kernel_launches++;
+  CU(cudaMemcpyAsync(rgb_inout, c->d_out_rgb.p, sizeof(float) * 3 * npx, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return RT_OK;
+}
+
 int rt_render(rt_ctx* c, float* rgb_inout) { return rt_render_progressive(c, rgb_inout, 0, nullptr, nullptr); }
 
 int rt_render_progressive(rt_ctx* c, float* rgb_inout, int32_t every, rt_progress_fn fn, void* user) {

@@ -916,6 +916,22 @@ __global__ void k_composite(const float4* __restrict__ acc_rgb, const int* __res
     out[3 * pixel + ch] = __fadd_rn(__fdiv_rn(s[ch], fn), __fdiv_rn(__fmul_rn(bg, miss), fn));
   }
 }
+// the same composite on full-frame sums/counters (after the multi-GPU reduce): rgb_inout holds the background
+__global__ void k_composite_frame(const float* __restrict__ sum_rgb, const int* __restrict__ counter, long long npx,
+                                  int num_rays, float* rgb_inout) {
+  const long long px = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (px >= npx) return;
+  const float fn = (float)num_rays, miss = (float)(num_rays - counter[px]);
+#pragma unroll
+  for (int ch = 0; ch < 3; ch++) {
+    const float bg = rgb_inout[3 * px + ch];
+    rgb_inout[3 * px + ch] = __fadd_rn(__fdiv_rn(sum_rgb[3 * px + ch], fn), __fdiv_rn(__fmul_rn(bg, miss), fn));
+  }
+}
+void launch_composite_frame(const float* sum_rgb, const int* counter, long long npx, int num_rays, float* rgb_inout,
+                            cudaStream_t st) {
+  k_composite_frame<<<(unsigned)((npx + 255) / 256), 256, 0, st>>>(sum_rgb, counter, npx, num_rays, rgb_inout);
+}
 // background and out may be the same buffer (rt_render composites in place)
 void launch_composite(const float4* acc_rgb, const int* acc_cnt, const int* pix_map, int npix, int num_rays,
                       const float* background, float* out, cudaStream_t st) {

@@ -79,6 +79,8 @@ void launch_resolve(const float4* col0, int npix, int nsamp, float4* acc_rgb, in
 void launch_scatter(const float4* acc_rgb, const int* acc_cnt, const int* pix_map, int npix, float* out_rgb,
                     int* out_cnt, cudaStream_t st);
 // the final composite over the background on the device (rt_render): rgb_inout holds the background on entry
+void launch_composite_frame(const float* sum_rgb, const int* counter, long long npx, int num_rays, float* rgb_inout,
+                            cudaStream_t st);
 void launch_composite(const float4* acc_rgb, const int* acc_cnt, const int* pix_map, int npix, int num_rays,
                       const float* background, float* out, cudaStream_t st);
 // parity hooks: caller-supplied rays through the SAME persistent trace kernels the renderer uses

@@ -10,7 +10,7 @@ The reference is a single process; the render path shards 
   * pixels    interleaved 16x16 tiles round-robin over ranks ("tile": bit-identical to 1 GPU, the reduce
               adds zeros) or sample-index ranges ("sample": each rank renders all pixels for its samples);
   * frame     the fp32 per-pixel sums and the int32 hit counters are sum-reduced to rank 0, which
-              composites over the background (Renderer.cpp:262-265) and writes the PPM.
+              composites over the background on its GPU (Renderer.cpp:262-265) and writes the PPM.
 
 Nothing here computes on the CPU: the functions move torch tensors and call the C ABI.
 """
@@ -114,6 +114,9 @@ def render_distributed(scene, num_rays, mode, num_photons=0, k=5, *, background,
     reduce_frame(sum_t, cnt_t, 0, group)
     out = None
     if rank == 0:
-        out = Renderer.composite(num_rays, sum_t.cpu().numpy(), cnt_t.cpu().numpy(), background)
+        if sum_t.is_cuda:  # composite on the device, one D2H of the frame
+            out = r.composite_device(num_rays, sum_t.data_ptr(), cnt_t.data_ptr(), background)
+        else:              # gloo tests: host tensors
+            out = Renderer.composite(num_rays, sum_t.numpy(), cnt_t.numpy(), background)
     r.close()
     return out

@@ -413,3 +413,20 @@ def test_device_bvh_build_follows_the_policy_and_traces_identically(rt, gold, na
     monkeypatch.setenv("RT_BVH_BUILD", "gpu")
     b = rt.Renderer(scene, 2, 1, seed=3, width=96, height=64).render_accumulate()
     assert beq(a[0], b[0]) and (a[1] == b[1]).all()
+
+
+def test_composite_device_equals_host_composite(rt):
+    """rt_composite_device (rank 0 after the NCCL reduce) == rt_composite on the host == what rt_render returns."""
+    import torch
+    scene = rt.Scene.load(scene_path("stock"))
+    W, H, N = 40, 30, 3
+    r = rt.Renderer(scene, N, 1, seed=2, width=W, height=H)
+    s_t = torch.zeros((H, W, 3), dtype=torch.float32, device="cuda")
+    c_t = torch.zeros((H, W), dtype=torch.int32, device="cuda")
+    r.render_accumulate_device(s_t.data_ptr(), c_t.data_ptr())
+    torch.cuda.synchronize()
+    bg = rt.Image(W, H).fillBackground().pixels
+    on_device = r.composite_device(N, s_t.data_ptr(), c_t.data_ptr(), bg)
+    on_host = rt.Renderer.composite(N, s_t.cpu().numpy(), c_t.cpu().numpy(), bg)
+    assert beq(on_device, on_host)
+    assert beq(on_device, r.render(rt.Image(W, H).fillBackground()).pixels)
