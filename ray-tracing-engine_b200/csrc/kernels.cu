@@ -30,6 +30,10 @@ namespace rtb {
 
 constexpr unsigned kFull = 0xffffffffu;
 constexpr int kDone = INT_MIN;    // traversal cursor value: no work (never a valid ~slot)
+#ifndef RT_ANY_FIXED_ORDER
+#define RT_ANY_FIXED_ORDER 0
+#endif
+constexpr bool kAnyFixedOrder = RT_ANY_FIXED_ORDER != 0;  // any-hit: visit child 0 first instead of the nearer child
 constexpr int kRefillBelowDefault = 14;  // refill a warp's idle lanes when fewer lanes than this are live
 __constant__ int c_refill_below = kRefillBelowDefault;
 #define kRefillBelow c_refill_below
@@ -314,7 +318,7 @@ RT_DI void trace_body_spec(const DScene& S, const float4* __restrict__ ro, const
         const bool h0 = box_hit_fma(f3(n0.x, n0.y, n0.z), f3(n0.w, n1.x, n1.y), L.inv, L.oinv, L.h.t, tn0);
         const bool h1 = box_hit_fma(f3(n1.z, n1.w, n2.x), f3(n2.y, n2.z, n2.w), L.inv, L.oinv, L.h.t, tn1);
         const int c0 = __float_as_int(n3.x), c1 = __float_as_int(n3.y);
-        const bool first0 = tn0 <= tn1;
+        const bool first0 = (ANY && kAnyFixedOrder) ? true : tn0 <= tn1;
         if (h0 && h1) {
           st_ref[L.sp * kBlock] = first0 ? c1 : c0;
           if (!ANY) st_tn[L.sp * kBlock] = __float_as_int(first0 ? tn1 : tn0);
