@@ -9,6 +9,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -140,6 +141,26 @@ void build_pix_map(const rt_params& p, std::vector<int>& map) {
     }
 }
 
+// the host side of the map is a pure function of (W, H, rank, count, tile): keep the last few (a context per frame
+// in the e2e path would otherwise rebuild 176 k entries every time)
+std::vector<int> cached_pix_map(const rt_params& p) {
+  struct Entry {
+    int w, h, rank, count, tile;
+    std::vector<int> map;
+  };
+  static std::mutex mu;
+  static std::vector<Entry> cache;
+  const int count = p.shard_count > 1 ? p.shard_count : 1, rank = count > 1 ? p.shard_rank : 0;
+  const int tile = p.shard_tile > 0 ? p.shard_tile : 16;
+  std::lock_guard<std::mutex> lock(mu);
+  for (const Entry& e : cache)
+    if (e.w == p.width && e.h == p.height && e.rank == rank && e.count == count && e.tile == tile) return e.map;
+  if (cache.size() >= 4) cache.erase(cache.begin());
+  cache.push_back(Entry{p.width, p.height, rank, count, tile, {}});
+  build_pix_map(p, cache.back().map);
+  return cache.back().map;
+}
+
 int ensure_pix_map(rt_ctx* c) {
   const rt_params& p = c->params;
   int count = p.shard_count > 1 ? p.shard_count : 1, rank = count > 1 ? p.shard_rank : 0;
@@ -147,8 +168,7 @@ int ensure_pix_map(rt_ctx* c) {
   if (c->pix_w == p.width && c->pix_h == p.height && c->pix_rank == rank && c->pix_count == count &&
       c->pix_tile == tile)
     return RT_OK;
-  std::vector<int> map;
-  build_pix_map(p, map);
+  const std::vector<int> map = cached_pix_map(p);
   CU(c->d_pix_map.ensure(map.size()));
   if (!map.empty()) CU(cudaMemcpy(c->d_pix_map.p, map.data(), map.size() * sizeof(int), cudaMemcpyHostToDevice));
   c->npix = (int)map.size();
@@ -167,6 +187,23 @@ int trace_stack_depth(const rt_ctx* c) {
 
 // bytes of wavefront state per path slot (ensure_work below)
 constexpr size_t kBytesPerPath = 16 * 2 + 32 * 2 + 16 + 3 * (32 + 16 + 1) + 4 + 32;
+
+void release_work(rt_ctx* c) {
+  c->d_col0.release();
+  c->d_col1.release();
+  c->d_qo0.release();
+  c->d_qo1.release();
+  c->d_qd0.release();
+  c->d_qd1.release();
+  c->d_hit.release();
+  c->d_hit_path.release();
+  c->d_sh_o.release();
+  c->d_sh_d.release();
+  c->d_contrib.release();
+  c->d_occ.release();
+  c->d_perm.release();
+  c->d_sorted.release();
+}
 
 int ensure_work(rt_ctx* c, size_t paths, bool path_mode) {
   const size_t shadow = shadow_slots_for((unsigned)paths);
@@ -353,23 +390,29 @@ struct Progress {
 };
 int render_to_device(rt_ctx* c, float* out_rgb_dev, int* out_cnt_dev, float* composite_dev = nullptr,
                      const Progress* progress = nullptr) {
+  static const bool timing = getenv("RT_TIMING") != nullptr;
+  double t_prev = now_ms();
+  auto tick = [&](const char* what) {
+    if (!timing) return;
+    const double t = now_ms();
+    fprintf(stderr, "[render] %s %.3f ms; ", what, t - t_prev);
+    t_prev = t;
+  };
   int rc = bind(c);
   if (rc) return rc;
   if ((rc = prepare_photons(c))) return rc;
   if ((rc = ensure_pix_map(c))) return rc;
+  tick("bind+pixmap");
   const rt_params& p = c->params;
   const size_t npx = (size_t)p.width * p.height;
   const bool path_mode = p.mode == 1;
-  // batch size: bounded by free HBM (kBytesPerPath of wavefront state per path) and by 2^30 paths
+  // Batch size: <= 32 M paths (kBytesPerPath of wavefront state each, 9.3 GB) by default.  Free HBM is only asked for
+  // when that allocation fails (cudaMemGetInfo costs 1.2-1.6 ms, a twentieth of a cfg2 frame): then the batch shrinks
+  // to half of what is free and the allocation is retried once.
   int spb = p.samples_per_batch;
-  if (spb <= 0) {
-    // default: batches of <= 32 M paths (8.4 GB of wavefront state), fewer when HBM is short
-    if (c->auto_paths == 0) {
-      size_t free_b = 0, total_b = 0;
-      CU(cudaMemGetInfo(&free_b, &total_b));
-      size_t budget = std::min<size_t>(free_b / 2 + c->d_col0.n * kBytesPerPath, (size_t)32 << 30);
-      c->auto_paths = std::max<size_t>(1, std::min<size_t>(budget / kBytesPerPath, (size_t)32 << 20));
-    }
+  const bool auto_batch = spb <= 0;
+  if (auto_batch) {
+    if (c->auto_paths == 0) c->auto_paths = (size_t)32 << 20;
     spb = (int)std::max<size_t>(1, std::min<size_t>(c->auto_paths / std::max(c->npix, 1), 1 << 20));
   }
   const int samp_first = p.sample_first;
@@ -382,7 +425,22 @@ int render_to_device(rt_ctx* c, float* out_rgb_dev, int* out_cnt_dev, float* com
     snapshot.resize(3 * npx);
     CU(c->d_scratch.ensure(sizeof(float) * 3 * npx));
   }
-  if ((rc = ensure_work(c, (size_t)c->npix * spb, path_mode))) return rc;
+  tick("batch sizing");
+  rc = ensure_work(c, (size_t)c->npix * spb, path_mode);
+  if (rc == RT_ERR_OOM && auto_batch) {
+    cudaGetLastError();
+    release_work(c);
+    CU(cudaStreamSynchronize(c->stream));
+    size_t free_b = 0, total_b = 0;
+    CU(cudaMemGetInfo(&free_b, &total_b));
+    c->auto_paths = std::max<size_t>(1, std::min<size_t>(free_b / 2 / kBytesPerPath, (size_t)32 << 20));
+    spb = (int)std::max<size_t>(1, std::min<size_t>(c->auto_paths / std::max(c->npix, 1), 1 << 20));
+    spb = std::max(1, std::min(spb, std::max(samp_end - samp_first, 1)));
+    if (preview) spb = std::max(1, std::min(spb, progress->every));
+    rc = ensure_work(c, (size_t)c->npix * spb, path_mode);
+  }
+  if (rc) return rc;
+  tick("ensure_work");
   CU(c->d_acc.ensure(c->npix));
   CU(c->d_acc_cnt.ensure(c->npix));
   CU(cudaMemsetAsync(c->d_acc.p, 0, sizeof(float4) * (size_t)c->npix, c->stream));
@@ -425,7 +483,9 @@ int render_to_device(rt_ctx* c, float* out_rgb_dev, int* out_cnt_dev, float* com
     }
   }
   CU(cudaEventRecord(c->ev1, c->stream));
+  tick("launches");
   CU(cudaStreamSynchronize(c->stream));
+  tick("sync");
   CU(cudaGetLastError());
   float ms = 0.f;
   CU(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
@@ -438,7 +498,10 @@ int render_to_device(rt_ctx* c, float* out_rgb_dev, int* out_cnt_dev, float* com
   }
   c->stats.trace_ms = seg_ms;
   c->stats.samples += (uint64_t)c->npix * (uint64_t)std::max(samp_end - samp_first, 0);
-  return pull_counters(c);
+  rc = pull_counters(c);
+  tick("events+counters");
+  if (timing) fprintf(stderr, "\n");
+  return rc;
 }
 
 }  // namespace
