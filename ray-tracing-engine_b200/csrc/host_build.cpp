@@ -259,14 +259,23 @@ namespace {
 struct KdItem {
   float v[7];
 };
-int make_tree(KdItem* nodes, size_t begin, size_t end, size_t index) {  // kdtree.h:60-69
+// kdtree.h:60-69.  The two recursive calls work on disjoint ranges, so the upper levels fork threads: every
+// std::nth_element call sees exactly the input it sees in the serial recursion, and the array ends up identical.
+int make_tree(KdItem* nodes, size_t begin, size_t end, size_t index, int fork_levels) {
   if (end <= begin) return 0;
   size_t n = begin + (end - begin) / 2;
   std::nth_element(nodes + begin, nodes + n, nodes + end,
                    [index](const KdItem& a, const KdItem& b) { return a.v[index] < b.v[index]; });
   index = (index + 1) % 3;
-  int hl = make_tree(nodes, begin, n, index);
-  int hr = make_tree(nodes, n + 1, end, index);
+  int hl = 0, hr = 0;
+  if (fork_levels > 0 && end - begin > 16384) {
+    std::thread t([&]() { hl = make_tree(nodes, begin, n, index, fork_levels - 1); });
+    hr = make_tree(nodes, n + 1, end, index, fork_levels - 1);
+    t.join();
+  } else {
+    hl = make_tree(nodes, begin, n, index, 0);
+    hr = make_tree(nodes, n + 1, end, index, 0);
+  }
   return 1 + std::max(hl, hr);
 }
 int32_t link_tree(size_t begin, size_t end, int32_t* left, int32_t* right) {
@@ -312,7 +321,8 @@ void build_top_level(int n_roots, const float* boxes6, const int32_t* refs, floa
 void build_kdtree(std::vector<float>& photons7, int* height_out) {
   static_assert(sizeof(KdItem) == 28, "Particle is 28 bytes");
   size_t n = photons7.size() / 7;
-  int h = make_tree(reinterpret_cast<KdItem*>(photons7.data()), 0, n, 0);
+  unsigned hw = std::thread::hardware_concurrency();
+  int h = make_tree(reinterpret_cast<KdItem*>(photons7.data()), 0, n, 0, hw >= 16 ? 4 : hw >= 8 ? 3 : hw >= 4 ? 2 : hw >= 2 ? 1 : 0);
   if (height_out) *height_out = h;
 }
 
