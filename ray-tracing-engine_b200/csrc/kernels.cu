@@ -30,6 +30,9 @@ namespace rtb {
 
 constexpr unsigned kFull = 0xffffffffu;
 constexpr int kDone = INT_MIN;    // traversal cursor value: no work (never a valid ~slot)
+#ifndef RT_SHADE_MINB
+#define RT_SHADE_MINB 8  // minimum CTAs/SM of the direct-lighting k_shade (register cap 64)
+#endif
 #ifndef RT_ANY_FIXED_ORDER
 #define RT_ANY_FIXED_ORDER 0
 #endif
@@ -703,7 +706,7 @@ RT_DI float3 shade_photon(const DScene& S, float3 dir, float3 n, float3 P, const
 size_t knn_smem_bytes(int k, int frames) { return (size_t)(2 * k + 3 * frames) * kBlock * sizeof(int); }
 
 template <int MODE, bool PHOTON>
-__global__ void __launch_bounds__(kBlock, PHOTON ? 6 : 8) k_shade(const RenderArgs A, const int seg) {
+__global__ void __launch_bounds__(kBlock, PHOTON ? 6 : RT_SHADE_MINB) k_shade(const RenderArgs A, const int seg) {
   extern __shared__ unsigned long long s_knn[];  // PHOTON only: k 64-bit candidate rows, then 3*frames int rows
   const DScene& S = A.scene;
   const unsigned n = seg == 0 ? (unsigned)A.npix * (unsigned)A.nsamp : A.q_count[kQHits0 + seg - 1];
