@@ -30,6 +30,9 @@ namespace rtb {
 
 constexpr unsigned kFull = 0xffffffffu;
 constexpr int kDone = INT_MIN;    // traversal cursor value: no work (never a valid ~slot)
+#ifndef RT_TRACE_MINB
+#define RT_TRACE_MINB 10  // minimum CTAs/SM of the postponed-leaf trace kernels: 47 registers, no spills (1: 55 registers, 9 CTAs; 12: 40 registers, slower)
+#endif
 #ifndef RT_SHADE_MINB
 #define RT_SHADE_MINB 8  // minimum CTAs/SM of the direct-lighting k_shade (register cap 64)
 #endif
@@ -376,7 +379,7 @@ RT_DI void trace_body_spec(const DScene& S, const float4* __restrict__ ro, const
 
 #define RT_TRACE_KERNEL_SPEC(NAME, LEAFT, UNROLL)                                                                           \
   template <bool ANY, bool BLOCKED>                                                                                 \
-  __global__ void __launch_bounds__(kBlock, 1)                                                                      \
+  __global__ void __launch_bounds__(kBlock, RT_TRACE_MINB)                                                                      \
       NAME(const DScene S, const float4* __restrict__ ro, const float4* __restrict__ rd, const unsigned* n_ptr,    \
            unsigned n_fixed, float4* __restrict__ hits, unsigned char* __restrict__ occ, unsigned* fetch, int depth) { \
     extern __shared__ int s_dyn[];                                                                                  \
