@@ -265,23 +265,34 @@ __global__ void k_mark(const Seg* __restrict__ seg, const int* __restrict__ seg_
   side[ord[i]] = right ? 1 : 0;
 }
 
+// The three axis orders are processed by one launch each step (blockIdx.y = axis); per-axis arrays are strided by T
+// (flags, scan, out) or by nb (block sums).
+struct Orders {
+  const int* in[3];
+  int* out[3];
+};
 // flags of one axis' order: 1 = the triangle at this position moves to the right child of a segment cut on ANOTHER axis
-__global__ void k_flags(const Seg* __restrict__ seg, const int* __restrict__ seg_of_pos, const int* __restrict__ ord,
-                        const unsigned char* __restrict__ side, int axis, int T, int* flags) {
+__global__ void k_flags(const Seg* __restrict__ seg, const int* __restrict__ seg_of_pos, Orders ord,
+                        const unsigned char* __restrict__ side, int T, int* flags) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int axis = blockIdx.y;
   if (i >= T) return;
   const int s = seg_of_pos[i];
   int f = 0;
   if (s >= 0) {
     const int a = seg[s].axis;
-    if (a >= 0 && a != axis) f = side[ord[i]];
+    if (a >= 0 && a != axis) f = side[ord.in[axis][i]];
   }
-  flags[i] = f;
+  flags[(size_t)axis * T + i] = f;
 }
 // exclusive scan of T ints: per-block scan + block sums, scan of the sums by one block, add back
 constexpr int kScanBlock = 1024;
-__global__ void __launch_bounds__(kScanBlock) k_scan_block(const int* __restrict__ in, int T, int* out, int* block_sum) {
+__global__ void __launch_bounds__(kScanBlock) k_scan_block(const int* __restrict__ in_all, int T, int* out_all,
+                                                           int* block_sum_all) {
   __shared__ int s[kScanBlock];
+  const int* in = in_all + (size_t)blockIdx.y * T;
+  int* out = out_all + (size_t)blockIdx.y * T;
+  int* block_sum = block_sum_all + (size_t)blockIdx.y * gridDim.x;
   const int i = blockIdx.x * kScanBlock + threadIdx.x;
   const int v = i < T ? in[i] : 0;
   s[threadIdx.x] = v;
@@ -295,8 +306,9 @@ __global__ void __launch_bounds__(kScanBlock) k_scan_block(const int* __restrict
   if (i < T) out[i] = s[threadIdx.x] - v;
   if (threadIdx.x == kScanBlock - 1) block_sum[blockIdx.x] = s[threadIdx.x];
 }
-__global__ void __launch_bounds__(kScanBlock) k_scan_sums(int* block_sum, int nb) {  // nb <= kScanBlock * kScanBlock
+__global__ void __launch_bounds__(kScanBlock) k_scan_sums(int* block_sum_all, int nb) {  // one CTA per axis
   __shared__ int s[kScanBlock];
+  int* block_sum = block_sum_all + (size_t)blockIdx.x * nb;
   int carry = 0;
   for (int base = 0; base < nb; base += kScanBlock) {
     const int i = base + threadIdx.x;
@@ -315,11 +327,15 @@ __global__ void __launch_bounds__(kScanBlock) k_scan_sums(int* block_sum, int nb
     carry += total;
   }
 }
-__global__ void k_partition(const Seg* __restrict__ seg, const int* __restrict__ seg_of_pos, const int* __restrict__ ord,
-                            const int* __restrict__ flags, const int* __restrict__ scan, const int* __restrict__ block_sum,
-                            int axis, int T, int* out) {
+__global__ void k_partition(const Seg* __restrict__ seg, const int* __restrict__ seg_of_pos, Orders ord,
+                            const int* __restrict__ flags_all, const int* __restrict__ scan_all,
+                            const int* __restrict__ block_sum_all, int T, int nb) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int axis = blockIdx.y;
   if (i >= T) return;
+  const int* flags = flags_all + (size_t)axis * T;
+  const int* scan = scan_all + (size_t)axis * T;
+  const int* block_sum = block_sum_all + (size_t)axis * nb;
   const int s = seg_of_pos[i];
   int dst = i;
   if (s >= 0) {
@@ -331,7 +347,7 @@ __global__ void k_partition(const Seg* __restrict__ seg, const int* __restrict__
       dst = flags[i] ? g.b + nl + r : g.b + (i - g.b) - r;
     }
   }
-  out[dst] = ord[i];
+  ord.out[axis][dst] = ord.in[axis][i];
 }
 __global__ void k_init_pos(const Seg* __restrict__ seg, int S, int* seg_of_pos) {  // level 0: mesh ranges
   const int s = blockIdx.y;
@@ -439,7 +455,8 @@ bool build_bvh_device(const float4* d_pos, const int4* d_vidx, int T, int M, con
   {
     auto P = Arena::padded;
     const size_t t = (size_t)T;
-    BV(arena.reserve(2 * P(t * 16) + 3 * P((size_t)n2 * 8) + 9 * P(t * 4) + P((size_t)nb * 4) + 2 * P(4) + P(t) +
+    BV(arena.reserve(2 * P(t * 16) + 3 * P((size_t)n2 * 8) + 9 * P(t * 4) + 2 * P(3 * t * 4) + P(3 * (size_t)nb * 4) +
+                     2 * P(4) + P(t) +
                      2 * P(max_seg * sizeof(Seg)) + 2 * P(6 * max_seg * 4) + P(6 * (size_t)nonempty * 4) +
                      P((size_t)nonempty * 4) + 4096));
   }
@@ -452,9 +469,10 @@ bool build_bvh_device(const float4* d_pos, const int4* d_vidx, int T, int M, con
   struct IntBuf {
     int* p;
   };
-  IntBuf ord[3] = {{arena.take<int>(T)}, {arena.take<int>(T)}, {arena.take<int>(T)}}, ord_tmp{arena.take<int>(T)},
-         seg_pos{arena.take<int>(T)}, seg_pos_next{arena.take<int>(T)}, flags{arena.take<int>(T)}, scan{arena.take<int>(T)},
-         block_sum{arena.take<int>(nb)}, slot_tri{arena.take<int>(T)}, next_count{arena.take<int>(1)},
+  IntBuf ord[3] = {{arena.take<int>(T)}, {arena.take<int>(T)}, {arena.take<int>(T)}},
+         ord_tmp[3] = {{arena.take<int>(T)}, {arena.take<int>(T)}, {arena.take<int>(T)}}, seg_pos{arena.take<int>(T)},
+         seg_pos_next{arena.take<int>(T)}, flags{arena.take<int>(3 * (size_t)T)}, scan{arena.take<int>(3 * (size_t)T)},
+         block_sum{arena.take<int>(3 * (size_t)nb)}, slot_tri{arena.take<int>(T)}, next_count{arena.take<int>(1)},
          root_ref{arena.take<int>(nonempty)};
   struct {
     unsigned char* p;
@@ -507,7 +525,7 @@ bool build_bvh_device(const float4* d_pos, const int4* d_vidx, int T, int M, con
   unsigned *cur_box = box_a.p, *nxt_box = box_b.p;
   int *pos_cur = seg_pos.p, *pos_nxt = seg_pos_next.p;
   int* o[3] = {ord[0].p, ord[1].p, ord[2].p};
-  int* o_tmp = ord_tmp.p;
+  int* o_tmp[3] = {ord_tmp[0].p, ord_tmp[1].p, ord_tmp[2].p};
   const int levels = tree_depth(max_n);
   // Segment counts per level are known without asking the device: a mesh of n triangles contributes segments of at
   // most two distinct sizes per level (floor and ceiling halves), so the host tracks {size: count} and the level loop
@@ -522,13 +540,18 @@ bool build_bvh_device(const float4* d_pos, const int4* d_vidx, int T, int M, con
                                                 root_ref.p, nxt, next_count.p, nxt_box);
     k_mark<<<blocksT, threads, 0, st>>>(cur, pos_cur, o[0], o[1], o[2], T, side.p, pos_nxt);
     launches += 3;
-    for (int a = 0; a < 3 && level + 1 < levels; a++) {
-      k_flags<<<blocksT, threads, 0, st>>>(cur, pos_cur, o[a], side.p, a, T, flags.p);
-      k_scan_block<<<nb, kScanBlock, 0, st>>>(flags.p, T, scan.p, block_sum.p);
-      k_scan_sums<<<1, kScanBlock, 0, st>>>(block_sum.p, nb);
-      k_partition<<<blocksT, threads, 0, st>>>(cur, pos_cur, o[a], flags.p, scan.p, block_sum.p, a, T, o_tmp);
+    if (level + 1 < levels) {  // the three orders in one launch per step (blockIdx.y = axis)
+      Orders oo;
+      for (int a = 0; a < 3; a++) {
+        oo.in[a] = o[a];
+        oo.out[a] = o_tmp[a];
+      }
+      k_flags<<<dim3(blocksT, 3), threads, 0, st>>>(cur, pos_cur, oo, side.p, T, flags.p);
+      k_scan_block<<<dim3(nb, 3), kScanBlock, 0, st>>>(flags.p, T, scan.p, block_sum.p);
+      k_scan_sums<<<3, kScanBlock, 0, st>>>(block_sum.p, nb);
+      k_partition<<<dim3(blocksT, 3), threads, 0, st>>>(cur, pos_cur, oo, flags.p, scan.p, block_sum.p, T, nb);
       launches += 4;
-      std::swap(o[a], o_tmp);
+      for (int a = 0; a < 3; a++) std::swap(o[a], o_tmp[a]);
     }
     long long S_next = 0;
     std::vector<std::pair<int, long long>> next_sizes;
