@@ -76,9 +76,9 @@ RT_DI void trace_pop(TraceLane& L, const int* st_ref, const int* st_tn) {
 template <bool ANY>
 RT_DI void trace_write(const TraceLane& L, float4* __restrict__ hits, unsigned char* __restrict__ occ) {
   if (ANY)
-    occ[L.idx] = (L.h.gid != 0x7fffffff) ? 1 : 0;
+    __stcs(occ + L.idx, (unsigned char)((L.h.gid != 0x7fffffff) ? 1 : 0));
   else
-    hits[L.idx] = make_float4(L.h.t, L.h.u, L.h.v, __int_as_float(L.h.gid != 0x7fffffff ? L.h.gid : -1));
+    __stcs(hits + L.idx, make_float4(L.h.t, L.h.u, L.h.v, __int_as_float(L.h.gid != 0x7fffffff ? L.h.gid : -1)));
 }
 // A new ray enters the scene through the list of per-mesh roots (the reference loops over the meshes,
 // RayTracer.h:56-85): all root boxes are tested back to back, the nearest hit one becomes the cursor and the others
@@ -197,7 +197,7 @@ RT_DI void trace_body(const DScene& S, const float4* __restrict__ ro, const floa
         bool valid = my < n;
         if (BLOCKED && valid) valid = ((my / 96u) * 32u + (my & 31u)) < items;
         if (valid) {
-          const float4 a = __ldg(ro + my), b = __ldg(rd + my);
+          const float4 a = __ldcs(ro + my), b = __ldcs(rd + my);  // streamed once: keep L1 for the BVH
           L.idx = my;
           L.o = f3(a);
           L.d = f3(b);
@@ -294,7 +294,7 @@ RT_DI void trace_body_spec(const DScene& S, const float4* __restrict__ ro, const
         bool valid = my < n;
         if (BLOCKED && valid) valid = ((my / 96u) * 32u + (my & 31u)) < items;
         if (valid) {
-          const float4 a = __ldg(ro + my), b = __ldg(rd + my);
+          const float4 a = __ldcs(ro + my), b = __ldcs(rd + my);  // streamed once: keep L1 for the BVH
           L.idx = my;
           L.o = f3(a);
           L.d = f3(b);
