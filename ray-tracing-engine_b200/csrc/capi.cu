@@ -258,6 +258,7 @@ void fill_args(rt_ctx* c, RenderArgs& a, const int* pix_map, int npix, bool use_
   a.photon = use_photons ? 1 : 0;
   a.k = p.k;
   a.kd_frames = c->kd_height + 1;
+  a.num_sms = c->num_sms;
   a.num_photons = p.num_photons;
   a.brute = (p.flags & RT_FLAG_BRUTE_FORCE) ? 1 : 0;
   a.seed_mixed = mix64(p.seed + kGolden);

@@ -829,6 +829,14 @@ void launch_shade(const RenderArgs& a, int seg, int grid, cudaStream_t st) {
   if (a.photon) {
     cudaFuncSetAttribute(k_shade<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
     cudaFuncSetAttribute(k_shade<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    // grid-stride kernel: launch exactly what is resident (the k-NN shared memory allows 6 CTAs/SM at k = 10, 2 at
+    // k = 50; 8 per SM left a third of the CTAs for a second, mostly empty wave -- 26 % warps active in ncu)
+    int occ = 0;
+    if (a.mode == 0)
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_shade<0, true>, kBlock, sm);
+    else
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_shade<1, true>, kBlock, sm);
+    if (occ > 0 && a.num_sms > 0) grid = grid < a.num_sms * occ ? grid : a.num_sms * occ;
   }
   if (a.mode == 0) {
     if (a.photon)

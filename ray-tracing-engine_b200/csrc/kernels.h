@@ -34,6 +34,7 @@ struct RenderArgs {
   int photon;       // 1: gather from the photon map instead of direct lighting
   int k;            // neighbours
   int kd_frames;    // kd-tree height + 1: stack frames per thread of kd_knearest_sorted
+  int num_sms;      // multiprocessors of the device (grid sizing of the grid-stride kernels)
   int num_photons;  // REQUESTED photon count (Renderer.cpp:99)
   int brute;        // 1: O(T) scan instead of BVH
   int stack_depth;  // traversal stack entries per ray (>= bvh depth)
