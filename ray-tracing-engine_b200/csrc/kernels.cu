@@ -385,16 +385,9 @@ RT_DI void trace_body_spec(const DScene& S, const float4* __restrict__ ro, const
     extern __shared__ int s_dyn[];                                                                                  \
     trace_body_spec<ANY, BLOCKED, LEAFT, UNROLL>(S, ro, rd, n_ptr, n_fixed, hits, occ, fetch, depth, s_dyn);                \
   }
-RT_TRACE_KERNEL_SPEC(k_trace_sp8, 8, 1)    // variant 5 (default since the root-list entry: 29.6 ms/frame vs 30.2 for variant 1)
-RT_TRACE_KERNEL_SPEC(k_trace_sp12, 12, 1)  // variant 6
-RT_TRACE_KERNEL_SPEC(k_trace_sp16, 16, 1)  // variant 7
-RT_TRACE_KERNEL_SPEC(k_trace_sp24, 24, 1)  // variant 8
-RT_TRACE_KERNEL_SPEC(k_trace_sp8u2, 8, 2)  // variant 9: two node steps per round of votes
+// Variants kept for comparison (RT_TRACE_VARIANT); everything else that was measured is in profiles/r1_tuning.md.
+RT_TRACE_KERNEL_SPEC(k_trace_sp8, 8, 1)    // variant 5: one node step per round of votes (28.1 ms/frame)
 RT_TRACE_KERNEL_SPEC(k_trace_sp8u3, 8, 3)  // variant 10 (default): 26.2 ms/frame; u2 26.7, u4 26.8, u6 27.7, u1 28.1
-RT_TRACE_KERNEL_SPEC(k_trace_sp12u2, 12, 2)  // variant 11
-RT_TRACE_KERNEL_SPEC(k_trace_sp8u4, 8, 4)    // variant 12
-RT_TRACE_KERNEL_SPEC(k_trace_sp8u6, 8, 6)    // variant 13
-RT_TRACE_KERNEL_SPEC(k_trace_sp12u4, 12, 4)  // variant 14
 
 #define RT_TRACE_KERNEL(NAME, LEAFB, MINB)                                                                        \
   template <bool ANY, bool BLOCKED>                                                                                 \
@@ -404,13 +397,10 @@ RT_TRACE_KERNEL_SPEC(k_trace_sp12u4, 12, 4)  // variant 14
     extern __shared__ int s_dyn[];                                                                                  \
     trace_body<ANY, BLOCKED, LEAFB>(S, ro, rd, n_ptr, n_fixed, hits, occ, fetch, depth, s_dyn);                     \
   }
-// Measured on B200, cfg2 frame (profiles/r1_tuning.md): variant 0 37.4 ms, 1 33.6 ms, 2 34.1 ms,
-// 3 37.1 ms, 4 34.5 ms  ->  variant 1 is the default.
+// Measured on B200, cfg2 frame (profiles/r1_tuning.md): variant 0 37.4 ms, variant 1 33.6 ms at the time; the
+// postponed-leaf kernels above superseded both.
 RT_TRACE_KERNEL(k_trace_lb8, 8, 1)    // variant 1: batch leaf tests, >= 8 lanes
 RT_TRACE_KERNEL(k_trace, 0, 1)        // variant 0: test leaves as they come
-RT_TRACE_KERNEL(k_trace_lb16, 16, 1)  // variant 2: >= 16 lanes
-RT_TRACE_KERNEL(k_trace_occ, 0, 12)   // variant 3: variant 0 capped to 40 registers (12 CTAs/SM)
-RT_TRACE_KERNEL(k_trace_lb8occ, 8, 12)  // variant 4
 
 static int g_trace_variant = -1;
 int trace_variant() {
@@ -448,17 +438,6 @@ int trace_ctas_per_sm(int stack_depth) {
   const size_t sm = trace_smem_bytes(stack_depth);
   switch (trace_variant()) {
     case 0: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_trace<false, false>, kBlock, sm); break;
-    case 2: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_trace_lb16<false, false>, kBlock, sm); break;
-    case 3: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_trace_occ<false, false>, kBlock, sm); break;
-    case 4: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_trace_lb8occ<false, false>, kBlock, sm); break;
-    case 6: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_trace_sp12<false, false>, kBlock, sm); break;
-    case 7: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_trace_sp16<false, false>, kBlock, sm); break;
-    case 8: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_trace_sp24<false, false>, kBlock, sm); break;
-    case 9: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_trace_sp8u2<false, false>, kBlock, sm); break;
-    case 11: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_trace_sp12u2<false, false>, kBlock, sm); break;
-    case 12: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_trace_sp8u4<false, false>, kBlock, sm); break;
-    case 13: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_trace_sp8u6<false, false>, kBlock, sm); break;
-    case 14: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_trace_sp12u4<false, false>, kBlock, sm); break;
     case 1: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_trace_lb8<false, false>, kBlock, sm); break;
     case 5: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_trace_sp8<false, false>, kBlock, sm); break;
     default: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_trace_sp8u3<false, false>, kBlock, sm); break;
@@ -490,17 +469,6 @@ static void launch_trace_t(const DScene& S, const float4* ro, const float4* rd, 
   } while (0)
     switch (trace_variant()) {
       case 0: RT_LAUNCH(k_trace); break;
-      case 2: RT_LAUNCH(k_trace_lb16); break;
-      case 3: RT_LAUNCH(k_trace_occ); break;
-      case 4: RT_LAUNCH(k_trace_lb8occ); break;
-      case 6: RT_LAUNCH(k_trace_sp12); break;
-      case 7: RT_LAUNCH(k_trace_sp16); break;
-      case 8: RT_LAUNCH(k_trace_sp24); break;
-      case 9: RT_LAUNCH(k_trace_sp8u2); break;
-      case 11: RT_LAUNCH(k_trace_sp12u2); break;
-      case 12: RT_LAUNCH(k_trace_sp8u4); break;
-      case 13: RT_LAUNCH(k_trace_sp8u6); break;
-      case 14: RT_LAUNCH(k_trace_sp12u4); break;
       case 1: RT_LAUNCH(k_trace_lb8); break;
       case 5: RT_LAUNCH(k_trace_sp8); break;
       default: RT_LAUNCH(k_trace_sp8u3); break;

@@ -1,5 +1,5 @@
 """Time kernel tuning variants on the headline workload (device time from CUDA events inside the library).
-usage: python scripts/tune.py [variant ...]   (each variant runs in its own process: RT_TRACE_VARIANT)"""
+usage: python scripts/tune.py [variant ...]  (variants 0, 1, 5, 10)   (each variant runs in its own process: RT_TRACE_VARIANT)"""
 import json, os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if len(sys.argv) > 1 and sys.argv[1] == "--one":
