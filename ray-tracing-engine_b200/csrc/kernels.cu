@@ -636,9 +636,10 @@ void launch_sort_hits(const RenderArgs& a, int seg, cudaStream_t st) {
     configured = true;
   }
   cudaMemsetAsync(a.sort_hist, 0, (kSortBuckets + 2) * sizeof(unsigned), st);
-  k_sort_count<<<148, kSortThreads, kSortSmem, st>>>(a, seg);
+  const int ctas = (a.num_sms > 0 ? a.num_sms : 148) * (kSortSmem <= 48 * 1024 ? 2 : 1);  // resident CTAs
+  k_sort_count<<<ctas, kSortThreads, kSortSmem, st>>>(a, seg);
   k_sort_scan<<<1, 1024, 0, st>>>(a.sort_hist);
-  k_sort_scatter<<<148, kSortThreads, kSortSmem, st>>>(a, seg);
+  k_sort_scatter<<<ctas, kSortThreads, kSortSmem, st>>>(a, seg);
 }
 
 // ----------------------------------------------------------------------------------------------
