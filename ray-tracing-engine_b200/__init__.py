@@ -166,6 +166,7 @@ def _host_lib():
         lib.rth_camera.argtypes = [C.c_int, C.c_int, vp]
         lib.rth_background.argtypes = [C.c_int, C.c_int, vp]
         lib.rth_save_ppm.argtypes = [C.c_char_p, C.c_int, C.c_int, vp]
+        lib.rth_save_ppm_binary.argtypes = [C.c_char_p, C.c_int, C.c_int, vp]
         _hostlib = lib
     return _hostlib
 

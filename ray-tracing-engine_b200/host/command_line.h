@@ -1,7 +1,8 @@
 // command_line.h -- the reference's command line (source/CommandLine.h:9-102): same flags, defaults,
 // banner and error texts.  Additive options (absent = stock behaviour): -i/-input <file.off> replaces
 // ../meshes/cube_tri.off, -meshdir <dir>, -subdiv <n>, -seed <n>, -device <n>, -brute, -update <n> (rewrite
-// update.ppm every n sample passes as the reference does after every pass, Renderer.cpp:268-269; 0 = at the end).
+// update.ppm every n sample passes as the reference does after every pass, Renderer.cpp:268-269; 0 = at the end),
+// -p6 1 (binary P6 output instead of ASCII P3, same quantisation).
 #pragma once
 #include <cstdlib>
 #include <iostream>
@@ -14,6 +15,7 @@ struct CommandLine {
   // additive
   std::string input, meshDir = "../meshes";
   int subdiv = 0, device = 0, update = 0;
+  bool p6 = false;  // -p6 1: write binary P6 instead of the reference's ASCII P3
   unsigned long long seed = 1;
   bool brute = false;
 
@@ -25,7 +27,7 @@ struct CommandLine {
                  "tracing)>][-p/-numPhotons <number of photons for a photon map. If "
                  "defined, photon map-based rendering is used.>][-k <number of "
                  "neighbours in photon mapping. Use only with -p/-numPhotons>]"
-                 "[-i/-input <mesh.off>][-meshdir <dir>][-subdiv <n>][-seed <n>][-device <n>][-brute 1][-update <n>]"
+                 "[-i/-input <mesh.off>][-meshdir <dir>][-subdiv <n>][-seed <n>][-device <n>][-brute 1][-update <n>][-p6 1]"
               << std::endl;
   }
 
@@ -53,6 +55,7 @@ struct CommandLine {
       else if (a == "-device") device = std::atoi(argv[++i]);
       else if (a == "-brute") brute = std::atoi(argv[++i]) != 0;
       else if (a == "-update") update = std::atoi(argv[++i]);
+      else if (a == "-p6") p6 = std::atoi(argv[++i]) != 0;
       else throw std::runtime_error("Unknown argument <" + a + ">");
     }
     // CommandLine.h:78-96

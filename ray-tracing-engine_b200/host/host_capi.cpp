@@ -84,4 +84,9 @@ void rth_save_ppm(const char* path, int width, int height, const float* rgb) {
   rth::save_ppm(path, width, height, v);
 }
 
+void rth_save_ppm_binary(const char* path, int width, int height, const float* rgb) {
+  std::vector<float> v(rgb, rgb + (size_t)width * height * 3);
+  rth::save_ppm_binary(path, width, height, v);
+}
+
 }  // extern "C"

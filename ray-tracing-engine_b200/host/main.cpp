@@ -91,11 +91,12 @@ int main(int argc, char** argv) {
   // passes from a device-side composite of the samples so far, 0 only once at the end (same final file).
   struct Preview {
     int w, h;
-  } preview{(int)args.width, (int)args.height};
+    bool p6;
+  } preview{(int)args.width, (int)args.height, args.p6};
   auto on_update = [](void* user, int32_t done, int32_t total, const float* rgb) {
     const Preview* pv = static_cast<const Preview*>(user);
     std::vector<float> snap(rgb, rgb + 3 * (size_t)pv->w * pv->h);
-    rth::save_ppm("update.ppm", pv->w, pv->h, snap);
+    (pv->p6 ? rth::save_ppm_binary : rth::save_ppm)("update.ppm", pv->w, pv->h, snap);
     printProgressBar(total > 0 ? (float)done / (float)total : 1.f);
   };
   if ((rc = rt_render_progressive(ctx, image.data(), args.update > 0 ? args.update : (int)args.numRays + 1, on_update,
@@ -103,7 +104,7 @@ int main(int argc, char** argv) {
     die(rc);  // Main.cpp:224
   printProgressBar(1.f);
   std::cout << std::endl;
-  rth::save_ppm(args.outputFilename, (int)args.width, (int)args.height, image);  // Main.cpp:227
+  (args.p6 ? rth::save_ppm_binary : rth::save_ppm)(args.outputFilename, (int)args.width, (int)args.height, image);  // Main.cpp:227
 
   rt_stats st{};
   rt_get_stats(ctx, &st);

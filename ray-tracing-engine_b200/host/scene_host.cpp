@@ -269,6 +269,19 @@ void save_ppm(const std::string& filename, int width, int height, const std::vec
   out.close();
 }
 
+void save_ppm_binary(const std::string& filename, int width, int height, const std::vector<float>& rgb) {
+  std::ofstream out(filename.c_str(), std::ios::binary);
+  if (!out) {
+    std::cerr << "Cannot open file " << filename.c_str() << std::endl;
+    std::exit(1);
+  }
+  out << "P6\n" << width << " " << height << "\n255\n";
+  std::vector<unsigned char> bytes((size_t)width * height * 3);
+  for (size_t i = 0; i < bytes.size(); i++) bytes[i] = (unsigned char)static_cast<unsigned int>(255.f * rgb[i]);
+  out.write(reinterpret_cast<const char*>(bytes.data()), (std::streamsize)bytes.size());
+  out.close();
+}
+
 void save_pcd(const std::string& filename, const std::vector<rt_photon>& photons) {
   std::ofstream out(filename.c_str());
   if (!out) {

@@ -63,6 +63,8 @@ void build_reference_scene(int width, int height, const SceneOptions& opt, HostS
 // Image (source/Image.h, Image.cpp)
 void fill_background(int width, int height, std::vector<float>& rgb);                      // Image.cpp:12-21
 void save_ppm(const std::string& filename, int width, int height, const std::vector<float>& rgb);  // Image.cpp:23-43
+// the same pixels (same `unsigned(255.f * v)` quantisation) as binary P6: 6 MB instead of ~23 MB of text at 1080p
+void save_ppm_binary(const std::string& filename, int width, int height, const std::vector<float>& rgb);
 // PhotonMap::saveToPCD (source/PhotonMap.h:59-84)
 void save_pcd(const std::string& filename, const std::vector<rt_photon>& photons);
 

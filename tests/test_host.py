@@ -175,6 +175,11 @@ def test_image_background_and_ppm(gold, tmp_path):
     p2 = str(tmp_path / "b.ppm")
     lib.rth_save_ppm(p2.encode(), 3, 2, _capi.ptr(img.pixels))
     assert open(p2).read() == open(path).read()
+    # -p6 1: binary P6 with the same quantisation
+    p3 = str(tmp_path / "c.ppm")
+    lib.rth_save_ppm_binary(p3.encode(), 3, 2, _capi.ptr(img.pixels))
+    assert open(p3, "rb").read() == b"P6\n3 2\n255\n" + bytes([0, 127, 255, 254, 51, 25, 255, 255, 255, 1, 0, 76, 63, 191, 153,
+                                                                0, 0, 0])
 
 
 def test_cli_banner_and_errors(tmp_path):
