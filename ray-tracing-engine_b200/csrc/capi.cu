@@ -5,12 +5,14 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/rt_b200.h"
@@ -357,6 +359,20 @@ int photons_per_light(const rt_ctx* c, float* light_pdf_out) {
   return (int)((float)c->params.num_photons * light_pdf);
 }
 
+// fn(begin, end) over [0, n) on up to 8 host threads when n is large (scene packing for million-triangle scenes)
+template <typename F>
+void parallel_ranges(int64_t n, F fn) {
+  unsigned hw = std::thread::hardware_concurrency();
+  int nt = n >= (1 << 18) ? (int)std::min<unsigned>(8, hw ? hw : 1) : 1;
+  if (nt <= 1) {
+    fn((int64_t)0, n);
+    return;
+  }
+  std::vector<std::thread> th;
+  for (int t = 0; t < nt; t++) th.emplace_back([=]() { fn(n * t / nt, n * (t + 1) / nt); });
+  for (auto& x : th) x.join();
+}
+
 // largest |coordinate| of any vertex, light or the camera: scales the BVH padding (host_build.h)
 float scene_extent(const rt_scene* s) {
   float extent = 0.f;
@@ -594,9 +610,14 @@ int rt_create(const rt_scene* s, const rt_params* p, int device, rt_ctx** out) {
     return fail(RT_ERR_NO_DEVICE, "no CUDA device available (this library has no CPU fallback)");
   }
   if (device < 0 || device >= ndev) return fail(RT_ERR_INVALID, "device ordinal out of range");
-  for (int t = 0; t < 3 * s->num_triangles; t++)
-    if (s->triangles[t] < 0 || s->triangles[t] >= s->num_vertices)
-      return fail(RT_ERR_INVALID, "triangle vertex index out of range");
+  {
+    std::atomic<bool> bad{false};
+    parallel_ranges(3 * (int64_t)s->num_triangles, [&](int64_t b, int64_t e) {
+      for (int64_t t = b; t < e; t++)
+        if (s->triangles[t] < 0 || s->triangles[t] >= s->num_vertices) bad = true;
+    });
+    if (bad) return fail(RT_ERR_INVALID, "triangle vertex index out of range");
+  }
 
   const double t_create0 = now_ms();
   rt_ctx* c = new rt_ctx();
@@ -650,17 +671,19 @@ int rt_create(const rt_scene* s, const rt_params* p, int device, rt_ctx** out) {
   // ---- shading data up first: the device BVH builder reads positions and triangle indices from HBM ----
   std::vector<float4> h_pos(std::max(c->V, 1)), h_nrm(std::max(c->V, 1));
   std::vector<int4> h_vidx(std::max(c->T, 1));
-  for (int v = 0; v < c->V; v++) {
-    h_pos[v] = make_float4(s->positions[3 * v], s->positions[3 * v + 1], s->positions[3 * v + 2], 0.f);
-    h_nrm[v] = make_float4(s->normals[3 * v], s->normals[3 * v + 1], s->normals[3 * v + 2], 0.f);
-  }
-  {
+  parallel_ranges(c->V, [&](int64_t b, int64_t e) {
+    for (int64_t v = b; v < e; v++) {
+      h_pos[v] = make_float4(s->positions[3 * v], s->positions[3 * v + 1], s->positions[3 * v + 2], 0.f);
+      h_nrm[v] = make_float4(s->normals[3 * v], s->normals[3 * v + 1], s->normals[3 * v + 2], 0.f);
+    }
+  });
+  parallel_ranges(c->T, [&](int64_t b, int64_t e) {
     int m = 0;
-    for (int t = 0; t < c->T; t++) {
+    for (int64_t t = b; t < e; t++) {
       while (m + 1 < c->M && t >= s->mesh_first_triangle[m + 1]) m++;
       h_vidx[t] = make_int4(s->triangles[3 * t], s->triangles[3 * t + 1], s->triangles[3 * t + 2], m);
     }
-  }
+  });
   std::vector<DMaterial> h_mats(std::max(c->M, 1));
   for (int m = 0; m < c->M; m++) {
     const rt_material& a = s->materials[m];
