@@ -107,6 +107,7 @@ struct rt_ctx {
   DevBuf<unsigned long long> d_counters;
   DevBuf<unsigned char> d_scratch;
   size_t auto_paths = 0;  // cached batch-size decision (paths per wavefront batch)
+  bool oom_injected = false;  // RT_TEST_OOM_ONCE (tests only)
   std::vector<cudaEvent_t> seg_events;  // pairs around every k_segment launch of the current render
   size_t seg_events_used = 0;
   rt_stats stats{};
@@ -444,12 +445,22 @@ int render_to_device(rt_ctx* c, float* out_rgb_dev, int* out_cnt_dev, float* com
   }
   tick("batch sizing");
   rc = ensure_work(c, (size_t)c->npix * spb, path_mode);
+  if (auto_batch && rc == RT_OK && getenv("RT_TEST_OOM_ONCE") && !c->oom_injected) {  // test hook for the retry path
+    c->oom_injected = true;
+    rc = RT_ERR_OOM;
+  }
   if (rc == RT_ERR_OOM && auto_batch) {
     cudaGetLastError();
     release_work(c);
     CU(cudaStreamSynchronize(c->stream));
+    {  // hand the pool's cached blocks back so that the query below sees them as free
+      cudaMemPool_t pool;
+      CU(cudaDeviceGetDefaultMemPool(&pool, c->device));
+      CU(cudaMemPoolTrimTo(pool, 0));
+    }
     size_t free_b = 0, total_b = 0;
     CU(cudaMemGetInfo(&free_b, &total_b));
+    if (getenv("RT_TEST_OOM_ONCE")) free_b = std::min<size_t>(free_b, (size_t)64 << 20);  // force several batches
     c->auto_paths = std::max<size_t>(1, std::min<size_t>(free_b / 2 / kBytesPerPath, (size_t)32 << 20));
     spb = (int)std::max<size_t>(1, std::min<size_t>(c->auto_paths / std::max(c->npix, 1), 1 << 20));
     spb = std::max(1, std::min(spb, std::max(samp_end - samp_first, 1)));

@@ -219,3 +219,16 @@ def test_million_triangle_scene_bvh_equals_bruteforce(rt, tmp_path):
     s1, c1 = r.render_accumulate()
     s2, c2 = r.render_accumulate()
     assert beq(s1, s2) and (c1 == c2).all() and c1.min() == 1
+
+
+def test_out_of_memory_retry_renders_the_same_frame(rt, monkeypatch):
+    """When the default 32 M-path wavefront allocation fails, the batch shrinks to half of the free HBM and the
+    render is retried (csrc/capi.cu).  RT_TEST_OOM_ONCE injects the failure and pretends 64 MB are free: the frame is
+    rendered in many small batches and must be bit-identical (samples are accumulated in index order)."""
+    scene = rt.Scene.load(scene_path("stock"))
+    want_s, want_c = rt.Renderer(scene, 6, 1, seed=8, width=160, height=120).render_accumulate()
+    monkeypatch.setenv("RT_TEST_OOM_ONCE", "1")
+    r = rt.Renderer(scene, 6, 1, seed=8, width=160, height=120)
+    s, c = r.render_accumulate()
+    assert beq(s, want_s) and (c == want_c).all()
+    assert r.stats()["kernel_launches"] > 30, "the injected failure must have forced more than one batch"
