@@ -93,6 +93,9 @@ typedef struct rt_params {
 
 #define RT_MAX_K 64
 #define RT_FLAG_BRUTE_FORCE 1 /* trace with the O(T) scan instead of the BVH (parity hook) */
+#define RT_FLAG_KNN_EXACT 2   /* gather the canonical exact k nearest photons (by distance, then array index) instead of
+                                 reproducing kdtree::knearest's two quirks: fewer node visits, but 0.5-2.8 % of the
+                                 queries -- and the pixels they feed -- differ from the reference */
 
 /* one ray / one nearest-hit record, as the parity hooks exchange them */
 typedef struct rt_ray {

@@ -23,7 +23,7 @@ import os
 import numpy as np
 
 from . import _capi
-from ._capi import RT_FLAG_BRUTE_FORCE, RtError, rt_params, rt_stats  # noqa: F401
+from ._capi import RT_FLAG_BRUTE_FORCE, RT_FLAG_KNN_EXACT, RtError, rt_params, rt_stats  # noqa: F401
 
 __all__ = ["Scene", "Image", "Renderer", "RtError", "RAYTRACE", "PATHTRACE"]
 

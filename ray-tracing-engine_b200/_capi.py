@@ -17,6 +17,7 @@ LIB_PATH = os.path.join(PKG_DIR, "lib", "librt_b200.so")
 RT_OK = 0
 RT_ERR_INVALID, RT_ERR_NO_DEVICE, RT_ERR_CUDA, RT_ERR_EMPTY_TREE, RT_ERR_K_TOO_LARGE, RT_ERR_OOM = -1, -2, -3, -4, -5, -6
 RT_FLAG_BRUTE_FORCE = 1
+RT_FLAG_KNN_EXACT = 2
 RT_MAX_K = 64
 
 

@@ -260,6 +260,7 @@ void fill_args(rt_ctx* c, RenderArgs& a, const int* pix_map, int npix, bool use_
   a.mode = p.mode == 1 ? 1 : 0;                // CommandLine.h:84-87: anything else is ray tracing
   a.photon = use_photons ? 1 : 0;
   a.k = p.k;
+  a.knn_exact = (p.flags & RT_FLAG_KNN_EXACT) ? 1 : 0;
   a.kd_frames = c->kd_height + 1;
   a.num_sms = c->num_sms;
   a.num_photons = p.num_photons;
@@ -1139,7 +1140,8 @@ int rt_knn(rt_ctx* c, const float* queries, int64_t n, int32_t k, int32_t* node_
   if (e == cudaSuccess) e = d_idx.ensure((size_t)n * k);
   if (e == cudaSuccess) e = cudaMemcpy(d_q.p, queries, sizeof(float) * 3 * (size_t)n, cudaMemcpyHostToDevice);
   if (e == cudaSuccess) {
-    launch_knn(c->scene, d_q.p, n, k, c->kd_height + 1, d_idx.p, c->d_counters.p, c->stream);
+    launch_knn(c->scene, d_q.p, n, k, c->kd_height + 1, (c->params.flags & RT_FLAG_KNN_EXACT) ? 1 : 0, d_idx.p,
+               c->d_counters.p, c->stream);
     c->stats.kernel_launches++;
     e = cudaStreamSynchronize(c->stream);
   }

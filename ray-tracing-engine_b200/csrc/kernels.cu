@@ -659,8 +659,11 @@ __device__ __noinline__ void knn_exact_redo(const DScene& S, float3 q, int k, un
 }
 
 RT_DI float3 shade_photon(const DScene& S, float3 dir, float3 n, float3 P, const DMaterial& m, int k, int num_photons,
-                          unsigned long long* sc, int* kst, unsigned long long& visits) {
-  if (kd_knearest_sorted(S, P, k, sc, kst, kBlock, visits)) knn_exact_redo(S, P, k, sc, kBlock);
+                          int exact, unsigned long long* sc, int* kst, unsigned long long& visits) {
+  if (exact)
+    kd_knearest_exact(S, P, k, sc, kst, kBlock, visits);
+  else if (kd_knearest_sorted(S, P, k, sc, kst, kBlock, visits))
+    knn_exact_redo(S, P, k, sc, kBlock);
   float r = kd_dist_of(sc[(k - 1) * kBlock]);  // farthest of the k (candidates are in ascending distance)
   float area = (float)__dmul_rn(__dmul_rn(3.141592653589793, (double)r), (double)r);
   float3 avg = f3(0.f, 0.f, 0.f);
@@ -748,7 +751,7 @@ __global__ void __launch_bounds__(kBlock, PHOTON ? 6 : RT_SHADE_MINB) k_shade(co
       A.hit_path[j] = (int)p;
       if (PHOTON) {
         n_knn++;
-        float3 c = shade_photon(S, d, nrm, P, m, A.k, A.num_photons, s_knn + threadIdx.x,
+        float3 c = shade_photon(S, d, nrm, P, m, A.k, A.num_photons, A.knn_exact, s_knn + threadIdx.x,
                                 (int*)(s_knn + A.k * kBlock) + threadIdx.x, n_visits);
         A.contrib[shadow_slot(j, 0)] = make_float4(c.x, c.y, c.z, 0.f);
         A.occ[shadow_slot(j, 0)] = 0;
@@ -942,24 +945,26 @@ void launch_bsdf(DMaterial m, const float* n_wi_wo, long long n, float* rgb, cud
 }
 
 __global__ void __launch_bounds__(kBlock) k_knn(const DScene S, const float* __restrict__ q3, long long n, int k,
-                                                int* node_index, unsigned long long* counters) {
+                                                int exact, int* node_index, unsigned long long* counters) {
   extern __shared__ unsigned long long s_knn[];
   long long i = (long long)blockIdx.x * kBlock + threadIdx.x;
   if (i >= n) return;
   unsigned long long* sc = s_knn + threadIdx.x;
   unsigned long long visits = 0;
   const float3 q = f3(q3[3 * i], q3[3 * i + 1], q3[3 * i + 2]);
-  if (kd_knearest_sorted(S, q, k, sc, (int*)(s_knn + k * kBlock) + threadIdx.x, kBlock, visits))
+  if (exact)
+    kd_knearest_exact(S, q, k, sc, (int*)(s_knn + k * kBlock) + threadIdx.x, kBlock, visits);
+  else if (kd_knearest_sorted(S, q, k, sc, (int*)(s_knn + k * kBlock) + threadIdx.x, kBlock, visits))
     knn_exact_redo(S, q, k, sc, kBlock);
   for (int j = 0; j < k; j++) node_index[i * k + j] = kd_index_of(sc[j * kBlock]);
   atomicAdd(counters + kCntKdVisits, visits);
   atomicAdd(counters + kCntKnn, 1ull);
 }
-void launch_knn(const DScene& s, const float* q3, long long n, int k, int kd_frames, int* node_index,
+void launch_knn(const DScene& s, const float* q3, long long n, int k, int kd_frames, int exact, int* node_index,
                 unsigned long long* counters, cudaStream_t st) {
   const size_t sm = knn_smem_bytes(k, kd_frames);
   cudaFuncSetAttribute(k_knn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-  k_knn<<<(int)((n + kBlock - 1) / kBlock), kBlock, sm, st>>>(s, q3, n, k, node_index, counters);
+  k_knn<<<(int)((n + kBlock - 1) / kBlock), kBlock, sm, st>>>(s, q3, n, k, exact, node_index, counters);
 }
 
 // ----------------------------------------------------------------------------------------------

@@ -33,6 +33,7 @@ struct RenderArgs {
   int mode;         // 0 ray, 1 path
   int photon;       // 1: gather from the photon map instead of direct lighting
   int k;            // neighbours
+  int knn_exact;    // RT_FLAG_KNN_EXACT
   int kd_frames;    // kd-tree height + 1: stack frames per thread of kd_knearest_sorted
   int num_sms;      // multiprocessors of the device (grid sizing of the grid-stride kernels)
   int num_photons;  // REQUESTED photon count (Renderer.cpp:99)
@@ -95,7 +96,7 @@ void launch_bsdf(DMaterial m, const float* n_wi_wo, long long n, float* rgb, cud
 // photon emission: path q = light*npaths + j traces path (first_path + j) of `light`
 void launch_emit(const DScene& s, uint64_t seed_mixed, int per_light, float light_pdf, int first_path, int npaths,
                  int brute, float4* out_a, float4* out_b, unsigned long long* counters, cudaStream_t st);
-void launch_knn(const DScene& s, const float* q3, long long n, int k, int kd_frames, int* node_index,
+void launch_knn(const DScene& s, const float* q3, long long n, int k, int kd_frames, int exact, int* node_index,
                 unsigned long long* counters, cudaStream_t st);
 
 }  // namespace rtb

@@ -713,4 +713,66 @@ RT_DI bool kd_knearest_sorted(const DScene& S, float3 q, int k, unsigned long lo
   return tie;
 }
 
+// ------------------------------------------------------------------------------------------------
+// kd_knearest_exact (RT_FLAG_KNN_EXACT; off by default because it changes 0.5-2.8 % of the
+// queries against the reference): the k photons with the smallest (distance, array index), in that order -- a
+// canonical exact k-NN on the same tree.  No seeds, no `best == 0` shortcut, and the bound is on the current k-th
+// distance itself: a far side is skipped when every photon behind the plane is strictly farther than it.
+// Candidates are the same packed (distance bits << 32 | index) words, whose integer order IS (distance, index).
+// ------------------------------------------------------------------------------------------------
+RT_DI void kd_knearest_exact(const DScene& S, float3 q, int k, unsigned long long* sc, int* kst, int ks,
+                             unsigned long long& visits) {
+  int cnt = 0;
+  unsigned long long worst = ~0ull;  // packed k-th candidate; all-ones while fewer than k are held
+  int sp = 0, b = 0, e = S.kd_count, axis = 0;
+  unsigned nv = 0;
+  while (e > b) {
+    const int n = b + (e - b) / 2;
+    nv++;
+    const float4 p = __ldg(S.kd_pos + n);
+    const unsigned long long cand = kd_pack(v_dist(f3(p), q), n);
+    if (cand < worst) {
+      int m = (cnt < k ? cnt : k - 1) - 1;  // last slot that stays
+      unsigned long long w = 0;
+      while (m >= 0 && (w = sc[m * ks]) > cand) {
+        sc[(m + 1) * ks] = w;
+        m--;
+      }
+      sc[(m + 1) * ks] = cand;
+      if (cnt < k) cnt++;
+      if (cnt == k) worst = sc[(k - 1) * ks];
+    }
+    float pa = p.x, qa = q.x;
+    if (axis == 1) pa = p.y, qa = q.y;
+    if (axis == 2) pa = p.z, qa = q.z;
+    const float dx = __fsub_rn(pa, qa);
+    const bool left_near = dx > 0.f;
+    const int nb = left_near ? b : n + 1, ne = left_near ? n : e;
+    const int fb = left_near ? n + 1 : b, fe = left_near ? e : n;
+    axis = axis == 2 ? 0 : axis + 1;
+    if (fe > fb) {
+      // every photon in the far side is at least |dx| away (2-ulp margin for sqrt(fl(a*a)) < |a|); the k-th
+      // distance only shrinks, so a side that cannot matter now is not pushed at all
+      const float thr = __fmul_rn(fabsf(dx), 0.9999995f);
+      if (cnt < k || !(thr > kd_dist_of(worst))) {
+        kst[(3 * sp) * ks] = fb;
+        kst[(3 * sp + 1) * ks] = fe | (axis << 28);
+        kst[(3 * sp + 2) * ks] = __float_as_int(thr);
+        sp++;
+      }
+    }
+    b = nb;
+    e = ne;
+    while (e <= b && sp > 0) {
+      sp--;
+      if (cnt == k && __int_as_float(kst[(3 * sp + 2) * ks]) > kd_dist_of(worst)) continue;
+      const int fe2 = kst[(3 * sp + 1) * ks];
+      b = kst[(3 * sp) * ks];
+      axis = (fe2 >> 28) & 3;
+      e = fe2 & 0x0fffffff;
+    }
+  }
+  visits += nv;
+}
+
 }  // namespace rtb

@@ -15,6 +15,8 @@ struct CommandLine {
   // additive
   std::string input, meshDir = "../meshes";
   int subdiv = 0, device = 0, update = 0;
+  bool knnExact = false;  // -knn exact: canonical exact k nearest photons (RT_FLAG_KNN_EXACT) instead of the
+                          // reference's kdtree::knearest (default, "-knn reference")
   bool p6 = false;  // -p6 1: write binary P6 instead of the reference's ASCII P3
   unsigned long long seed = 1;
   bool brute = false;
@@ -27,7 +29,7 @@ struct CommandLine {
                  "tracing)>][-p/-numPhotons <number of photons for a photon map. If "
                  "defined, photon map-based rendering is used.>][-k <number of "
                  "neighbours in photon mapping. Use only with -p/-numPhotons>]"
-                 "[-i/-input <mesh.off>][-meshdir <dir>][-subdiv <n>][-seed <n>][-device <n>][-brute 1][-update <n>][-p6 1]"
+                 "[-i/-input <mesh.off>][-meshdir <dir>][-subdiv <n>][-seed <n>][-device <n>][-brute 1][-update <n>][-p6 1][-knn reference|exact]"
               << std::endl;
   }
 
@@ -56,6 +58,7 @@ struct CommandLine {
       else if (a == "-brute") brute = std::atoi(argv[++i]) != 0;
       else if (a == "-update") update = std::atoi(argv[++i]);
       else if (a == "-p6") p6 = std::atoi(argv[++i]) != 0;
+      else if (a == "-knn") knnExact = std::string(argv[++i]) == "exact";
       else throw std::runtime_error("Unknown argument <" + a + ">");
     }
     // CommandLine.h:78-96

@@ -55,7 +55,7 @@ int main(int argc, char** argv) {
   p.num_photons = (int32_t)args.numPhotons;
   p.k = (int32_t)args.k;
   p.seed = args.seed;
-  p.flags = args.brute ? RT_FLAG_BRUTE_FORCE : 0;
+  p.flags = (args.brute ? RT_FLAG_BRUTE_FORCE : 0) | (args.knnExact ? RT_FLAG_KNN_EXACT : 0);
 
   rt_scene view = scene.view();
   rt_ctx* ctx = nullptr;
