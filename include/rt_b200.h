@@ -137,9 +137,10 @@ typedef struct rt_ctx rt_ctx;
 const char* rt_last_error(void);
 int rt_device_count(void);
 
-/* Copies the scene to the device (caller keeps ownership of every host array), builds the BVH with
- * the reference's split policy (source/BVH.h:100-161) on the host and uploads it. `device` is the
- * CUDA ordinal (one context per GPU). */
+/* Copies the scene to the device (caller keeps ownership of every host array) and builds the BVH with
+ * the reference's split policy (source/BVH.h:100-161): on the device from 8192 triangles (csrc/bvh_build.cu), on
+ * the host below that (csrc/host_build.cpp); both produce the same tree up to the order of equal keys.
+ * `device` is the CUDA ordinal (one context per GPU). */
 int rt_create(const rt_scene* scene, const rt_params* params, int device, rt_ctx** out);
 int rt_destroy(rt_ctx* ctx);
 int rt_set_params(rt_ctx* ctx, const rt_params* params); /* new size / N / mode / k / seed / shard */
@@ -202,7 +203,8 @@ int rt_set_photons(rt_ctx* ctx, const rt_photon* photons, int64_t n);
 int rt_build_photon_map(rt_ctx* ctx); /* emit all + set, as Renderer.cpp:209-213 */
 int rt_get_photons(rt_ctx* ctx, rt_photon* out, int64_t capacity, int64_t* count);
 /* kdtree::knearest (source/kdtree.h:87-107,180-195) for n query points (3 floats each): indices into
- * the kd-ordered node array (see rt_get_kdtree) in the reference's output order, k per query. */
+ * the kd-ordered node array (see rt_get_kdtree) in the reference's output order, k per query.
+ * With RT_FLAG_KNN_EXACT in the context's flags: the exact k nearest by (distance, index) instead. */
 int rt_knn(rt_ctx* ctx, const float* queries, int64_t n, int32_t k, int32_t* node_index);
 int rt_get_kdtree(rt_ctx* ctx, rt_photon* nodes, int32_t* left, int32_t* right, int32_t* root, int64_t capacity);
 
