@@ -147,7 +147,8 @@ int rt_set_params(rt_ctx* ctx, const rt_params* params); /* new size / N / mode 
 
 /* rt_composite on the device: sum_rgb_device / counter_device are full-frame device buffers (e.g. the result of
  * the NCCL reduce of every rank's rt_render_accumulate_device), rgb_inout a HOST buffer holding the background on
- * entry and the composite on exit.  Same arithmetic as rt_composite, bit for bit. */
+ * entry and the composite on exit.  Same arithmetic as rt_composite, bit for bit.  The kernel runs on the context's
+ * own stream: the caller must have synchronised with whatever produced the device buffers (e.g. the NCCL stream). */
 int rt_composite_device(rt_ctx* ctx, int32_t num_rays, const float* sum_rgb_device, const int32_t* counter_device,
                         float* rgb_inout);
 

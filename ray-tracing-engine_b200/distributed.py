@@ -110,11 +110,15 @@ def render_distributed(scene, num_rays, mode, num_photons=0, k=5, *, background,
     H, W = r.height, r.width
     sum_t = torch.zeros((H, W, 3), dtype=torch.float32, device=device)
     cnt_t = torch.zeros((H, W), dtype=torch.int32, device=device)
+    if sum_t.is_cuda:
+        torch.cuda.synchronize(sum_t.device)  # torch's fill kernels vs the context's own stream
     r.render_accumulate_device(sum_t.data_ptr(), cnt_t.data_ptr())
     reduce_frame(sum_t, cnt_t, 0, group)
     out = None
     if rank == 0:
         if sum_t.is_cuda:  # composite on the device, one D2H of the frame
+            # the reduce runs on NCCL's stream and the composite on the context's own: wait for the collective first
+            torch.cuda.synchronize(sum_t.device)
             out = r.composite_device(num_rays, sum_t.data_ptr(), cnt_t.data_ptr(), background)
         else:              # gloo tests: host tensors
             out = Renderer.composite(num_rays, sum_t.numpy(), cnt_t.numpy(), background)
