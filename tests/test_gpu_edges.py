@@ -232,3 +232,16 @@ def test_out_of_memory_retry_renders_the_same_frame(rt, monkeypatch):
     s, c = r.render_accumulate()
     assert beq(s, want_s) and (c == want_c).all()
     assert r.stats()["kernel_launches"] > 30, "the injected failure must have forced more than one batch"
+
+
+def test_two_gpu_distributed_render_matches_one_gpu(rt):
+    """scripts/dist_check.py under torchrun on 2 GPUs (NCCL): tile sharding bit-identical to the 1-GPU frame, sample
+    sharding within 1e-5, with and without a sharded + all-gathered photon map.  Skipped on a single-GPU box."""
+    import subprocess, sys
+    from conftest import ROOT
+    if rt.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29533",
+                          f"{ROOT}/scripts/dist_check.py"], capture_output=True, text=True, timeout=600)
+    assert "DIST_CHECK PASS" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
