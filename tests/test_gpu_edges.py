@@ -226,12 +226,14 @@ def test_out_of_memory_retry_renders_the_same_frame(rt, monkeypatch):
     render is retried (csrc/capi.cu).  RT_TEST_OOM_ONCE injects the failure and pretends 64 MB are free: the frame is
     rendered in many small batches and must be bit-identical (samples are accumulated in index order)."""
     scene = rt.Scene.load(scene_path("stock"))
-    want_s, want_c = rt.Renderer(scene, 6, 1, seed=8, width=160, height=120).render_accumulate()
+    r0 = rt.Renderer(scene, 6, 1, seed=8, width=160, height=120)
+    want_s, want_c = r0.render_accumulate()
+    one_batch = r0.stats()["kernel_launches"]
     monkeypatch.setenv("RT_TEST_OOM_ONCE", "1")
     r = rt.Renderer(scene, 6, 1, seed=8, width=160, height=120)
     s, c = r.render_accumulate()
     assert beq(s, want_s) and (c == want_c).all()
-    assert r.stats()["kernel_launches"] > 30, "the injected failure must have forced more than one batch"
+    assert r.stats()["kernel_launches"] > one_batch, "the injected failure must have forced more than one batch"
 
 
 def test_two_gpu_distributed_render_matches_one_gpu(rt):
