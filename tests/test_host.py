@@ -198,6 +198,11 @@ def test_cli_banner_and_errors(tmp_path):
     assert "Mode: Ray tracing" in r.stdout and "Photon map ON with 100 photons. Number of searched neighbours equals 3" in r.stdout
     assert "width: 380, height: 270" in r.stdout and "Output image filename: output.ppm" in r.stdout
     assert r.returncode == 1 and "Error Loading OFF file: Error loading OFF file: /nonexistent/cube_tri.off" in r.stderr
+    # the additive options parse (and leave the reference's banner alone); without a GPU the run then stops in rt_create
+    r = subprocess.run([exe, "-update", "4", "-p6", "1", "-knn", "exact", "-seed", "7", "-subdiv", "0", "-device", "0",
+                        "-brute", "0", "-meshdir", "/nonexistent"], capture_output=True, text=True, cwd=tmp_path)
+    assert "Mode: Ray tracing" in r.stdout and "Photon map OFF" in r.stdout and "Unknown argument" not in r.stderr
+    assert r.returncode == 1 and "cube_tri.off" in r.stderr
 
 
 # ----------------------------------------------------------------------------- host BVH builder
