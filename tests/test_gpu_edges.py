@@ -247,3 +247,24 @@ def test_two_gpu_distributed_render_matches_one_gpu(rt):
                           "--master-addr", "127.0.0.1", "--master-port", "29533",
                           f"{ROOT}/scripts/dist_check.py"], capture_output=True, text=True, timeout=600)
     assert "DIST_CHECK PASS" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+def test_python_cli_writes_the_same_file_as_the_cxx_cli(rt, tmp_path):
+    """`python -m ray_tracing_engine_b200.render_cli` (the multi-GPU front end, here on one GPU) and `bin/RayTracer`
+    write byte-identical PPMs for the same command line."""
+    import os, subprocess, sys
+    from conftest import ROOT
+    sys.path.insert(0, ROOT)
+    from bench import materialize_meshes
+    exe = os.path.join(ROOT, "ray-tracing-engine_b200", "bin", "RayTracer")
+    if not os.path.exists(exe):
+        pytest.skip("CLI not built")
+    mdir = materialize_meshes(str(tmp_path / "meshes"))
+    args = ["-width", "96", "-height", "64", "-m", "1", "-N", "3", "-p", "2000", "-k", "4", "-meshdir", mdir, "-seed", "5"]
+    a = subprocess.run([exe] + args + ["-o", "a.ppm"], capture_output=True, text=True, cwd=tmp_path)
+    assert a.returncode == 0, a.stderr[-1000:]
+    env = dict(os.environ, PYTHONPATH=ROOT)
+    b = subprocess.run([sys.executable, "-m", "ray_tracing_engine_b200.render_cli"] + args + ["-o", "b.ppm"],
+                       capture_output=True, text=True, cwd=tmp_path, env=env)
+    assert b.returncode == 0, b.stderr[-1000:]
+    assert open(tmp_path / "a.ppm", "rb").read() == open(tmp_path / "b.ppm", "rb").read()

@@ -54,7 +54,7 @@ def test_no_cpu_fallback():
         rt.Renderer(scene, 1, 0)
     assert e.value.code == _capi.RT_ERR_NO_DEVICE
     src = "".join(open(os.path.join(ROOT, "ray-tracing-engine_b200", f)).read()
-                  for f in ("__init__.py", "_capi.py", "distributed.py"))
+                  for f in ("__init__.py", "_capi.py", "distributed.py", "render_cli.py"))
     assert "oracle" not in re.sub(r'""".*?"""', "", src, flags=re.S).replace("# ", ""), \
         "the product package must not import the oracle"
     out = subprocess.run(["ldd", _capi.LIB_PATH], capture_output=True, text=True).stdout
@@ -203,6 +203,19 @@ def test_cli_banner_and_errors(tmp_path):
                         "-brute", "0", "-meshdir", "/nonexistent"], capture_output=True, text=True, cwd=tmp_path)
     assert "Mode: Ray tracing" in r.stdout and "Photon map OFF" in r.stdout and "Unknown argument" not in r.stderr
     assert r.returncode == 1 and "cube_tri.off" in r.stderr
+
+
+def test_multi_gpu_cli_parses_the_reference_flags():
+    from ray_tracing_engine_b200 import render_cli
+    a = render_cli.parse(["-w", "420", "-height", "300", "-n", "8", "-m", "7", "-p", "100", "-k", "3", "-o", "x.ppm"])
+    assert (a["width"], a["height"], a["numRays"], a["mode"], a["numPhotons"], a["k"], a["output"]) == \
+        (420, 300, 8, 0, 100, 3, "x.ppm")           # an invalid mode falls back to ray tracing (CommandLine.h:84-87)
+    d = render_cli.parse([])
+    assert (d["width"], d["height"], d["numRays"], d["mode"], d["k"], d["output"]) == (380, 270, 16, 0, 5, "output.ppm")
+    for bad, msg in ((["-bogus", "1"], "Unknown argument <-bogus>"), (["-width"], "Missing argument")):
+        with pytest.raises(SystemExit) as e:
+            render_cli.parse(bad)
+        assert msg in str(e.value)
 
 
 # ----------------------------------------------------------------------------- host BVH builder
