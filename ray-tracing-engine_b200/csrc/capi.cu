@@ -6,6 +6,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <cfloat>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -378,7 +379,11 @@ void parallel_ranges(int64_t n, F fn) {
 // largest |coordinate| of any vertex, light or the camera: scales the BVH padding (host_build.h)
 float scene_extent(const rt_scene* s) {
   float extent = 0.f;
-  for (int64_t i = 0; i < 3 * (int64_t)s->num_vertices; i++) extent = std::max(extent, std::fabs(s->positions[i]));
+  for (int64_t i = 0; i < 3 * (int64_t)s->num_vertices; i++) {
+    const float a = std::fabs(s->positions[i]);
+    if (!(a <= FLT_MAX)) return INFINITY;  // NaN or inf: std::max would silently skip a NaN
+    extent = std::max(extent, a);
+  }
   for (int l = 0; l < s->num_lights; l++)
     for (int a = 0; a < 3; a++) extent = std::max(extent, std::fabs(s->lights[l].position[a]) + s->lights[l].side);
   for (int a = 0; a < 3; a++) extent = std::max(extent, std::fabs(s->camera.position[a]));

@@ -268,3 +268,16 @@ def test_python_cli_writes_the_same_file_as_the_cxx_cli(rt, tmp_path):
                        capture_output=True, text=True, cwd=tmp_path, env=env)
     assert b.returncode == 0, b.stderr[-1000:]
     assert open(tmp_path / "a.ppm", "rb").read() == open(tmp_path / "b.ppm", "rb").read()
+
+
+def test_non_finite_vertices_are_rejected(rt):
+    """A NaN or infinite coordinate would poison every box of the BVH; rt_create refuses the scene."""
+    stock = rt.Scene.load(scene_path("stock"))
+    for bad in (np.nan, np.inf, -np.inf, 3e8):
+        pos = stock.pos.copy()
+        pos[5, 1] = bad
+        scene = rt.Scene(pos, stock.nrm, stock.tri, stock.mesh_tri_off, stock.mesh_vtx_off, stock.mats, stock.lights,
+                         stock.cam, stock.w, stock.h, stock.lights_ctor)
+        with pytest.raises(rt.RtError) as e:
+            rt.Renderer(scene, 1, 0)
+        assert e.value.code == -1 and "finite" in str(e.value)
