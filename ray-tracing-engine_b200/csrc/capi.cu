@@ -184,6 +184,17 @@ int ensure_pix_map(rt_ctx* c) {
   return RT_OK;
 }
 
+// which restatement of kdtree::knearest runs (kernels.h RenderArgs::knn_exact): the ascending array wins for small k
+// (cfg3, k = 10: 71 ms per frame against 78 with the heap), the heap for large k (cfg4, k = 50: 3.5 ms against 6.9);
+// measured crossover at k ~ 12 (scripts/knn_k_sweep.py)
+int knn_flavour_k(const rt_params& p, int k) {
+  if (p.flags & RT_FLAG_KNN_EXACT) return 1;
+  const char* e = getenv("RT_KNN_HEAP_FROM_K");  // read per call: the tests switch it
+  const int heap_from = e ? atoi(e) : 12;
+  return k >= heap_from ? -1 : 0;
+}
+int knn_flavour(const rt_params& p) { return knn_flavour_k(p, p.k); }
+
 // stack entries a traversal can need: the whole tree from node 0 (k_emit), or the root list plus one mesh's tree
 int trace_stack_depth(const rt_ctx* c) {
   return std::max(std::max(c->bvh.depth, c->scene.num_roots > 0 ? c->bvh.mesh_depth + c->scene.num_roots : 0), 1);
@@ -261,7 +272,7 @@ void fill_args(rt_ctx* c, RenderArgs& a, const int* pix_map, int npix, bool use_
   a.mode = p.mode == 1 ? 1 : 0;                // CommandLine.h:84-87: anything else is ray tracing
   a.photon = use_photons ? 1 : 0;
   a.k = p.k;
-  a.knn_exact = (p.flags & RT_FLAG_KNN_EXACT) ? 1 : 0;
+  a.knn_exact = knn_flavour(p);
   a.kd_frames = c->kd_height + 1;
   a.num_sms = c->num_sms;
   a.num_photons = p.num_photons;
@@ -1145,7 +1156,7 @@ int rt_knn(rt_ctx* c, const float* queries, int64_t n, int32_t k, int32_t* node_
   if (e == cudaSuccess) e = d_idx.ensure((size_t)n * k);
   if (e == cudaSuccess) e = cudaMemcpy(d_q.p, queries, sizeof(float) * 3 * (size_t)n, cudaMemcpyHostToDevice);
   if (e == cudaSuccess) {
-    launch_knn(c->scene, d_q.p, n, k, c->kd_height + 1, (c->params.flags & RT_FLAG_KNN_EXACT) ? 1 : 0, d_idx.p,
+    launch_knn(c->scene, d_q.p, n, k, c->kd_height + 1, knn_flavour_k(c->params, k), d_idx.p,
                c->d_counters.p, c->stream);
     c->stats.kernel_launches++;
     e = cudaStreamSynchronize(c->stream);

@@ -660,8 +660,10 @@ __device__ __noinline__ void knn_exact_redo(const DScene& S, float3 q, int k, un
 
 RT_DI float3 shade_photon(const DScene& S, float3 dir, float3 n, float3 P, const DMaterial& m, int k, int num_photons,
                           int exact, unsigned long long* sc, int* kst, unsigned long long& visits) {
-  if (exact)
+  if (exact > 0)
     kd_knearest_exact(S, P, k, sc, kst, kBlock, visits);
+  else if (exact < 0)  // large k: libstdc++'s heap restated (log k moves per insertion, ties for free)
+    kd_knearest_heap(S, P, k, sc, kst, kBlock, visits);
   else if (kd_knearest_sorted(S, P, k, sc, kst, kBlock, visits))
     knn_exact_redo(S, P, k, sc, kBlock);
   float r = kd_dist_of(sc[(k - 1) * kBlock]);  // farthest of the k (candidates are in ascending distance)
@@ -952,8 +954,10 @@ __global__ void __launch_bounds__(kBlock) k_knn(const DScene S, const float* __r
   unsigned long long* sc = s_knn + threadIdx.x;
   unsigned long long visits = 0;
   const float3 q = f3(q3[3 * i], q3[3 * i + 1], q3[3 * i + 2]);
-  if (exact)
+  if (exact > 0)
     kd_knearest_exact(S, q, k, sc, (int*)(s_knn + k * kBlock) + threadIdx.x, kBlock, visits);
+  else if (exact < 0)
+    kd_knearest_heap(S, q, k, sc, (int*)(s_knn + k * kBlock) + threadIdx.x, kBlock, visits);
   else if (kd_knearest_sorted(S, q, k, sc, (int*)(s_knn + k * kBlock) + threadIdx.x, kBlock, visits))
     knn_exact_redo(S, q, k, sc, kBlock);
   for (int j = 0; j < k; j++) node_index[i * k + j] = kd_index_of(sc[j * kBlock]);

@@ -33,7 +33,8 @@ struct RenderArgs {
   int mode;         // 0 ray, 1 path
   int photon;       // 1: gather from the photon map instead of direct lighting
   int k;            // neighbours
-  int knn_exact;    // RT_FLAG_KNN_EXACT
+  int knn_exact;    // k-NN flavour: 1 = RT_FLAG_KNN_EXACT (canonical exact), 0 = reference search with the ascending
+                    // candidate array (small k), -1 = reference search with libstdc++'s heap restated (large k)
   int kd_frames;    // kd-tree height + 1: stack frames per thread of kd_knearest_sorted
   int num_sms;      // multiprocessors of the device (grid sizing of the grid-stride kernels)
   int num_photons;  // REQUESTED photon count (Renderer.cpp:99)

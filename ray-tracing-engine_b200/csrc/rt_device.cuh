@@ -714,6 +714,128 @@ RT_DI bool kd_knearest_sorted(const DScene& S, float3 q, int k, unsigned long lo
 }
 
 // ------------------------------------------------------------------------------------------------
+// kd_knearest_heap: the same single-loop traversal with the candidates kept as libstdc++'s own max-heap (the element
+// moves of make_heap / pop_heap / push_heap / sort_heap restated literally, std::__adjust_heap and std::__push_heap)
+// over packed words in shared memory.  A new candidate is usually small, so the eviction costs one sift-down of
+// ~log2(k) levels and the insertion stops at the leaf, against ~0.6 k shifts in the ascending array; ties need no
+// special case because the moves ARE the reference's.  Selected with -DRT_KNN_HEAP=1 (see profiles/r1_tuning.md).
+// ------------------------------------------------------------------------------------------------
+struct KdHeapP {
+  unsigned long long* a;
+  int hs;
+  RT_DI unsigned long long get(int j) const { return a[j * hs]; }
+  RT_DI void set(int j, unsigned long long w) { a[j * hs] = w; }
+  RT_DI static bool less(unsigned long long x, unsigned long long y) { return (unsigned)(x >> 32) < (unsigned)(y >> 32); }
+  RT_DI void push_up(int hole, int top, unsigned long long v) {  // std::__push_heap
+    int parent = (hole - 1) / 2;
+    while (hole > top) {
+      const unsigned long long pw = get(parent);
+      if (!less(pw, v)) break;
+      set(hole, pw);
+      hole = parent;
+      parent = (hole - 1) / 2;
+    }
+    set(hole, v);
+  }
+  RT_DI void adjust(int hole, int len, unsigned long long v) {  // std::__adjust_heap
+    const int top = hole;
+    int second = hole;
+    while (second < (len - 1) / 2) {
+      second = 2 * (second + 1);
+      unsigned long long ws = get(second);
+      const unsigned long long wl = get(second - 1);
+      if (less(ws, wl)) {
+        second--;
+        ws = wl;
+      }
+      set(hole, ws);
+      hole = second;
+    }
+    if ((len & 1) == 0 && second == (len - 2) / 2) {
+      second = 2 * (second + 1);
+      set(hole, get(second - 1));
+      hole = second - 1;
+    }
+    push_up(hole, top, v);
+  }
+  RT_DI void make(int len) {  // std::make_heap
+    if (len < 2) return;
+    for (int parent = (len - 2) / 2;; parent--) {
+      adjust(parent, len, get(parent));
+      if (parent == 0) return;
+    }
+  }
+  RT_DI void pop(int len) {  // std::pop_heap: the largest goes to slot len-1
+    if (len > 1) {
+      const unsigned long long v = get(len - 1);
+      set(len - 1, get(0));
+      adjust(0, len - 1, v);
+    }
+  }
+  RT_DI void sort(int len) {  // std::sort_heap
+    while (len > 1) {
+      pop(len);
+      len--;
+    }
+  }
+};
+RT_DI void kd_knearest_heap(const DScene& S, float3 q, int k, unsigned long long* sc, int* kst, int ks,
+                            unsigned long long& visits) {
+  KdHeapP H{sc, ks};
+  for (int j = 0; j < k; j++) H.set(j, kd_pack(v_dist(f3(__ldg(S.kd_pos + j)), q), j));  // kdtree.h:186
+  H.make(k);
+  float best = kd_dist_of(H.get(0));  // m_bestdist
+  int sp = 0, b = 0, e = S.kd_count, axis = 0;
+  unsigned nv = 0;
+  while (e > b) {
+    const int n = b + (e - b) / 2;
+    nv++;
+    const float4 p = __ldg(S.kd_pos + n);
+    const float dnode = v_dist(f3(p), q);
+    if (dnode < best) {  // kdtree.h:92-99
+      H.pop(k);
+      best = kd_dist_of(H.get(0));  // the new top BEFORE the insertion (for k == 1: the evicted candidate itself)
+      H.push_up(k - 1, 0, kd_pack(dnode, n));
+    }
+    int nb = b, ne = b;
+    if (best != 0.f) {
+      float pa = p.x, qa = q.x;
+      if (axis == 1) pa = p.y, qa = q.y;
+      if (axis == 2) pa = p.z, qa = q.z;
+      const float dx = __fsub_rn(pa, qa);
+      const bool left_near = dx > 0.f;
+      nb = left_near ? b : n + 1;
+      ne = left_near ? n : e;
+      const int fb = left_near ? n + 1 : b, fe = left_near ? e : n;
+      axis = axis == 2 ? 0 : axis + 1;
+      if (fe > fb) {
+        const float t_sq = __double2float_rd(__dmul_rn((double)dx, (double)dx));
+        const float t_pl = __fmul_rn(fabsf(dx), 0.9999995f);
+        const float thr = fmaxf(t_sq, t_pl);
+        if (best > thr || k == 1) {
+          kst[(3 * sp) * ks] = fb;
+          kst[(3 * sp + 1) * ks] = fe | (axis << 28);
+          kst[(3 * sp + 2) * ks] = __float_as_int(thr);
+          sp++;
+        }
+      }
+    }
+    b = nb;
+    e = ne;
+    while (e <= b && sp > 0) {
+      sp--;
+      if (best <= __int_as_float(kst[(3 * sp + 2) * ks])) continue;
+      const int fe = kst[(3 * sp + 1) * ks];
+      b = kst[(3 * sp) * ks];
+      axis = (fe >> 28) & 3;
+      e = fe & 0x0fffffff;
+    }
+  }
+  H.sort(k);
+  visits += nv;
+}
+
+// ------------------------------------------------------------------------------------------------
 // kd_knearest_exact (RT_FLAG_KNN_EXACT; off by default because it changes 0.5-2.8 % of the
 // queries against the reference): the k photons with the smallest (distance, array index), in that order -- a
 // canonical exact k-NN on the same tree.  No seeds, no `best == 0` shortcut, and the bound is on the current k-th

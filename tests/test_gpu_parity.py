@@ -236,6 +236,20 @@ def test_kdtree_and_knn_match_reference(rt, gold):
 
 
 
+@pytest.mark.parametrize("heap_from", ["0", "1000"])
+def test_both_knn_restatements_match_the_reference(rt, gold, monkeypatch, heap_from):
+    """kdtree::knearest has two device restatements -- an ascending candidate array with a tie fallback (small k) and
+    libstdc++'s heap moves restated literally (k >= 12): each must reproduce the golden results for every k."""
+    monkeypatch.setenv("RT_KNN_HEAP_FROM_K", heap_from)
+    g = gold("photons.npz")
+    r = make_renderer(rt, "stock")
+    r.set(num_photons=3000, k=10)
+    r.set_photons(g["list"])
+    nodes = r.kdtree()[0]
+    for k in (1, 5, 10, 50):
+        assert beq(nodes[r.knearest(g["queries"], k)][:, :, :3], g[f"knn_{k}"]), (heap_from, k)
+
+
 def test_knn_parity_at_scale(rt, O):
     """The SIMT k-NN (sorted candidates + tie fallback) against kdtree::knearest restated on the CPU, on photon
     maps the GPU emitted: 35 k photons / k=10 and 357 k photons / k=50, queries near and exactly on photons
