@@ -26,7 +26,7 @@ extern "C" {
 
 typedef enum rt_status {
   RT_OK = 0,
-  RT_ERR_INVALID = -1,      /* bad argument (null pointer, negative count, k > 64, ...)               */
+  RT_ERR_INVALID = -1,      /* bad argument (null pointer, negative count, k > RT_MAX_K, ...)         */
   RT_ERR_NO_DEVICE = -2,    /* no usable CUDA device / driver                                         */
   RT_ERR_CUDA = -3,         /* a CUDA runtime call or kernel failed; see rt_last_error()              */
   RT_ERR_EMPTY_TREE = -4,   /* kdtree.h:181  "tree is empty"                                          */
@@ -91,7 +91,11 @@ typedef struct rt_params {
   int32_t flags;        /* RT_FLAG_* */
 } rt_params;
 
-#define RT_MAX_K 64
+/* kdtree::knearest accepts any k <= number of nodes (source/kdtree.h:180-183) and Scene::lightsources() any number
+ * of lights (source/Scene.h:14-26, source/Renderer.cpp:49); the limits below only bound index arithmetic.  Up to
+ * k = 64 the candidates of a query live in shared memory, beyond that in a global scratch (slower, same results). */
+#define RT_MAX_K 4096
+#define RT_MAX_LIGHTS 4096
 #define RT_FLAG_BRUTE_FORCE 1 /* trace with the O(T) scan instead of the BVH (parity hook) */
 #define RT_FLAG_KNN_EXACT 2   /* gather the canonical exact k nearest photons (by distance, then array index) instead of
                                  reproducing kdtree::knearest's two quirks: fewer node visits, but 0.5-2.8 % of the
@@ -114,6 +118,19 @@ typedef struct rt_photon {
   float weight;
 } rt_photon;
 
+enum {
+  RT_KERNEL_RAYGEN = 0,        /* k_raygen                                                      */
+  RT_KERNEL_TRACE_NEAREST = 1, /* k_trace_sp8u3<nearest>                                        */
+  RT_KERNEL_SORT = 2,          /* k_sort_count / k_sort_scan / k_sort_scatter                   */
+  RT_KERNEL_SHADE = 3,         /* k_shade (direct lighting, or the k-nearest-photon gather)     */
+  RT_KERNEL_TRACE_ANY = 4,     /* k_trace_sp8u3<any-hit> over the shadow rays                   */
+  RT_KERNEL_COMBINE = 5,       /* k_combine                                                     */
+  RT_KERNEL_RESOLVE = 6,       /* k_resolve                                                     */
+  RT_KERNEL_EMIT = 7,          /* k_emit (photon emission)                                      */
+  RT_KERNEL_OTHER = 8,         /* scatter / composite                                           */
+  RT_NUM_KERNEL_CLASSES = 9
+};
+
 typedef struct rt_stats {
   uint64_t rays;           /* logical RayTracer::rayTrace invocations (primary+bounce+shadow+photon) */
   uint64_t primary_rays, bounce_rays, shadow_rays, photon_rays;
@@ -130,12 +147,19 @@ typedef struct rt_stats {
   double kd_build_ms;      /* host wall time of the last kd-tree build (rt_set_photons)              */
   uint64_t kd_visits;      /* kd-tree nodes visited by the k-NN queries: kdtree::visited() summed, minus
                               the visits the exact plane-distance bound skips                        */
+  /* CUDA-event time (ms) and launch count of every kernel class in the LAST rt_render* / rt_emit_photons call
+   * (classes: RT_KERNEL_*); the events sit on the launching stream around each launch. */
+  double kernel_ms[RT_NUM_KERNEL_CLASSES];
+  uint64_t kernel_count[RT_NUM_KERNEL_CLASSES];
 } rt_stats;
 
 typedef struct rt_ctx rt_ctx;
 
 const char* rt_last_error(void);
 int rt_device_count(void);
+/* sizeof of {rt_material, rt_light, rt_camera, rt_scene, rt_params, rt_ray, rt_hit, rt_photon, rt_stats} as this
+ * library was compiled (pure host function): lets a foreign-language binding verify its struct mirrors. */
+int rt_abi_sizes(int32_t* out, int32_t capacity);
 
 /* Copies the scene to the device (caller keeps ownership of every host array) and builds the BVH with
  * the reference's split policy (source/BVH.h:100-161): on the device from 8192 triangles (csrc/bvh_build.cu), on
@@ -175,6 +199,11 @@ int rt_render_progressive(rt_ctx* ctx, float* rgb_inout, int32_t every, rt_progr
  * torch tensors) and leaves the result there for an NCCL reduce. */
 int rt_render_accumulate(rt_ctx* ctx, float* sum_rgb, int32_t* counter);
 int rt_render_accumulate_device(rt_ctx* ctx, float* sum_rgb_device, int32_t* counter_device);
+/* The same as ONE buffer of W*H float4 {sum_r, sum_g, sum_b, counter} (device pointer, 16-byte aligned), so that a
+ * multi-GPU frame needs a single sum-reduce: the counter is exact as a binary32 for num_rays < 2^24.
+ * rt_composite_packed_device is rt_composite_device on that layout. */
+int rt_render_accumulate_packed_device(rt_ctx* ctx, float* sum_rgbn_device);
+int rt_composite_packed_device(rt_ctx* ctx, int32_t num_rays, const float* sum_rgbn_device, float* rgb_inout);
 /* `saveImage = update/N + background*(N-counter)/N` (source/Renderer.cpp:262-265) on the host. */
 int rt_composite(int32_t width, int32_t height, int32_t num_rays, const float* sum_rgb, const int32_t* counter,
                  float* rgb_inout);

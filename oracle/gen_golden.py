@@ -232,6 +232,115 @@ def stock_binary():
                 f"-ffp-contract=off, stock minstd_rand0 engine)\n")
 
 
+# ------------------------------------------------------------------------------------------------
+# Round 2: the configs the north_star target names, at their own sample count (N = 128), and an
+# INDEPENDENT converged mean from the reference's own serial minstd_rand0 engine.
+# ------------------------------------------------------------------------------------------------
+def sample_hash16(samples):
+    """16-bit fingerprint of every clamped sample colour (3 binary32 words): lets a test count bit-identical
+    samples without storing 12 bytes per sample.  Restated in tests/test_gpu_parity.py."""
+    b = np.ascontiguousarray(samples, np.float32).view(np.uint32).astype(np.uint64)
+    h = (b[..., 0] * np.uint64(0x9E3779B1) ^ b[..., 1]) * np.uint64(0x85EBCA77) ^ b[..., 2]
+    h ^= h >> np.uint64(29)
+    h = (h * np.uint64(0xC2B2AE3D)) & np.uint64(0xFFFFFFFFFFFF)
+    return ((h >> np.uint64(24)) & np.uint64(0xFFFF)).astype(np.uint16)
+
+
+def _band_worker(args):
+    off, N, mode, photons, k, plist, window, rows = args
+    ref = O.RefOracle()
+    ref.create_scene(420, 420, custom_off=off)
+    pm = ref.photon_map_from_list(plist) if plist is not None else None
+    x0, _, x1, _ = window
+    r = ref.render(N, mode, SEED, num_photons=photons, k=k, photon_map=pm, window=(x0, rows[0], x1, rows[1]),
+                   want_samples=True)
+    return dict(sum_rgb=r["sum_rgb"], counter=r["counter"], hash16=sample_hash16(r["samples"]),
+                found=r["found"].astype(np.int8))
+
+
+def render_window_parallel(off, N, mode, window, photons=0, k=0, plist=None, procs=8):
+    import multiprocessing as mp
+    x0, y0, x1, y1 = window
+    rows = y1 - y0
+    bands = [(y0 + rows * i // procs, y0 + rows * (i + 1) // procs) for i in range(procs)]
+    jobs = [(off, N, mode, photons, k, plist, window, b) for b in bands if b[1] > b[0]]
+    with mp.get_context("fork").Pool(len(jobs)) as pool:
+        parts = pool.map(_band_worker, jobs)
+    return dict(sum_rgb=np.concatenate([p["sum_rgb"] for p in parts], 0),
+                counter=np.concatenate([p["counter"] for p in parts], 0),
+                hash16=np.concatenate([p["hash16"] for p in parts], 1),
+                found=np.concatenate([p["found"] for p in parts], 1))
+
+
+def headline_windows():
+    """BASELINE configs[1] and [2] at their own N: example.off scene, -m 1 -N 128, a 64x64 window, every sample
+    (sum, counter, primary-hit flags and a 16-bit fingerprint per sample), without and with a 50 000-photon map
+    emitted by the reference (the shared list is committed with the golden)."""
+    off = f"{MESHES}/example.off"
+    win = (170, 150, 234, 214)
+    t = time.time()
+    r = render_window_parallel(off, 128, 1, win)
+    log("headline cfg2 window", f"{time.time() - t:.0f}s")
+    save("render_example_m1_N128_win.npz", window=np.array(win), N=np.array([128]), sum_rgb=r["sum_rgb"],
+         counter=r["counter"].astype(np.int16), hash16=r["hash16"], found=np.packbits(r["found"].astype(bool)))
+    ref = O.RefOracle()
+    ref.create_scene(420, 420, custom_off=off)
+    t = time.time()
+    pm = ref.photon_map_create(50000, SEED)
+    plist, hist = pm.get()
+    log("example-scene photon emission", len(plist), "stored", f"{time.time() - t:.0f}s")
+    t = time.time()
+    r = render_window_parallel(off, 128, 1, win, photons=50000, k=10, plist=plist)
+    log("headline cfg3 window", f"{time.time() - t:.0f}s")
+    save("render_example_m1_N128_p50000_k10_win.npz", window=np.array(win), N=np.array([128]), photons=plist,
+         depth_hist=hist, sum_rgb=r["sum_rgb"], counter=r["counter"].astype(np.int16), hash16=r["hash16"],
+         found=np.packbits(r["found"].astype(bool)))
+
+
+def _stock_mean_worker(args):
+    seed, W, H, N = args
+    ref = O.RefOracle(stock_rng=True)
+    ref.create_scene(W, H)
+    ref.lib.ref_reseed(seed)
+    acc = np.zeros((H, W, 3), np.float64)
+    acc2 = np.zeros((H, W, 3), np.float64)
+    cnt = np.zeros((H, W), np.int64)
+    chunk = 64
+    for s0 in range(0, N, chunk):  # sample ranges in order: the serial engine is consumed exactly as one N-sample run
+        r = ref.render(N, 1, 0, samples=(s0, min(N, s0 + chunk)), want_samples=True)
+        smp = r["samples"].astype(np.float64)
+        acc += smp.sum(0)
+        acc2 += (smp * smp).sum(0)
+        cnt += r["counter"]
+    return acc, acc2, cnt
+
+
+def converged_mean():
+    """SURVEY.md section 4 test 5: the reference's converged mean from its OWN engine (std::default_random_engine =
+    minstd_rand0 consumed serially, LightSource.h:6) -- statistically independent of the counter-based streams the
+    GPU and the shared-RNG oracle use.  Stock scene, 105x105, -m 1, N = 2048, 3 seeds: per-pixel mean and per-pixel
+    sample variance (float64 accumulation of the clamped sample colours)."""
+    import multiprocessing as mp
+    W = H = 105
+    N, seeds = 2048, (1, 2, 3)
+    t = time.time()
+    with mp.get_context("fork").Pool(len(seeds)) as pool:
+        parts = pool.map(_stock_mean_worker, [(s, W, H, N) for s in seeds])
+    n = N * len(seeds)
+    mean_seed = np.stack([p[0] / N for p in parts])
+    acc = sum(p[0] for p in parts)
+    acc2 = sum(p[1] for p in parts)
+    mean = acc / n
+    var = (acc2 / n - mean * mean) * n / (n - 1)
+    hitfrac = sum(p[2] for p in parts) / n
+    seed_rmse = [float(np.sqrt(np.mean((mean_seed[i] - mean_seed[j]) ** 2))) for i, j in ((0, 1), (0, 2), (1, 2))]
+    log("converged mean", f"{time.time() - t:.0f}s", "seed-to-seed RMSE of the N=2048 means", seed_rmse,
+        "sqrt(2*mean var/N) =", float(np.sqrt(2 * var.mean() / N)))
+    save("converged_stock_m1_105.npz", W=np.array([W]), N=np.array([N]), seeds=np.array(seeds),
+         mean=mean.astype(np.float32), var=var.astype(np.float32), hit_fraction=hitfrac.astype(np.float32),
+         mean_per_seed=mean_seed.astype(np.float32), seed_rmse=np.array(seed_rmse))
+
+
 ALL = dict(scenes=scenes, rng=rng, sampling=sampling, bsdf=bsdf, trace=trace, photons=photons,
            render_light=render_light, stock_binary=stock_binary)
 
@@ -243,6 +352,6 @@ if __name__ == "__main__":
     O.build(ref=True)
     names = [n for n in a.only.split(",") if n] or list(ALL)
     for n in names:
-        (ALL | dict(render_heavy=render_heavy))[n]()
+        (ALL | dict(render_heavy=render_heavy, headline_windows=headline_windows, converged_mean=converged_mean))[n]()
     if a.heavy and "render_heavy" not in names:
         render_heavy()

@@ -305,6 +305,17 @@ class Renderer:
         """Same, into device buffers (e.g. torch tensors' data_ptr()) on this context's GPU."""
         _capi.check(self.lib.rt_render_accumulate_device(self._ctx, C.c_void_p(sum_rgb_ptr), C.c_void_p(counter_ptr)))
 
+    def render_accumulate_packed_device(self, sum_rgbn_ptr: int):
+        """The sums and the counter as one [H,W,4] float32 device buffer (a single reduce across GPUs)."""
+        _capi.check(self.lib.rt_render_accumulate_packed_device(self._ctx, C.c_void_p(sum_rgbn_ptr)))
+
+    def composite_packed_device(self, num_rays, sum_rgbn_ptr: int, background):
+        """Renderer.cpp:262-265 on the packed DEVICE frame (after the multi-GPU reduce); returns [H,W,3]."""
+        out = np.ascontiguousarray(background, np.float32).copy()
+        _capi.check(self.lib.rt_composite_packed_device(self._ctx, int(num_rays), C.c_void_p(sum_rgbn_ptr),
+                                                        _capi.ptr(out)))
+        return out
+
     @staticmethod
     def composite(num_rays, sum_rgb, counter, background):
         """source/Renderer.cpp:262-265."""
@@ -428,7 +439,10 @@ class Renderer:
     def stats(self):
         s = rt_stats()
         _capi.check(self.lib.rt_get_stats(self._ctx, C.byref(s)))
-        return {name: getattr(s, name) for name, _ in rt_stats._fields_}
+        out = {name: getattr(s, name) for name, _ in rt_stats._fields_ if not name.startswith("kernel_")}
+        out["kernel_ms"] = {n: float(s.kernel_ms[i]) for i, n in enumerate(_capi.KERNEL_CLASSES)}
+        out["kernel_count"] = {n: int(s.kernel_count[i]) for i, n in enumerate(_capi.KERNEL_CLASSES)}
+        return out
 
     def reset_stats(self):
         _capi.check(self.lib.rt_reset_stats(self._ctx))

@@ -18,7 +18,9 @@ RT_OK = 0
 RT_ERR_INVALID, RT_ERR_NO_DEVICE, RT_ERR_CUDA, RT_ERR_EMPTY_TREE, RT_ERR_K_TOO_LARGE, RT_ERR_OOM = -1, -2, -3, -4, -5, -6
 RT_FLAG_BRUTE_FORCE = 1
 RT_FLAG_KNN_EXACT = 2
-RT_MAX_K = 64
+RT_MAX_K = 4096
+RT_MAX_LIGHTS = 4096
+KERNEL_CLASSES = ("raygen", "trace_nearest", "sort", "shade", "trace_any", "combine", "resolve", "emit", "other")
 
 
 class RtError(RuntimeError):
@@ -63,7 +65,8 @@ class rt_stats(C.Structure):
                 ("samples", C.c_uint64), ("kernel_launches", C.c_uint64), ("device_ms", C.c_double),
                 ("trace_ms", C.c_double), ("photon_ms", C.c_double), ("bvh_nodes", C.c_int32),
                 ("bvh_depth", C.c_int32), ("photons_stored", C.c_int64), ("create_ms", C.c_double),
-                ("bvh_build_ms", C.c_double), ("kd_build_ms", C.c_double), ("kd_visits", C.c_uint64)]
+                ("bvh_build_ms", C.c_double), ("kd_build_ms", C.c_double), ("kd_visits", C.c_uint64),
+                ("kernel_ms", C.c_double * len(KERNEL_CLASSES)), ("kernel_count", C.c_uint64 * len(KERNEL_CLASSES))]
 
 
 PROGRESS_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_float))
@@ -73,6 +76,7 @@ _vp, _i32, _i64 = C.c_void_p, C.c_int32, C.c_int64
 SYMBOLS = {
     "rt_last_error": (C.c_char_p, []),
     "rt_device_count": (C.c_int, []),
+    "rt_abi_sizes": (C.c_int, [_vp, _i32]),
     "rt_create": (C.c_int, [C.POINTER(rt_scene), C.POINTER(rt_params), C.c_int, C.POINTER(_vp)]),
     "rt_destroy": (C.c_int, [_vp]),
     "rt_set_params": (C.c_int, [_vp, C.POINTER(rt_params)]),
@@ -80,6 +84,8 @@ SYMBOLS = {
     "rt_render_progressive": (C.c_int, [_vp, _vp, _i32, _vp, _vp]),
     "rt_render_accumulate": (C.c_int, [_vp, _vp, _vp]),
     "rt_render_accumulate_device": (C.c_int, [_vp, _vp, _vp]),
+    "rt_render_accumulate_packed_device": (C.c_int, [_vp, _vp]),
+    "rt_composite_packed_device": (C.c_int, [_vp, _i32, _vp, _vp]),
     "rt_composite": (C.c_int, [_i32, _i32, _i32, _vp, _vp, _vp]),
     "rt_composite_device": (C.c_int, [_vp, _i32, _vp, _vp, _vp]),
     "rt_render_samples": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),

@@ -95,7 +95,11 @@ struct rt_ctx {
   int npix = 0;
   int pix_w = -1, pix_h = -1, pix_rank = -1, pix_count = -1, pix_tile = -1;
   DevBuf<float4> d_col0, d_col1, d_qo0, d_qo1, d_qd0, d_qd1, d_acc;
-  DevBuf<float4> d_hit, d_sh_o, d_sh_d, d_contrib;
+  DevBuf<float4> d_hit, d_hit_p, d_sh_d, d_contrib;
+  DevBuf<DLight> d_lights_ext;             // lights beyond the kMaxLights kept in kernel-parameter space
+  DevBuf<unsigned long long> d_knn_scratch;  // k-NN candidates of every resident thread when k > kKnnSharedMaxK
+  int knn_scratch_threads = 0;
+  int own_tri = 1;  // RT_OWN_TRI=0: shadow rays are not pre-tested against the triangle they start on
   DevBuf<unsigned char> d_occ;
   DevBuf<int> d_hit_path;
   DevBuf<unsigned int> d_perm, d_sort_hist;
@@ -109,8 +113,13 @@ struct rt_ctx {
   DevBuf<unsigned char> d_scratch;
   size_t auto_paths = 0;  // cached batch-size decision (paths per wavefront batch)
   bool oom_injected = false;  // RT_TEST_OOM_ONCE (tests only)
-  std::vector<cudaEvent_t> seg_events;  // pairs around every k_segment launch of the current render
-  size_t seg_events_used = 0;
+  // CUDA-event pairs around the kernel launches of the current render call, by kernel class
+  struct TimedSpan {
+    int cls;
+    cudaEvent_t e0, e1;
+  };
+  std::vector<TimedSpan> spans;
+  size_t spans_used = 0;
   rt_stats stats{};
 };
 
@@ -174,7 +183,10 @@ int ensure_pix_map(rt_ctx* c) {
     return RT_OK;
   const std::vector<int> map = cached_pix_map(p);
   CU(c->d_pix_map.ensure(map.size()));
-  if (!map.empty()) CU(cudaMemcpy(c->d_pix_map.p, map.data(), map.size() * sizeof(int), cudaMemcpyHostToDevice));
+  // stream-ordered allocation, copy and consumers share one stream; the source is pageable, so the call returns
+  // only once it has been staged (the vector may go away)
+  if (!map.empty())
+    CU(cudaMemcpyAsync(c->d_pix_map.p, map.data(), map.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
   c->npix = (int)map.size();
   c->pix_w = p.width;
   c->pix_h = p.height;
@@ -191,7 +203,7 @@ int knn_flavour_k(const rt_params& p, int k) {
   if (p.flags & RT_FLAG_KNN_EXACT) return 1;
   const char* e = getenv("RT_KNN_HEAP_FROM_K");  // read per call: the tests switch it
   const int heap_from = e ? atoi(e) : 12;
-  return k >= heap_from ? -1 : 0;
+  return (k >= heap_from || k > kMaxK) ? -1 : 0;  // the ascending array's tie fallback holds at most kMaxK candidates
 }
 int knn_flavour(const rt_params& p) { return knn_flavour_k(p, p.k); }
 
@@ -200,8 +212,10 @@ int trace_stack_depth(const rt_ctx* c) {
   return std::max(std::max(c->bvh.depth, c->scene.num_roots > 0 ? c->bvh.mesh_depth + c->scene.num_roots : 0), 1);
 }
 
-// bytes of wavefront state per path slot (ensure_work below)
-constexpr size_t kBytesPerPath = 16 * 2 + 32 * 2 + 16 + 3 * (32 + 16 + 1) + 4 + 32;
+// bytes of wavefront state per path slot (ensure_work below) with nl shadow slots per hit: colours 2 x 16, ray queues
+// 2 x 32, hit record 16, hit point 16, per shadow slot direction 16 + contribution 16 + occlusion 1, path id 4,
+// sort key 4, sorted payload 32
+size_t bytes_per_path(int nl) { return 16 * 2 + 32 * 2 + 16 + 16 + (size_t)std::max(nl, 1) * (16 + 16 + 1) + 4 + 4 + 32; }
 
 void release_work(rt_ctx* c) {
   c->d_col0.release();
@@ -212,7 +226,7 @@ void release_work(rt_ctx* c) {
   c->d_qd1.release();
   c->d_hit.release();
   c->d_hit_path.release();
-  c->d_sh_o.release();
+  c->d_hit_p.release();
   c->d_sh_d.release();
   c->d_contrib.release();
   c->d_occ.release();
@@ -220,14 +234,18 @@ void release_work(rt_ctx* c) {
   c->d_sorted.release();
 }
 
-int ensure_work(rt_ctx* c, size_t paths, bool path_mode) {
-  const size_t shadow = shadow_slots_for((unsigned)paths);
+// shadow slots per hit: one per light for direct lighting, one (the gathered contribution) with a photon map
+int shadow_lights(const rt_ctx* c, bool use_photons) { return use_photons ? 1 : c->L; }
+
+int ensure_work(rt_ctx* c, size_t paths, bool path_mode, int nl) {
+  const size_t shadow = std::max<size_t>(shadow_slots_for(paths, (unsigned)std::max(nl, 0)), 1);
+  if (shadow >= ((size_t)1 << 32)) return fail(RT_ERR_INVALID, "batch too large for the 32-bit shadow-ray queue");
   CU(c->d_col0.ensure(paths));
   CU(c->d_qo0.ensure(paths));
   CU(c->d_qd0.ensure(paths));
   CU(c->d_hit.ensure(paths));
   CU(c->d_hit_path.ensure(paths));
-  CU(c->d_sh_o.ensure(shadow));
+  CU(c->d_hit_p.ensure(paths));
   CU(c->d_sh_d.ensure(shadow));
   CU(c->d_contrib.ensure(shadow));
   CU(c->d_occ.ensure(shadow));
@@ -253,11 +271,20 @@ int validate_params(const rt_params* p) {
   if (p->num_photons < 0) return fail(RT_ERR_INVALID, "num_photons must be >= 0");
   if (p->num_photons > 0 && (p->k < 1 || p->k > RT_MAX_K))
     return fail(RT_ERR_INVALID, "k must be in [1, " + std::to_string(RT_MAX_K) + "] when a photon map is used");
+  if (p->num_photons >= (1 << 28)) return fail(RT_ERR_INVALID, "too many photons");
   if (p->shard_count > 1 && (p->shard_rank < 0 || p->shard_rank >= p->shard_count))
     return fail(RT_ERR_INVALID, "shard_rank out of range");
   if ((int64_t)p->width * p->height > (int64_t)1 << 30) return fail(RT_ERR_INVALID, "image too large");
   if (p->sample_first < 0 || (p->sample_count > 0 && p->sample_first + p->sample_count > p->num_rays))
     return fail(RT_ERR_INVALID, "sample range outside [0, num_rays)");
+  return RT_OK;
+}
+
+// k > kKnnSharedMaxK: the candidates of every resident thread of the k-NN shade kernel live in global memory
+int ensure_knn_scratch(rt_ctx* c, int k, int threads) {
+  if (k <= kKnnSharedMaxK) return RT_OK;
+  CU(c->d_knn_scratch.ensure((size_t)k * (size_t)threads));
+  c->knn_scratch_threads = threads;
   return RT_OK;
 }
 
@@ -288,8 +315,12 @@ void fill_args(rt_ctx* c, RenderArgs& a, const int* pix_map, int npix, bool use_
   a.ray_d[0] = c->d_qd0.p;
   a.ray_d[1] = c->d_qd1.p;
   a.hit = c->d_hit.p;
-  a.sh_o = c->d_sh_o.p;
+  a.nl = shadow_lights(c, use_photons);
+  a.own_tri = c->own_tri;
+  a.hit_p = c->d_hit_p.p;
   a.sh_d = c->d_sh_d.p;
+  a.knn_scratch = c->d_knn_scratch.p;
+  a.knn_scratch_stride = c->knn_scratch_threads;
   a.contrib = c->d_contrib.p;
   a.occ = c->d_occ.p;
   a.hit_path = c->d_hit_path.p;
@@ -304,6 +335,44 @@ void fill_args(rt_ctx* c, RenderArgs& a, const int* pix_map, int npix, bool use_
   a.counters = c->d_counters.p;
 }
 
+// CUDA-event pair around the launches of one kernel class (on the launching stream)
+int span_begin(rt_ctx* c, int cls) {
+  if (c->spans.size() <= c->spans_used) {
+    rt_ctx::TimedSpan sp{cls, nullptr, nullptr};
+    CU(cudaEventCreate(&sp.e0));
+    CU(cudaEventCreate(&sp.e1));
+    c->spans.push_back(sp);
+  }
+  c->spans[c->spans_used].cls = cls;
+  CU(cudaEventRecord(c->spans[c->spans_used].e0, c->stream));
+  return RT_OK;
+}
+int span_end(rt_ctx* c, int launches) {
+  CU(cudaEventRecord(c->spans[c->spans_used].e1, c->stream));
+  c->stats.kernel_count[c->spans[c->spans_used].cls] += (uint64_t)launches;
+  c->stats.kernel_launches += (uint64_t)launches;
+  c->spans_used++;
+  return RT_OK;
+}
+// after the stream has been synchronised: add the spans' times to the per-class totals of the call
+int collect_spans(rt_ctx* c) {
+  for (size_t i = 0; i < c->spans_used; i++) {
+    float t = 0.f;
+    CU(cudaEventElapsedTime(&t, c->spans[i].e0, c->spans[i].e1));
+    c->stats.kernel_ms[c->spans[i].cls] += t;
+  }
+  c->spans_used = 0;
+  c->stats.trace_ms = c->stats.kernel_ms[kKTraceNearest] + c->stats.kernel_ms[kKTraceAny];
+  return RT_OK;
+}
+void reset_call_timing(rt_ctx* c) {
+  for (int i = 0; i < kKNumClasses; i++) {
+    c->stats.kernel_ms[i] = 0.0;
+    c->stats.kernel_count[i] = 0;
+  }
+  c->spans_used = 0;
+}
+
 // one wavefront batch: samples [s0, s0+nsamp) of the pixels in pix_map
 int run_batch(rt_ctx* c, RenderArgs& a, int s0, int nsamp) {
   a.s0 = s0;
@@ -314,45 +383,32 @@ int run_batch(rt_ctx* c, RenderArgs& a, int s0, int nsamp) {
   if (grid < 1) grid = 1;
   const int grid_shade = (int)std::min<long long>((paths + kBlock - 1) / kBlock, (long long)c->num_sms * 8);
   CU(cudaMemsetAsync(c->d_qcount.p, 0, kQNum * sizeof(unsigned), c->stream));
-  auto mark = [&]() -> int {
-    while (c->seg_events.size() < c->seg_events_used + 1) {
-      cudaEvent_t e;
-      CU(cudaEventCreate(&e));
-      c->seg_events.push_back(e);
-    }
-    CU(cudaEventRecord(c->seg_events[c->seg_events_used++], c->stream));
-    return RT_OK;
-  };
   int rc;
-  launch_raygen(a, c->stream);
-  c->stats.kernel_launches++;
+#define SPAN(cls, launches, call)          \
+  do {                                     \
+    if ((rc = span_begin(c, cls))) return rc; \
+    call;                                  \
+    if ((rc = span_end(c, launches))) return rc; \
+  } while (0)
+  SPAN(kKRaygen, 1, launch_raygen(a, c->stream));
   const int nseg = a.mode == 1 ? 3 : 1;
   for (int seg = 0; seg < nseg; seg++) {
-    if ((rc = mark())) return rc;
-    launch_trace_nearest(a, seg, grid, c->stream);
-    if ((rc = mark())) return rc;
-    if ((seg > 0 || a.photon) && a.perm) {  // spatial order: shadow-ray coherence / k-NN traversal coherence
-      launch_sort_hits(a, seg, c->stream);
-      c->stats.kernel_launches += 3;
-    }
-    launch_shade(a, seg, std::max(grid_shade, 1), c->stream);
-    c->stats.kernel_launches += 2;
-    if (!a.photon) {
-      if ((rc = mark())) return rc;
-      launch_trace_any(a, seg, grid, c->stream);
-      if ((rc = mark())) return rc;
-      c->stats.kernel_launches++;
-    }
-    launch_combine(a, seg, std::max(grid_shade, 1), c->stream);
-    c->stats.kernel_launches++;
+    SPAN(kKTraceNearest, 1, launch_trace_nearest(a, seg, grid, c->stream));
+    if ((seg > 0 || a.photon) && a.perm)  // spatial order: shadow-ray coherence / k-NN traversal coherence
+      SPAN(kKSort, 3, launch_sort_hits(a, seg, c->stream));
+    SPAN(kKShade, 1, launch_shade(a, seg, std::max(grid_shade, 1), c->stream));
+    if (!a.photon && a.nl > 0) SPAN(kKTraceAny, 1, launch_trace_any(a, seg, grid, c->stream));
+    SPAN(kKCombine, 1, launch_combine(a, seg, std::max(grid_shade, 1), c->stream));
   }
+#undef SPAN
   CU(cudaGetLastError());
   return RT_OK;
 }
 
 int pull_counters(rt_ctx* c) {
   unsigned long long h[kCntNum];
-  CU(cudaMemcpy(h, c->d_counters.p, sizeof(h), cudaMemcpyDeviceToHost));
+  CU(cudaMemcpyAsync(h, c->d_counters.p, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
   rt_stats& s = c->stats;
   s.shadow_rays = h[kCntShadow];
   s.photon_rays = h[kCntPhotonRays];
@@ -416,15 +472,23 @@ int prepare_photons(rt_ctx* c) {
   return RT_OK;
 }
 
+// wavefront buffers (and the k-NN scratch) for `paths` path slots, with the batch-size fallback of the auto mode
+int prepare_batch_buffers(rt_ctx* c, bool use_photons) {
+  if (!use_photons || c->params.k <= kKnnSharedMaxK) return RT_OK;
+  const int ctas = c->num_sms * shade_photon_ctas_per_sm(c->params.mode == 1 ? 1 : 0, c->params.k, c->kd_height + 1);
+  return ensure_knn_scratch(c, c->params.k, ctas * kBlock);
+}
+
 // the whole render: batches of samples -> ordered accumulation -> scatter into full-frame buffers
 // composite_dev != null: instead of the raw sums/counters, composite over the background it holds (rt_render)
+// packed_dev != null: the sums and the counter as one float4 per pixel (counter exact as a float up to 2^24 samples)
 struct Progress {
   int every = 0;
   rt_progress_fn fn = nullptr;
   void* user = nullptr;
 };
 int render_to_device(rt_ctx* c, float* out_rgb_dev, int* out_cnt_dev, float* composite_dev = nullptr,
-                     const Progress* progress = nullptr) {
+                     const Progress* progress = nullptr, float4* packed_dev = nullptr) {
   static const bool timing = getenv("RT_TIMING") != nullptr;
   double t_prev = now_ms();
   auto tick = [&](const char* what) {
@@ -435,19 +499,25 @@ int render_to_device(rt_ctx* c, float* out_rgb_dev, int* out_cnt_dev, float* com
   };
   int rc = bind(c);
   if (rc) return rc;
+  reset_call_timing(c);
   if ((rc = prepare_photons(c))) return rc;
   if ((rc = ensure_pix_map(c))) return rc;
   tick("bind+pixmap");
   const rt_params& p = c->params;
   const size_t npx = (size_t)p.width * p.height;
   const bool path_mode = p.mode == 1;
-  // Batch size: <= 32 M paths (kBytesPerPath of wavefront state each, 9.3 GB) by default.  Free HBM is only asked for
-  // when that allocation fails (cudaMemGetInfo costs 1.2-1.6 ms, a twentieth of a cfg2 frame): then the batch shrinks
-  // to half of what is free and the allocation is retried once.
+  const bool photons = use_photon_map(c);
+  const int nl = shadow_lights(c, photons);
+  if ((rc = prepare_batch_buffers(c, photons))) return rc;
+  // Batch size: <= 32 M paths (bytes_per_path() of wavefront state each, 8.9 GB with three lights) by default.  Free HBM is
+  // only asked for when that allocation fails (cudaMemGetInfo costs 1.2-1.6 ms, a twentieth of a cfg2 frame): then
+  // the batch shrinks to half of what is free and the allocation is retried once.
   int spb = p.samples_per_batch;
   const bool auto_batch = spb <= 0;
+  const size_t max_paths = std::min<size_t>((size_t)32 << 20, (((size_t)1 << 32) - 64) / (size_t)std::max(nl, 1));
   if (auto_batch) {
-    if (c->auto_paths == 0) c->auto_paths = (size_t)32 << 20;
+    if (c->auto_paths == 0) c->auto_paths = max_paths;
+    c->auto_paths = std::min(c->auto_paths, max_paths);
     spb = (int)std::max<size_t>(1, std::min<size_t>(c->auto_paths / std::max(c->npix, 1), 1 << 20));
   }
   const int samp_first = p.sample_first;
@@ -461,7 +531,7 @@ int render_to_device(rt_ctx* c, float* out_rgb_dev, int* out_cnt_dev, float* com
     CU(c->d_scratch.ensure(sizeof(float) * 3 * npx));
   }
   tick("batch sizing");
-  rc = ensure_work(c, (size_t)c->npix * spb, path_mode);
+  rc = ensure_work(c, (size_t)c->npix * spb, path_mode, nl);
   if (auto_batch && rc == RT_OK && getenv("RT_TEST_OOM_ONCE") && !c->oom_injected) {  // test hook for the retry path
     c->oom_injected = true;
     rc = RT_ERR_OOM;
@@ -478,11 +548,11 @@ int render_to_device(rt_ctx* c, float* out_rgb_dev, int* out_cnt_dev, float* com
     size_t free_b = 0, total_b = 0;
     CU(cudaMemGetInfo(&free_b, &total_b));
     if (getenv("RT_TEST_OOM_ONCE")) free_b = std::min<size_t>(free_b, (size_t)64 << 20);  // force several batches
-    c->auto_paths = std::max<size_t>(1, std::min<size_t>(free_b / 2 / kBytesPerPath, (size_t)32 << 20));
+    c->auto_paths = std::max<size_t>(1, std::min<size_t>(free_b / 2 / bytes_per_path(nl), max_paths));
     spb = (int)std::max<size_t>(1, std::min<size_t>(c->auto_paths / std::max(c->npix, 1), 1 << 20));
     spb = std::max(1, std::min(spb, std::max(samp_end - samp_first, 1)));
     if (preview) spb = std::max(1, std::min(spb, progress->every));
-    rc = ensure_work(c, (size_t)c->npix * spb, path_mode);
+    rc = ensure_work(c, (size_t)c->npix * spb, path_mode, nl);
   }
   if (rc) return rc;
   tick("ensure_work");
@@ -491,15 +561,15 @@ int render_to_device(rt_ctx* c, float* out_rgb_dev, int* out_cnt_dev, float* com
   CU(cudaMemsetAsync(c->d_acc.p, 0, sizeof(float4) * (size_t)c->npix, c->stream));
   CU(cudaMemsetAsync(c->d_acc_cnt.p, 0, sizeof(int) * (size_t)c->npix, c->stream));
   RenderArgs a;
-  fill_args(c, a, c->d_pix_map.p, c->npix, use_photon_map(c));
-  c->seg_events_used = 0;
+  fill_args(c, a, c->d_pix_map.p, c->npix, photons);
   CU(cudaEventRecord(c->ev0, c->stream));
   if (c->npix > 0) {
     for (int s0 = samp_first; s0 < samp_end; s0 += spb) {
       int ns = std::min(spb, samp_end - s0);
       if ((rc = run_batch(c, a, s0, ns))) return rc;
+      if ((rc = span_begin(c, kKResolve))) return rc;
       launch_resolve(c->d_col0.p, c->npix, ns, c->d_acc.p, c->d_acc_cnt.p, c->stream);
-      c->stats.kernel_launches++;
+      if ((rc = span_end(c, 1))) return rc;
       const int done = s0 + ns - samp_first;
       if (preview && s0 + ns < samp_end && done / progress->every != (done - ns) / progress->every) {
         // Renderer.cpp:262-269 after pass i = done-1: the composite of the first `done` samples
@@ -513,20 +583,29 @@ int render_to_device(rt_ctx* c, float* out_rgb_dev, int* out_cnt_dev, float* com
       }
     }
   }
+  if ((rc = span_begin(c, kKOther))) return rc;
+  int tail_launches = 0;
   if (composite_dev) {
     if (c->npix > 0) {
       launch_composite(c->d_acc.p, c->d_acc_cnt.p, c->d_pix_map.p, c->npix, p.num_rays, composite_dev, composite_dev,
                        c->stream);
-      c->stats.kernel_launches++;
+      tail_launches++;
+    }
+  } else if (packed_dev) {
+    CU(cudaMemsetAsync(packed_dev, 0, sizeof(float4) * npx, c->stream));
+    if (c->npix > 0) {
+      launch_scatter_packed(c->d_acc.p, c->d_acc_cnt.p, c->d_pix_map.p, c->npix, packed_dev, c->stream);
+      tail_launches++;
     }
   } else {
     CU(cudaMemsetAsync(out_rgb_dev, 0, sizeof(float) * 3 * npx, c->stream));
     CU(cudaMemsetAsync(out_cnt_dev, 0, sizeof(int) * npx, c->stream));
     if (c->npix > 0) {
       launch_scatter(c->d_acc.p, c->d_acc_cnt.p, c->d_pix_map.p, c->npix, out_rgb_dev, out_cnt_dev, c->stream);
-      c->stats.kernel_launches++;
+      tail_launches++;
     }
   }
+  if ((rc = span_end(c, tail_launches))) return rc;
   CU(cudaEventRecord(c->ev1, c->stream));
   tick("launches");
   CU(cudaStreamSynchronize(c->stream));
@@ -535,13 +614,7 @@ int render_to_device(rt_ctx* c, float* out_rgb_dev, int* out_cnt_dev, float* com
   float ms = 0.f;
   CU(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
   c->stats.device_ms = ms;
-  double seg_ms = 0.0;
-  for (size_t i = 0; i + 1 < c->seg_events_used; i += 2) {
-    float t = 0.f;
-    CU(cudaEventElapsedTime(&t, c->seg_events[i], c->seg_events[i + 1]));
-    seg_ms += t;
-  }
-  c->stats.trace_ms = seg_ms;
+  if ((rc = collect_spans(c))) return rc;
   c->stats.samples += (uint64_t)c->npix * (uint64_t)std::max(samp_end - samp_first, 0);
   rc = pull_counters(c);
   tick("events+counters");
@@ -554,6 +627,15 @@ int render_to_device(rt_ctx* c, float* out_rgb_dev, int* out_cnt_dev, float* com
 extern "C" {
 
 const char* rt_last_error(void) { return g_err.c_str(); }
+
+int rt_abi_sizes(int32_t* out, int32_t capacity) {
+  const int32_t sizes[9] = {(int32_t)sizeof(rt_material), (int32_t)sizeof(rt_light),  (int32_t)sizeof(rt_camera),
+                            (int32_t)sizeof(rt_scene),    (int32_t)sizeof(rt_params), (int32_t)sizeof(rt_ray),
+                            (int32_t)sizeof(rt_hit),      (int32_t)sizeof(rt_photon), (int32_t)sizeof(rt_stats)};
+  if (!out || capacity < 9) return fail(RT_ERR_INVALID, "rt_abi_sizes needs room for 9 values");
+  for (int i = 0; i < 9; i++) out[i] = sizes[i];
+  return RT_OK;
+}
 
 int rt_device_count(void) {
   int n = 0;
@@ -582,11 +664,13 @@ int rt_destroy(rt_ctx* c) {
   c->d_qo0.release();
   c->d_qo1.release();
   c->d_hit.release();
-  c->d_sh_o.release();
+  c->d_hit_p.release();
   c->d_sh_d.release();
   c->d_contrib.release();
   c->d_occ.release();
   c->d_hit_path.release();
+  c->d_lights_ext.release();
+  c->d_knn_scratch.release();
   c->d_perm.release();
   c->d_sorted.release();
   c->d_sort_hist.release();
@@ -599,7 +683,10 @@ int rt_destroy(rt_ctx* c) {
   c->d_qcount.release();
   c->d_counters.release();
   c->d_scratch.release();
-  for (cudaEvent_t e : c->seg_events) cudaEventDestroy(e);
+  for (auto& sp : c->spans) {
+    cudaEventDestroy(sp.e0);
+    cudaEventDestroy(sp.e1);
+  }
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
   if (c->stream) {
@@ -626,8 +713,7 @@ int rt_create(const rt_scene* s, const rt_params* p, int device, rt_ctx** out) {
   if (rc) return rc;
   if (s->num_vertices < 0 || s->num_triangles < 0 || s->num_meshes < 0 || s->num_lights < 0)
     return fail(RT_ERR_INVALID, "negative scene counts");
-  if (s->num_lights > kShadowLights)
-    return fail(RT_ERR_INVALID, "more than 3 light sources are not supported by the shadow-ray queue layout");
+  if (s->num_lights > 4096) return fail(RT_ERR_INVALID, "more than 4096 light sources");
   if (s->num_triangles > 0 && (!s->positions || !s->normals || !s->triangles || !s->mesh_first_triangle ||
                                !s->mesh_first_vertex || !s->materials))
     return fail(RT_ERR_INVALID, "null scene arrays");
@@ -690,6 +776,7 @@ int rt_create(const rt_scene* s, const rt_params* p, int device, rt_ctx** out) {
     c->bounds_hi = make_float3(hi[0], hi[1], hi[2]);
   }
   if (const char* e = getenv("RT_SORT_HITS")) c->sort_hits = atoi(e);
+  if (const char* e = getenv("RT_OWN_TRI")) c->own_tri = atoi(e) != 0;
   if (!(extent < 1e8f)) {  // keeps lo * safe_inv(d) finite in the slab test (rt_device.cuh)
     rt_destroy(c);
     return fail(RT_ERR_INVALID, "scene coordinates must be finite and smaller than 1e8");
@@ -721,10 +808,12 @@ int rt_create(const rt_scene* s, const rt_params* p, int device, rt_ctx** out) {
   CUC(c->d_nrm.ensure(h_nrm.size()));
   CUC(c->d_tri_vidx.ensure(h_vidx.size()));
   CUC(c->d_mats.ensure(h_mats.size()));
-  CUC(cudaMemcpy(c->d_pos.p, h_pos.data(), h_pos.size() * sizeof(float4), cudaMemcpyHostToDevice));
-  CUC(cudaMemcpy(c->d_nrm.p, h_nrm.data(), h_nrm.size() * sizeof(float4), cudaMemcpyHostToDevice));
-  CUC(cudaMemcpy(c->d_tri_vidx.p, h_vidx.data(), h_vidx.size() * sizeof(int4), cudaMemcpyHostToDevice));
-  CUC(cudaMemcpy(c->d_mats.p, h_mats.data(), h_mats.size() * sizeof(DMaterial), cudaMemcpyHostToDevice));
+  // Allocation (stream-ordered pool), upload and the kernels that read these buffers all run on c->stream, so they
+  // are ordered without a device-wide sync; pageable sources are staged before cudaMemcpyAsync returns.
+  CUC(cudaMemcpyAsync(c->d_pos.p, h_pos.data(), h_pos.size() * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
+  CUC(cudaMemcpyAsync(c->d_tri_vidx.p, h_vidx.data(), h_vidx.size() * sizeof(int4), cudaMemcpyHostToDevice, c->stream));
+  CUC(cudaMemcpyAsync(c->d_nrm.p, h_nrm.data(), h_nrm.size() * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
+  CUC(cudaMemcpyAsync(c->d_mats.p, h_mats.data(), h_mats.size() * sizeof(DMaterial), cudaMemcpyHostToDevice, c->stream));
 
   // ---- BVH (reference split policy): on the device for large scenes, on the host otherwise ----
   const double t_bvh0 = now_ms();
@@ -769,8 +858,9 @@ int rt_create(const rt_scene* s, const rt_params* p, int device, rt_ctx** out) {
     }
     CUC(c->d_nodes.ensure(c->bvh.nodes.size() / 4));
     CUC(c->d_tris.ensure(h_tris.size()));
-    CUC(cudaMemcpy(c->d_nodes.p, c->bvh.nodes.data(), c->bvh.nodes.size() * sizeof(float), cudaMemcpyHostToDevice));
-    CUC(cudaMemcpy(c->d_tris.p, h_tris.data(), h_tris.size() * sizeof(float4), cudaMemcpyHostToDevice));
+    CUC(cudaMemcpyAsync(c->d_nodes.p, c->bvh.nodes.data(), c->bvh.nodes.size() * sizeof(float), cudaMemcpyHostToDevice,
+                        c->stream));
+    CUC(cudaMemcpyAsync(c->d_tris.p, h_tris.data(), h_tris.size() * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
   }
   c->stats.bvh_build_ms = now_ms() - t_bvh0;
   if (std::max(c->bvh.depth, c->bvh.mesh_depth + kMaxRoots) > kStackDepth) {
@@ -780,7 +870,7 @@ int rt_create(const rt_scene* s, const rt_params* p, int device, rt_ctx** out) {
   c->stats.bvh_nodes = (int)c->bvh.num_nodes;
   c->stats.bvh_depth = c->bvh.depth;
   CUC(c->d_counters.ensure(kCntNum));
-  CUC(cudaMemset(c->d_counters.p, 0, sizeof(unsigned long long) * kCntNum));
+  CUC(cudaMemsetAsync(c->d_counters.p, 0, sizeof(unsigned long long) * kCntNum, c->stream));
   CUC(c->d_kd_pos.ensure(1));
   CUC(c->d_kd_dir.ensure(1));
 
@@ -793,11 +883,24 @@ int rt_create(const rt_scene* s, const rt_params* p, int device, rt_ctx** out) {
   S.mats = c->d_mats.p;
   S.num_lights = c->L;
   S.num_tris = c->T;
-  for (int l = 0; l < c->L; l++) {
-    const rt_light& a = s->lights[l];
-    S.lights[l] = DLight{h3(a.position), h3(a.color),  h3(a.normal), h3(a.vertical), h3(a.horizontal),
-                         a.intensity,    a.side,       a.ac,         a.al,           a.aq,
-                         a.factor};
+  {
+    std::vector<DLight> ext;
+    for (int l = 0; l < c->L; l++) {
+      const rt_light& a = s->lights[l];
+      const DLight d{h3(a.position), h3(a.color), h3(a.normal), h3(a.vertical), h3(a.horizontal),
+                     a.intensity,    a.side,      a.ac,         a.al,           a.aq,
+                     a.factor};
+      if (l < kMaxLights)
+        S.lights[l] = d;
+      else
+        ext.push_back(d);
+    }
+    S.lights_ext = nullptr;
+    if (!ext.empty()) {  // Scene::lightsources() may hold any number of lights (Scene.h:14-26, Renderer.cpp:49)
+      CUC(c->d_lights_ext.ensure(ext.size()));
+      CUC(cudaMemcpyAsync(c->d_lights_ext.p, ext.data(), ext.size() * sizeof(DLight), cudaMemcpyHostToDevice, c->stream));
+      S.lights_ext = c->d_lights_ext.p;
+    }
   }
   S.cam = DCamera{h3(s->camera.position), h3(s->camera.lower_left), h3(s->camera.horizontal), h3(s->camera.vertical)};
   S.kd_pos = c->d_kd_pos.p;
@@ -810,6 +913,7 @@ int rt_create(const rt_scene* s, const rt_params* p, int device, rt_ctx** out) {
     S.root_lo[r] = make_float4(q[0], q[1], q[2], 0.f);
     S.root_hi[r] = make_float4(q[3], q[4], q[5], q[6]);
   }
+  CUC(cudaStreamSynchronize(c->stream));  // uploads done: the host staging vectors above go out of scope
 #undef CUC
   c->stats.create_ms = now_ms() - t_create0;
   *out = c;
@@ -821,6 +925,13 @@ int rt_render_accumulate_device(rt_ctx* c, float* sum_rgb_device, int32_t* count
   return render_to_device(c, sum_rgb_device, counter_device);
 }
 
+int rt_render_accumulate_packed_device(rt_ctx* c, float* sum_rgbn_device) {
+  if (!c || !sum_rgbn_device) return fail(RT_ERR_INVALID, "null argument");
+  if ((size_t)sum_rgbn_device % 16) return fail(RT_ERR_INVALID, "the packed frame must be 16-byte aligned");
+  if (c->params.num_rays >= (1 << 24)) return fail(RT_ERR_INVALID, "packed counters are exact only below 2^24 samples");
+  return render_to_device(c, nullptr, nullptr, nullptr, nullptr, reinterpret_cast<float4*>(sum_rgbn_device));
+}
+
 int rt_render_accumulate(rt_ctx* c, float* sum_rgb, int32_t* counter) {
   if (!c || !sum_rgb || !counter) return fail(RT_ERR_INVALID, "null argument");
   int rc = bind(c);
@@ -829,8 +940,9 @@ int rt_render_accumulate(rt_ctx* c, float* sum_rgb, int32_t* counter) {
   CU(c->d_out_rgb.ensure(3 * npx));
   CU(c->d_out_cnt.ensure(npx));
   if ((rc = render_to_device(c, c->d_out_rgb.p, c->d_out_cnt.p))) return rc;
-  CU(cudaMemcpy(sum_rgb, c->d_out_rgb.p, sizeof(float) * 3 * npx, cudaMemcpyDeviceToHost));
-  CU(cudaMemcpy(counter, c->d_out_cnt.p, sizeof(int) * npx, cudaMemcpyDeviceToHost));
+  CU(cudaMemcpyAsync(sum_rgb, c->d_out_rgb.p, sizeof(float) * 3 * npx, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaMemcpyAsync(counter, c->d_out_cnt.p, sizeof(int) * npx, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
   return RT_OK;
 }
 
@@ -839,6 +951,7 @@ int rt_render_accumulate(rt_ctx* c, float* sum_rgb, int32_t* counter) {
 int rt_composite(int32_t width, int32_t height, int32_t num_rays, const float* sum_rgb, const int32_t* counter,
                  float* rgb_inout) {
   if (!sum_rgb || !counter || !rgb_inout || width < 1 || height < 1) return fail(RT_ERR_INVALID, "bad argument");
+  if (num_rays < 1) return fail(RT_ERR_INVALID, "num_rays must be >= 1 to composite");
   const float fn = (float)num_rays;
   for (size_t px = 0; px < (size_t)width * height; px++) {
     const float miss = (float)(num_rays - counter[px]);
@@ -852,9 +965,27 @@ int rt_composite(int32_t width, int32_t height, int32_t num_rays, const float* s
   return RT_OK;
 }
 
+// the same composite on the packed frame (sums + counter as one float4 per pixel) a single reduce produces
+int rt_composite_packed_device(rt_ctx* c, int32_t num_rays, const float* sum_rgbn_device, float* rgb_inout) {
+  if (!c || !sum_rgbn_device || !rgb_inout) return fail(RT_ERR_INVALID, "null argument");
+  if (num_rays < 1) return fail(RT_ERR_INVALID, "num_rays must be >= 1 to composite");
+  int rc = bind(c);
+  if (rc) return rc;
+  const size_t npx = (size_t)c->params.width * c->params.height;
+  CU(c->d_out_rgb.ensure(3 * npx));
+  CU(cudaMemcpyAsync(c->d_out_rgb.p, rgb_inout, sizeof(float) * 3 * npx, cudaMemcpyHostToDevice, c->stream));
+  launch_composite_packed(reinterpret_cast<const float4*>(sum_rgbn_device), (long long)npx, num_rays, c->d_out_rgb.p,
+                          c->stream);
+  c->stats.kernel_launches++;
+  CU(cudaMemcpyAsync(rgb_inout, c->d_out_rgb.p, sizeof(float) * 3 * npx, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return RT_OK;
+}
+
 int rt_composite_device(rt_ctx* c, int32_t num_rays, const float* sum_rgb_device, const int32_t* counter_device,
                         float* rgb_inout) {
   if (!c || !sum_rgb_device || !counter_device || !rgb_inout) return fail(RT_ERR_INVALID, "null argument");
+  if (num_rays < 1) return fail(RT_ERR_INVALID, "num_rays must be >= 1 to composite");
   int rc = bind(c);
   if (rc) return rc;
   const size_t npx = (size_t)c->params.width * c->params.height;
@@ -873,7 +1004,12 @@ int rt_render_progressive(rt_ctx* c, float* rgb_inout, int32_t every, rt_progres
   if (!c || !rgb_inout) return fail(RT_ERR_INVALID, "null argument");
   const rt_params& p = c->params;
   const size_t npx = (size_t)p.width * p.height;
-  if (p.num_rays < 1) return RT_OK;  // Renderer.cpp:219: no pass, image = saveImage (we leave the input)
+  if (p.num_rays < 1) {
+    // Renderer.cpp:208,219,271: the sample loop does not run and `image = saveImage`, a default-constructed
+    // Image(w, h) whose Vec3f pixels are zero (Image.h:12-15, Vec3.h:21) -- -N 0 yields a black frame.
+    std::memset(rgb_inout, 0, sizeof(float) * 3 * npx);
+    return RT_OK;
+  }
   int rc = bind(c);
   if (rc) return rc;
   // background up, the whole Renderer::render on the device (composite included), frame down
@@ -881,7 +1017,8 @@ int rt_render_progressive(rt_ctx* c, float* rgb_inout, int32_t every, rt_progres
   CU(cudaMemcpyAsync(c->d_out_rgb.p, rgb_inout, sizeof(float) * 3 * npx, cudaMemcpyHostToDevice, c->stream));
   Progress progress{every, fn, user};
   if ((rc = render_to_device(c, nullptr, nullptr, c->d_out_rgb.p, &progress))) return rc;
-  CU(cudaMemcpy(rgb_inout, c->d_out_rgb.p, sizeof(float) * 3 * npx, cudaMemcpyDeviceToHost));
+  CU(cudaMemcpyAsync(rgb_inout, c->d_out_rgb.p, sizeof(float) * 3 * npx, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
   if (fn && every > 0) fn(user, p.num_rays, p.num_rays, rgb_inout);  // the last pass: update.ppm == the result
   return RT_OK;
 }
@@ -901,23 +1038,29 @@ int rt_render_samples(rt_ctx* c, int32_t x0, int32_t y0, int32_t x1, int32_t y1,
     for (int x = x0; x < x1; x++) map[(size_t)(y - y0) * ww + (x - x0)] = y * p.width + x;
   const size_t paths = map.size() * (size_t)ns;
   if (paths > ((size_t)1 << 30)) return fail(RT_ERR_INVALID, "window too large");
+  const bool photons = use_photon_map(c);
+  if (paths * (size_t)std::max(shadow_lights(c, photons), 1) >= ((size_t)1 << 32))
+    return fail(RT_ERR_INVALID, "window too large");
   DevBuf<int> d_map;
   CU(d_map.ensure(map.size()));
-  CU(cudaMemcpy(d_map.p, map.data(), map.size() * sizeof(int), cudaMemcpyHostToDevice));
-  if ((rc = ensure_work(c, paths, p.mode == 1))) {
+  CU(cudaMemcpyAsync(d_map.p, map.data(), map.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  if ((rc = prepare_batch_buffers(c, photons)) || (rc = ensure_work(c, paths, p.mode == 1, shadow_lights(c, photons)))) {
     d_map.release();
     return rc;
   }
   RenderArgs a;
-  fill_args(c, a, d_map.p, (int)map.size(), use_photon_map(c));
-  c->seg_events_used = 0;
+  fill_args(c, a, d_map.p, (int)map.size(), photons);
+  reset_call_timing(c);
   rc = run_batch(c, a, s0, ns);
   std::vector<float4> h(paths);
-  cudaError_t e = cudaStreamSynchronize(c->stream);
-  if (e == cudaSuccess) e = cudaMemcpy(h.data(), c->d_col0.p, paths * sizeof(float4), cudaMemcpyDeviceToHost);
+  cudaError_t e = cudaSuccess;
+  if (rc == RT_OK) e = cudaMemcpyAsync(h.data(), c->d_col0.p, paths * sizeof(float4), cudaMemcpyDeviceToHost, c->stream);
+  cudaError_t e2 = cudaStreamSynchronize(c->stream);
+  if (e == cudaSuccess) e = e2;
   d_map.release();
   if (rc) return rc;
   if (e != cudaSuccess) return fail(RT_ERR_CUDA, cudaGetErrorString(e));
+  if ((rc = collect_spans(c))) return rc;
   c->stats.samples += paths;
   for (size_t i = 0; i < paths; i++) {
     rgb[3 * i] = h[i].x;
@@ -947,8 +1090,8 @@ static int trace_common(rt_ctx* c, const rt_ray* rays, int64_t n, rt_hit* hits, 
   if (e == cudaSuccess) e = d_h.ensure((size_t)n);
   if (e == cudaSuccess) e = d_occ.ensure((size_t)n);
   if (e == cudaSuccess) e = c->d_qcount.ensure(kQNum);
-  if (e == cudaSuccess) e = cudaMemcpy(d_o.p, ho.data(), sizeof(float4) * (size_t)n, cudaMemcpyHostToDevice);
-  if (e == cudaSuccess) e = cudaMemcpy(d_d.p, hd.data(), sizeof(float4) * (size_t)n, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_o.p, ho.data(), sizeof(float4) * (size_t)n, cudaMemcpyHostToDevice, c->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_d.p, hd.data(), sizeof(float4) * (size_t)n, cudaMemcpyHostToDevice, c->stream);
   if (e == cudaSuccess) {
     const int depth = trace_stack_depth(c);
     const int persistent = c->num_sms * trace_ctas_per_sm(depth);
@@ -997,7 +1140,7 @@ int rt_eval_bsdf(rt_ctx* c, const rt_material* m, const float* n_wi_wo, int64_t 
   DevBuf<float> d_in, d_out;
   cudaError_t e = d_in.ensure(9 * (size_t)n);
   if (e == cudaSuccess) e = d_out.ensure(3 * (size_t)n);
-  if (e == cudaSuccess) e = cudaMemcpy(d_in.p, n_wi_wo, sizeof(float) * 9 * (size_t)n, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_in.p, n_wi_wo, sizeof(float) * 9 * (size_t)n, cudaMemcpyHostToDevice, c->stream);
   if (e == cudaSuccess) {
     launch_bsdf(make_material(m->kd, m->alpha, h3(m->albedo), h3(m->f0)), d_in.p, n, d_out.p, c->stream);
     c->stats.kernel_launches++;
@@ -1042,8 +1185,10 @@ int rt_emit_photons(rt_ctx* c, int32_t first_path, int32_t num_paths, rt_photon*
                 (c->params.flags & RT_FLAG_BRUTE_FORCE) ? 1 : 0, d_a.p, d_b.p, c->d_counters.p, c->stream);
     cudaEventRecord(c->ev1, c->stream);
     c->stats.kernel_launches++;
+    c->stats.kernel_count[kKEmit]++;
     e = cudaStreamSynchronize(c->stream);
     if (e == cudaSuccess) cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+    c->stats.kernel_ms[kKEmit] = ms;
   }
   if (e == cudaSuccess) e = cudaMemcpy(ha.data(), d_a.p, total * sizeof(float4), cudaMemcpyDeviceToHost);
   if (e == cudaSuccess) e = cudaMemcpy(hb.data(), d_b.p, total * sizeof(float4), cudaMemcpyDeviceToHost);
@@ -1095,8 +1240,9 @@ int rt_set_photons(rt_ctx* c, const rt_photon* photons, int64_t n) {
   }
   CU(c->d_kd_pos.ensure(hp.size()));
   CU(c->d_kd_dir.ensure(hd.size()));
-  CU(cudaMemcpy(c->d_kd_pos.p, hp.data(), hp.size() * sizeof(float4), cudaMemcpyHostToDevice));
-  CU(cudaMemcpy(c->d_kd_dir.p, hd.data(), hd.size() * sizeof(float4), cudaMemcpyHostToDevice));
+  CU(cudaMemcpyAsync(c->d_kd_pos.p, hp.data(), hp.size() * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(c->d_kd_dir.p, hd.data(), hd.size() * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
   c->scene.kd_pos = c->d_kd_pos.p;
   c->scene.kd_dir = c->d_kd_dir.p;
   c->scene.kd_count = (int)n;
@@ -1148,16 +1294,22 @@ int rt_knn(rt_ctx* c, const float* queries, int64_t n, int32_t k, int32_t* node_
   if (n < 0 || (n > 0 && (!queries || !node_index))) return fail(RT_ERR_INVALID, "bad argument");
   if (c->scene.kd_count == 0) return fail(RT_ERR_EMPTY_TREE, "tree is empty");  // kdtree.h:181
   if (k > c->scene.kd_count) return fail(RT_ERR_K_TOO_LARGE, "k is greater than the number of nodes");
-  if (k < 1 || k > RT_MAX_K) return fail(RT_ERR_INVALID, "k must be in [1, 64]");
+  if (k < 1 || k > RT_MAX_K) return fail(RT_ERR_INVALID, "k must be in [1, " + std::to_string(RT_MAX_K) + "]");
   if (n == 0) return RT_OK;
+  // grid-stride kernel with exactly the resident CTA count (beyond kKnnSharedMaxK the candidates of every resident
+  // thread live in a global scratch sized for that grid)
+  const int ctas = (int)std::min<int64_t>((n + kBlock - 1) / kBlock,
+                                          (int64_t)c->num_sms * knn_ctas_per_sm(k, c->kd_height + 1));
+  if ((rc = ensure_knn_scratch(c, k, ctas * kBlock))) return rc;
   DevBuf<float> d_q;
   DevBuf<int> d_idx;
   cudaError_t e = d_q.ensure(3 * (size_t)n);
   if (e == cudaSuccess) e = d_idx.ensure((size_t)n * k);
-  if (e == cudaSuccess) e = cudaMemcpy(d_q.p, queries, sizeof(float) * 3 * (size_t)n, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess)
+    e = cudaMemcpyAsync(d_q.p, queries, sizeof(float) * 3 * (size_t)n, cudaMemcpyHostToDevice, c->stream);
   if (e == cudaSuccess) {
-    launch_knn(c->scene, d_q.p, n, k, c->kd_height + 1, knn_flavour_k(c->params, k), d_idx.p,
-               c->d_counters.p, c->stream);
+    launch_knn(c->scene, d_q.p, n, k, c->kd_height + 1, knn_flavour_k(c->params, k), d_idx.p, c->d_counters.p,
+               c->d_knn_scratch.p, ctas, c->stream);
     c->stats.kernel_launches++;
     e = cudaStreamSynchronize(c->stream);
   }
@@ -1194,7 +1346,8 @@ int rt_reset_stats(rt_ctx* c) {
   const double cms = c->stats.create_ms, bms = c->stats.bvh_build_ms, kms = c->stats.kd_build_ms;
   int rc = bind(c);
   if (rc) return rc;
-  CU(cudaMemset(c->d_counters.p, 0, sizeof(unsigned long long) * kCntNum));
+  CU(cudaMemsetAsync(c->d_counters.p, 0, sizeof(unsigned long long) * kCntNum, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
   c->stats = rt_stats{};
   c->stats.bvh_nodes = nodes;
   c->stats.bvh_depth = depth;

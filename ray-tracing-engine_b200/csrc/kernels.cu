@@ -161,14 +161,35 @@ RT_DI void trace_leaf_step(const DScene& S, TraceLane& L, const int* st_ref, con
     trace_pop<ANY>(L, st_ref, st_tn);
 }
 
+// Next work item of a trace kernel.  Plain queues hold (origin, direction) per ray.  BLOCKED (shadow rays): slot `my`
+// of the light-major layout belongs to hit j = shadow_slot_hit(my, nl); its origin is the hit point hit_p[j] shared by
+// the hit's nl rays, its direction rd[my]; w != 0 marks a ray k_shade already found occluded by the very triangle it
+// starts on (12-15 % of all shadow rays) -- the result is written, nothing to trace.
+template <bool BLOCKED>
+RT_DI bool trace_fetch(const float4* __restrict__ ro, const float4* __restrict__ rd, unsigned my, unsigned n,
+                       unsigned items, unsigned nl, float4& a, float4& b) {
+  if (my >= n) return false;
+  if (BLOCKED) {
+    const unsigned j = shadow_slot_hit(my, nl);
+    if (j >= items) return false;
+    b = __ldcs(rd + my);  // streamed once: keep L1 for the BVH
+    if (b.w != 0.f) return false;
+    a = __ldg(ro + j);
+    return true;
+  }
+  a = __ldcs(ro + my);
+  b = __ldcs(rd + my);
+  return true;
+}
+
 template <bool ANY, bool BLOCKED, int LEAFB>
 RT_DI void trace_body(const DScene& S, const float4* __restrict__ ro, const float4* __restrict__ rd,
                       const unsigned* n_ptr, unsigned n_fixed, float4* __restrict__ hits,
-                      unsigned char* __restrict__ occ, unsigned* fetch, int depth, int* s_dyn) {
+                      unsigned char* __restrict__ occ, unsigned* fetch, int depth, unsigned nl, int* s_dyn) {
   int* st_ref = s_dyn + threadIdx.x;
   int* st_tn = s_dyn + depth * kBlock + threadIdx.x;
   const unsigned items = n_ptr ? *n_ptr : n_fixed;                  // rays (or hit points when BLOCKED)
-  const unsigned n = BLOCKED ? shadow_slots_for(items) : items;    // queue slots to visit
+  const unsigned n = BLOCKED ? (unsigned)shadow_slots_for(items, nl) : items;  // queue slots to visit
   const unsigned lane = threadIdx.x & 31u;
   const unsigned lt_mask = (1u << lane) - 1u;
 
@@ -194,10 +215,8 @@ RT_DI void trace_body(const DScene& S, const float4* __restrict__ ro, const floa
       if (base + cnt >= n) exhausted = true;
       if (need) {
         const unsigned my = base + __popc(need_mask & lt_mask);
-        bool valid = my < n;
-        if (BLOCKED && valid) valid = ((my / 96u) * 32u + (my & 31u)) < items;
-        if (valid) {
-          const float4 a = __ldcs(ro + my), b = __ldcs(rd + my);  // streamed once: keep L1 for the BVH
+        float4 a, b;
+        if (trace_fetch<BLOCKED>(ro, rd, my, n, items, nl, a, b)) {
           L.idx = my;
           L.o = f3(a);
           L.d = f3(b);
@@ -261,11 +280,11 @@ RT_DI void trace_body(const DScene& S, const float4* __restrict__ ro, const floa
 template <bool ANY, bool BLOCKED, int LEAFT, int UNROLL = 1>
 RT_DI void trace_body_spec(const DScene& S, const float4* __restrict__ ro, const float4* __restrict__ rd,
                            const unsigned* n_ptr, unsigned n_fixed, float4* __restrict__ hits,
-                           unsigned char* __restrict__ occ, unsigned* fetch, int depth, int* s_dyn) {
+                           unsigned char* __restrict__ occ, unsigned* fetch, int depth, unsigned nl, int* s_dyn) {
   int* st_ref = s_dyn + threadIdx.x;
   int* st_tn = s_dyn + depth * kBlock + threadIdx.x;
   const unsigned items = n_ptr ? *n_ptr : n_fixed;
-  const unsigned n = BLOCKED ? shadow_slots_for(items) : items;
+  const unsigned n = BLOCKED ? (unsigned)shadow_slots_for(items, nl) : items;
   const unsigned lane = threadIdx.x & 31u;
   const unsigned lt_mask = (1u << lane) - 1u;
 
@@ -291,10 +310,8 @@ RT_DI void trace_body_spec(const DScene& S, const float4* __restrict__ ro, const
       if (base + cnt >= n) exhausted = true;
       if (!live) {
         const unsigned my = base + __popc(need_mask & lt_mask);
-        bool valid = my < n;
-        if (BLOCKED && valid) valid = ((my / 96u) * 32u + (my & 31u)) < items;
-        if (valid) {
-          const float4 a = __ldcs(ro + my), b = __ldcs(rd + my);  // streamed once: keep L1 for the BVH
+        float4 a, b;
+        if (trace_fetch<BLOCKED>(ro, rd, my, n, items, nl, a, b)) {
           L.idx = my;
           L.o = f3(a);
           L.d = f3(b);
@@ -381,9 +398,10 @@ RT_DI void trace_body_spec(const DScene& S, const float4* __restrict__ ro, const
   template <bool ANY, bool BLOCKED>                                                                                 \
   __global__ void __launch_bounds__(kBlock, RT_TRACE_MINB)                                                                      \
       NAME(const DScene S, const float4* __restrict__ ro, const float4* __restrict__ rd, const unsigned* n_ptr,    \
-           unsigned n_fixed, float4* __restrict__ hits, unsigned char* __restrict__ occ, unsigned* fetch, int depth) { \
+           unsigned n_fixed, float4* __restrict__ hits, unsigned char* __restrict__ occ, unsigned* fetch, int depth, \
+           unsigned nl) {                                                                                           \
     extern __shared__ int s_dyn[];                                                                                  \
-    trace_body_spec<ANY, BLOCKED, LEAFT, UNROLL>(S, ro, rd, n_ptr, n_fixed, hits, occ, fetch, depth, s_dyn);                \
+    trace_body_spec<ANY, BLOCKED, LEAFT, UNROLL>(S, ro, rd, n_ptr, n_fixed, hits, occ, fetch, depth, nl, s_dyn);    \
   }
 // Variants kept for comparison (RT_TRACE_VARIANT); everything else that was measured is in profiles/r1_tuning.md.
 RT_TRACE_KERNEL_SPEC(k_trace_sp8, 8, 1)    // variant 5: one node step per round of votes (28.1 ms/frame)
@@ -393,9 +411,10 @@ RT_TRACE_KERNEL_SPEC(k_trace_sp8u3, 8, 3)  // variant 10 (default): 26.2 ms/fram
   template <bool ANY, bool BLOCKED>                                                                                 \
   __global__ void __launch_bounds__(kBlock, MINB)                                                                   \
       NAME(const DScene S, const float4* __restrict__ ro, const float4* __restrict__ rd, const unsigned* n_ptr,    \
-           unsigned n_fixed, float4* __restrict__ hits, unsigned char* __restrict__ occ, unsigned* fetch, int depth) { \
+           unsigned n_fixed, float4* __restrict__ hits, unsigned char* __restrict__ occ, unsigned* fetch, int depth, \
+           unsigned nl) {                                                                                           \
     extern __shared__ int s_dyn[];                                                                                  \
-    trace_body<ANY, BLOCKED, LEAFB>(S, ro, rd, n_ptr, n_fixed, hits, occ, fetch, depth, s_dyn);                     \
+    trace_body<ANY, BLOCKED, LEAFB>(S, ro, rd, n_ptr, n_fixed, hits, occ, fetch, depth, nl, s_dyn);                 \
   }
 // Measured on B200, cfg2 frame (profiles/r1_tuning.md): variant 0 37.4 ms, variant 1 33.6 ms at the time; the
 // postponed-leaf kernels above superseded both.
@@ -416,13 +435,14 @@ void set_trace_variant(int v) { g_trace_variant = v; }
 template <bool ANY, bool BLOCKED>
 __global__ void __launch_bounds__(kBlock)
     k_trace_brute(const DScene S, const float4* __restrict__ ro, const float4* __restrict__ rd, const unsigned* n_ptr,
-                  unsigned n_fixed, float4* __restrict__ hits, unsigned char* __restrict__ occ) {
+                  unsigned n_fixed, float4* __restrict__ hits, unsigned char* __restrict__ occ, unsigned nl) {
   const unsigned items = n_ptr ? *n_ptr : n_fixed;
-  const unsigned n = BLOCKED ? shadow_slots_for(items) : items;
+  const unsigned n = BLOCKED ? (unsigned)shadow_slots_for(items, nl) : items;
   for (unsigned i = blockIdx.x * kBlock + threadIdx.x; i < n; i += gridDim.x * kBlock) {
-    if (BLOCKED && ((i / 96u) * 32u + (i & 31u)) >= items) continue;
+    float4 a, b;
+    if (!trace_fetch<BLOCKED>(ro, rd, i, n, items, nl, a, b)) continue;
     HitRec h;
-    const float3 o = f3(__ldg(ro + i)), d = f3(__ldg(rd + i));
+    const float3 o = f3(a), d = f3(b);
     const bool f = brute_trace<ANY>(S, o, d, h);
     if (ANY)
       occ[i] = f ? 1 : 0;
@@ -447,10 +467,10 @@ int trace_ctas_per_sm(int stack_depth) {
 
 template <bool ANY, bool BLOCKED>
 static void launch_trace_t(const DScene& S, const float4* ro, const float4* rd, const unsigned* n_ptr, unsigned n_fixed,
-                           float4* hits, unsigned char* occ, unsigned* fetch, int brute, int depth, int grid,
-                           cudaStream_t st) {
+                           float4* hits, unsigned char* occ, unsigned* fetch, int brute, int depth, unsigned nl,
+                           int grid, cudaStream_t st) {
   if (brute) {
-    k_trace_brute<ANY, BLOCKED><<<grid, kBlock, 0, st>>>(S, ro, rd, n_ptr, n_fixed, hits, occ);
+    k_trace_brute<ANY, BLOCKED><<<grid, kBlock, 0, st>>>(S, ro, rd, n_ptr, n_fixed, hits, occ, nl);
   } else {
     cudaMemsetAsync(fetch, 0, sizeof(unsigned), st);
     static const int refill = getenv("RT_REFILL_BELOW") ? atoi(getenv("RT_REFILL_BELOW")) : -1;
@@ -465,7 +485,7 @@ static void launch_trace_t(const DScene& S, const float4* ro, const float4* rd, 
 #define RT_LAUNCH(K)                                                                                          \
   do {                                                                                                        \
     if (carve >= 0) cudaFuncSetAttribute(K<ANY, BLOCKED>, cudaFuncAttributePreferredSharedMemoryCarveout, carve); \
-    K<ANY, BLOCKED><<<grid, kBlock, sm, st>>>(S, ro, rd, n_ptr, n_fixed, hits, occ, fetch, depth);           \
+    K<ANY, BLOCKED><<<grid, kBlock, sm, st>>>(S, ro, rd, n_ptr, n_fixed, hits, occ, fetch, depth, nl);       \
   } while (0)
     switch (trace_variant()) {
       case 0: RT_LAUNCH(k_trace); break;
@@ -480,19 +500,20 @@ static void launch_trace_t(const DScene& S, const float4* ro, const float4* rd, 
 void launch_trace_nearest(const RenderArgs& a, int seg, int grid, cudaStream_t st) {
   const unsigned* n_ptr = seg == 0 ? nullptr : a.q_count + kQHits0 + (seg - 1);
   launch_trace_t<false, false>(a.scene, a.ray_o[seg & 1], a.ray_d[seg & 1], n_ptr, (unsigned)a.npix * (unsigned)a.nsamp,
-                               a.hit, nullptr, a.q_count + kQFetchNearest0 + seg, a.brute, a.stack_depth, grid, st);
+                               a.hit, nullptr, a.q_count + kQFetchNearest0 + seg, a.brute, a.stack_depth, 1u, grid, st);
 }
 void launch_trace_any(const RenderArgs& a, int seg, int grid, cudaStream_t st) {
-  launch_trace_t<true, true>(a.scene, a.sh_o, a.sh_d, a.q_count + kQHits0 + seg, 0, nullptr, a.occ,
-                             a.q_count + kQFetchAny0 + seg, a.brute, a.stack_depth, grid, st);
+  if (a.nl < 1) return;  // a scene without lights casts no shadow rays
+  launch_trace_t<true, true>(a.scene, a.hit_p, a.sh_d, a.q_count + kQHits0 + seg, 0, nullptr, a.occ,
+                             a.q_count + kQFetchAny0 + seg, a.brute, a.stack_depth, (unsigned)a.nl, grid, st);
 }
 void launch_trace_rays(const DScene& s, const float4* ro, const float4* rd, unsigned n, float4* hits,
                        unsigned char* occluded, int any, int brute, int stack_depth, unsigned* fetch_counter, int grid,
                        cudaStream_t st) {
   if (any)
-    launch_trace_t<true, false>(s, ro, rd, nullptr, n, nullptr, occluded, fetch_counter, brute, stack_depth, grid, st);
+    launch_trace_t<true, false>(s, ro, rd, nullptr, n, nullptr, occluded, fetch_counter, brute, stack_depth, 1u, grid, st);
   else
-    launch_trace_t<false, false>(s, ro, rd, nullptr, n, hits, nullptr, fetch_counter, brute, stack_depth, grid, st);
+    launch_trace_t<false, false>(s, ro, rd, nullptr, n, hits, nullptr, fetch_counter, brute, stack_depth, 1u, grid, st);
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -658,31 +679,41 @@ __device__ __noinline__ void knn_exact_redo(const DScene& S, float3 q, int k, un
   for (int j = 0; j < k; j++) sc[j * ks] = kd_pack(hd[j], hi[j]);
 }
 
-RT_DI float3 shade_photon(const DScene& S, float3 dir, float3 n, float3 P, const DMaterial& m, int k, int num_photons,
-                          int exact, unsigned long long* sc, int* kst, unsigned long long& visits) {
+// sc: this thread's k candidate slots (stride ks between slots), kst: its stack frames (stride kBlock)
+RT_DI void knn_query(const DScene& S, float3 P, int k, int exact, unsigned long long* sc, int ks, int* kst,
+                     unsigned long long& visits) {
   if (exact > 0)
-    kd_knearest_exact(S, P, k, sc, kst, kBlock, visits);
+    kd_knearest_exact(S, P, k, sc, ks, kst, kBlock, visits);
   else if (exact < 0)  // large k: libstdc++'s heap restated (log k moves per insertion, ties for free)
-    kd_knearest_heap(S, P, k, sc, kst, kBlock, visits);
-  else if (kd_knearest_sorted(S, P, k, sc, kst, kBlock, visits))
-    knn_exact_redo(S, P, k, sc, kBlock);
-  float r = kd_dist_of(sc[(k - 1) * kBlock]);  // farthest of the k (candidates are in ascending distance)
+    kd_knearest_heap(S, P, k, sc, ks, kst, kBlock, visits);
+  else if (kd_knearest_sorted(S, P, k, sc, ks, kst, kBlock, visits))
+    knn_exact_redo(S, P, k, sc, ks);
+}
+
+RT_DI float3 shade_photon(const DScene& S, float3 dir, float3 n, float3 P, const DMaterial& m, int k, int num_photons,
+                          int exact, unsigned long long* sc, int ks, int* kst, unsigned long long& visits) {
+  knn_query(S, P, k, exact, sc, ks, kst, visits);
+  float r = kd_dist_of(sc[(unsigned)(k - 1) * (unsigned)ks]);  // farthest of the k (candidates are in ascending distance)
   float area = (float)__dmul_rn(__dmul_rn(3.141592653589793, (double)r), (double)r);
   float3 avg = f3(0.f, 0.f, 0.f);
   float cnt = 0.f;
   for (int j = 0; j < k; j++) {
-    avg = v_add(avg, f3(__ldg(S.kd_dir + kd_index_of(sc[j * kBlock]))));
+    avg = v_add(avg, f3(__ldg(S.kd_dir + kd_index_of(sc[(unsigned)j * (unsigned)ks]))));
     cnt = __fadd_rn(cnt, 1.f);
   }
   float rad = __fmul_rn(__fdiv_rn(__fdiv_rn(cnt, area), (float)num_photons), 100.f);
   float3 bsdf = evaluate_color_response(m, n, v_norm(avg), v_neg(dir));
   return v_scl(bsdf, rad);
 }
-// dynamic shared memory of the kernels that run kd_knearest_sorted: k candidate (distance, index) pairs and
-// `frames` stack frames of 3 ints per thread
-size_t knn_smem_bytes(int k, int frames) { return (size_t)(2 * k + 3 * frames) * kBlock * sizeof(int); }
+// dynamic shared memory of the kernels that run the k-NN: `frames` stack frames of 3 ints per thread, and -- up to
+// k = kKnnSharedMaxK -- the k candidate (distance, index) pairs; beyond that the candidates live in global memory
+size_t knn_smem_bytes(int k, int frames) {
+  return (size_t)((k <= kKnnSharedMaxK ? 2 * k : 0) + 3 * frames) * kBlock * sizeof(int);
+}
 
-template <int MODE, bool PHOTON>
+// NLT: 3 = the stock three-light loop unrolled (Main.cpp:101-124), 0 = any light count (Renderer.cpp:49).
+// GSC (PHOTON only): k-NN candidates in global memory (k > kKnnSharedMaxK).
+template <int MODE, bool PHOTON, int NLT, bool GSC>
 __global__ void __launch_bounds__(kBlock, PHOTON ? 6 : RT_SHADE_MINB) k_shade(const RenderArgs A, const int seg) {
   extern __shared__ unsigned long long s_knn[];  // PHOTON only: k 64-bit candidate rows, then 3*frames int rows
   const DScene& S = A.scene;
@@ -692,6 +723,7 @@ __global__ void __launch_bounds__(kBlock, PHOTON ? 6 : RT_SHADE_MINB) k_shade(co
   float4* qo_out = A.ray_o[(seg + 1) & 1];
   float4* qd_out = A.ray_d[(seg + 1) & 1];
   const unsigned lane = threadIdx.x & 31u;
+  const unsigned nl = PHOTON ? 1u : (NLT > 0 ? (unsigned)NLT : (unsigned)S.num_lights);
   unsigned n_hit = 0, n_knn = 0;
   unsigned long long n_visits = 0;
 
@@ -745,37 +777,52 @@ __global__ void __launch_bounds__(kBlock, PHOTON ? 6 : RT_SHADE_MINB) k_shade(co
       n_hit++;
       int pixel, sample;
       Rng g;
-      g.init(path_stream_key(A, p, pixel, sample), 4u + (PHOTON ? 4u : 10u) * (unsigned)seg);
-      float3 nrm, P;
+      // words consumed before this segment: 4 (jitter), then per earlier segment 2 per light + 4 (hemisphere);
+      // the photon gather draws nothing (Renderer.cpp:63-104)
+      g.init(path_stream_key(A, p, pixel, sample),
+             4u + (PHOTON ? 4u : 2u * (unsigned)S.num_lights + 4u) * (unsigned)seg);
+      float3 nrm, P, tp0, te1, te2;
       int mesh;
-      hit_geometry(S, h, nrm, P, mesh);
+      hit_geometry(S, h, nrm, P, mesh, tp0, te1, te2);
       const DMaterial m = S.mats[mesh];
       A.hit_path[j] = (int)p;
       if (PHOTON) {
         n_knn++;
-        float3 c = shade_photon(S, d, nrm, P, m, A.k, A.num_photons, A.knn_exact, s_knn + threadIdx.x,
-                                (int*)(s_knn + A.k * kBlock) + threadIdx.x, n_visits);
-        A.contrib[shadow_slot(j, 0)] = make_float4(c.x, c.y, c.z, 0.f);
-        A.occ[shadow_slot(j, 0)] = 0;
-        for (unsigned l = 1; l < (unsigned)kShadowLights; l++) A.occ[shadow_slot(j, l)] = 1;
+        unsigned long long* sc;
+        int ks;
+        int* kst;
+        if (GSC) {
+          sc = A.knn_scratch + (size_t)blockIdx.x * kBlock + threadIdx.x;
+          ks = A.knn_scratch_stride;
+          kst = (int*)s_knn + threadIdx.x;
+        } else {
+          sc = s_knn + threadIdx.x;
+          ks = kBlock;
+          kst = (int*)(s_knn + A.k * kBlock) + threadIdx.x;
+        }
+        float3 c = shade_photon(S, d, nrm, P, m, A.k, A.num_photons, A.knn_exact, sc, ks, kst, n_visits);
+        A.contrib[j] = make_float4(c.x, c.y, c.z, 0.f);  // nl == 1: slot(j, 0) = j; no shadow ray, no occlusion byte
       } else {
         // Renderer.cpp:49-60: per light 2 uniforms, the shadow ray, and (eagerly) radiance * bsdf
         const BsdfFrame bf = bsdf_frame(m, nrm, v_neg(d));
+        A.hit_p[j] = make_float4(P.x, P.y, P.z, 0.f);
 #pragma unroll
-        for (int l = 0; l < kShadowLights; l++) {
-          const unsigned s = shadow_slot(j, l);
-          if (l < S.num_lights) {
-            const DLight& L = S.lights[l];
-            float3 to_light = v_sub(light_rand_area_position(L, g), P);
-            float3 c = v_mul(light_evaluate(L, P), evaluate_color_response(m, bf, to_light));
-            A.sh_o[s] = make_float4(P.x, P.y, P.z, 0.f);
-            A.sh_d[s] = make_float4(to_light.x, to_light.y, to_light.z, 0.f);
-            A.contrib[s] = make_float4(c.x, c.y, c.z, 0.f);
-          } else {  // fewer than 3 lights: a ray that cannot hit anything, contribution dropped by occ
-            A.sh_o[s] = make_float4(P.x, P.y, P.z, 0.f);
-            A.sh_d[s] = make_float4(0.f, 0.f, 0.f, 0.f);
-            A.contrib[s] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int l = 0; l < (NLT > 0 ? NLT : (int)nl); l++) {
+          const unsigned s = shadow_slot(j, (unsigned)l, nl);
+          const DLight& L = light_at(S, l);
+          float3 to_light = v_sub(light_rand_area_position(L, g), P);
+          float3 c = v_mul(light_evaluate(L, P), evaluate_color_response(m, bf, to_light));
+          // Any-hit is an OR over all triangles (Renderer.cpp:52-55, RayTracer.h:40), so testing the triangle the ray
+          // starts on first cannot change the answer: 12-15 % of the shadow rays end here (shadow acne is part of
+          // the reference image), at this kernel's ~97 % lane use instead of the traversal's ~65 %.
+          bool self = false;
+          if (A.own_tri) {
+            float tu, tv, tt;
+            self = mt_intersect(P, to_light, tp0, te1, te2, tu, tv, tt) && tt > 0.f && tt < FLT_MAX;
           }
+          A.sh_d[s] = make_float4(to_light.x, to_light.y, to_light.z, self ? 1.f : 0.f);
+          A.contrib[s] = make_float4(c.x, c.y, c.z, 0.f);
+          if (self) A.occ[s] = 1;
         }
       }
       if (MODE == 1 && seg < 2) {  // Renderer.cpp:164-166: bounce
@@ -798,45 +845,66 @@ __global__ void __launch_bounds__(kBlock, PHOTON ? 6 : RT_SHADE_MINB) k_shade(co
   if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(A.counters + kCntNearest, (unsigned long long)n);
 }
 
+template <int MODE, bool GSC>
+static int shade_photon_occupancy(size_t sm) {
+  int occ = 0;
+  cudaFuncSetAttribute(k_shade<MODE, true, 0, GSC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_shade<MODE, true, 0, GSC>, kBlock, sm);
+  return occ < 1 ? 1 : occ;
+}
+int shade_photon_ctas_per_sm(int mode, int k, int kd_frames) {
+  const size_t sm = knn_smem_bytes(k, kd_frames);
+  const bool g = k > kKnnSharedMaxK;
+  if (mode == 0) return g ? shade_photon_occupancy<0, true>(sm) : shade_photon_occupancy<0, false>(sm);
+  return g ? shade_photon_occupancy<1, true>(sm) : shade_photon_occupancy<1, false>(sm);
+}
+
 void launch_shade(const RenderArgs& a, int seg, int grid, cudaStream_t st) {
-  const size_t sm = a.photon ? knn_smem_bytes(a.k, a.kd_frames) : 0;
   if (a.photon) {
-    cudaFuncSetAttribute(k_shade<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-    cudaFuncSetAttribute(k_shade<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    const size_t sm = knn_smem_bytes(a.k, a.kd_frames);
     // grid-stride kernel: launch exactly what is resident (the k-NN shared memory allows 6 CTAs/SM at k = 10, 2 at
     // k = 50; 8 per SM left a third of the CTAs for a second, mostly empty wave -- 26 % warps active in ncu)
-    int occ = 0;
-    if (a.mode == 0)
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_shade<0, true>, kBlock, sm);
-    else
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_shade<1, true>, kBlock, sm);
-    if (occ > 0 && a.num_sms > 0) grid = grid < a.num_sms * occ ? grid : a.num_sms * occ;
+    const int occ = shade_photon_ctas_per_sm(a.mode, a.k, a.kd_frames);
+    if (a.num_sms > 0) grid = grid < a.num_sms * occ ? grid : a.num_sms * occ;
+    const bool g = a.k > kKnnSharedMaxK;
+    if (g && (size_t)grid * kBlock > (size_t)a.knn_scratch_stride) grid = a.knn_scratch_stride / kBlock;
+    if (a.mode == 0) {
+      if (g) k_shade<0, true, 0, true><<<grid, kBlock, sm, st>>>(a, seg);
+      else k_shade<0, true, 0, false><<<grid, kBlock, sm, st>>>(a, seg);
+    } else {
+      if (g) k_shade<1, true, 0, true><<<grid, kBlock, sm, st>>>(a, seg);
+      else k_shade<1, true, 0, false><<<grid, kBlock, sm, st>>>(a, seg);
+    }
+    return;
   }
+  const bool three = a.scene.num_lights == 3;
   if (a.mode == 0) {
-    if (a.photon)
-      k_shade<0, true><<<grid, kBlock, sm, st>>>(a, seg);
-    else
-      k_shade<0, false><<<grid, kBlock, 0, st>>>(a, seg);
+    if (three) k_shade<0, false, 3, false><<<grid, kBlock, 0, st>>>(a, seg);
+    else k_shade<0, false, 0, false><<<grid, kBlock, 0, st>>>(a, seg);
   } else {
-    if (a.photon)
-      k_shade<1, true><<<grid, kBlock, sm, st>>>(a, seg);
-    else
-      k_shade<1, false><<<grid, kBlock, 0, st>>>(a, seg);
+    if (three) k_shade<1, false, 3, false><<<grid, kBlock, 0, st>>>(a, seg);
+    else k_shade<1, false, 0, false><<<grid, kBlock, 0, st>>>(a, seg);
   }
 }
 
 // ----------------------------------------------------------------------------------------------
-// k_combine: colorResponse = ((0 + a0) + a1) + a2 over the unoccluded lights (Renderer.cpp:44,49-60),
-// then the path sum c0 + (c1 + c2) and the per-sample clamp (Renderer.cpp:168,254)
+// k_combine: colorResponse = ((0 + a0) + a1) + a2 ... over the unoccluded lights in scene order
+// (Renderer.cpp:44,49-60), then the path sum c0 + (c1 + c2) and the per-sample clamp (Renderer.cpp:168,254)
 // ----------------------------------------------------------------------------------------------
+template <int NLT>
 __global__ void __launch_bounds__(256) k_combine(const RenderArgs A, const int seg) {
   const unsigned n = A.q_count[kQHits0 + seg];
+  const unsigned nl = NLT > 0 ? (unsigned)NLT : (unsigned)A.nl;
   for (unsigned j = blockIdx.x * 256 + threadIdx.x; j < n; j += gridDim.x * 256) {
     float3 c = f3(0.f, 0.f, 0.f);
+    if (A.photon) {
+      c = v_add(c, f3(A.contrib[j]));
+    } else {
 #pragma unroll
-    for (int l = 0; l < kShadowLights; l++) {
-      const unsigned s = shadow_slot(j, l);
-      if (A.occ[s] == 0 && (A.photon || l < A.scene.num_lights)) c = v_add(c, f3(A.contrib[s]));
+      for (int l = 0; l < (NLT > 0 ? NLT : (int)nl); l++) {
+        const unsigned s = shadow_slot(j, (unsigned)l, nl);
+        if (A.occ[s] == 0) c = v_add(c, f3(A.contrib[s]));
+      }
     }
     const unsigned p = (unsigned)A.hit_path[j];
     if (seg == 0) {
@@ -851,7 +919,12 @@ __global__ void __launch_bounds__(256) k_combine(const RenderArgs A, const int s
     }
   }
 }
-void launch_combine(const RenderArgs& a, int seg, int grid, cudaStream_t st) { k_combine<<<grid, 256, 0, st>>>(a, seg); }
+void launch_combine(const RenderArgs& a, int seg, int grid, cudaStream_t st) {
+  if (!a.photon && a.nl == 3)
+    k_combine<3><<<grid, 256, 0, st>>>(a, seg);
+  else
+    k_combine<0><<<grid, 256, 0, st>>>(a, seg);
+}
 
 // ----------------------------------------------------------------------------------------------
 // ordered accumulation: updateImage(x,y) += colorResponse for samples in index order
@@ -889,6 +962,34 @@ __global__ void k_scatter(const float4* __restrict__ acc_rgb, const int* __restr
 void launch_scatter(const float4* acc_rgb, const int* acc_cnt, const int* pix_map, int npix, float* out_rgb,
                     int* out_cnt, cudaStream_t st) {
   k_scatter<<<(npix + 255) / 256, 256, 0, st>>>(acc_rgb, acc_cnt, pix_map, npix, out_rgb, out_cnt);
+}
+
+__global__ void k_scatter_packed(const float4* __restrict__ acc_rgb, const int* __restrict__ acc_cnt,
+                                 const int* __restrict__ pix_map, int npix, float4* out) {
+  int pl = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pl >= npix) return;
+  const float4 a = acc_rgb[pl];
+  out[pix_map[pl]] = make_float4(a.x, a.y, a.z, (float)acc_cnt[pl]);  // counts < 2^24 are exact in binary32
+}
+void launch_scatter_packed(const float4* acc_rgb, const int* acc_cnt, const int* pix_map, int npix, float4* out,
+                           cudaStream_t st) {
+  k_scatter_packed<<<(npix + 255) / 256, 256, 0, st>>>(acc_rgb, acc_cnt, pix_map, npix, out);
+}
+// Renderer.cpp:262-265 on the packed frame: the counter arrives as a float holding an exact integer
+__global__ void k_composite_packed(const float4* __restrict__ sum_rgbn, long long npx, int num_rays, float* rgb_inout) {
+  const long long px = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (px >= npx) return;
+  const float4 a = sum_rgbn[px];
+  const float fn = (float)num_rays, miss = (float)(num_rays - (int)a.w);
+  const float s[3] = {a.x, a.y, a.z};
+#pragma unroll
+  for (int ch = 0; ch < 3; ch++) {
+    const float bg = rgb_inout[3 * px + ch];
+    rgb_inout[3 * px + ch] = __fadd_rn(__fdiv_rn(s[ch], fn), __fdiv_rn(__fmul_rn(bg, miss), fn));
+  }
+}
+void launch_composite_packed(const float4* sum_rgbn, long long npx, int num_rays, float* rgb_inout, cudaStream_t st) {
+  k_composite_packed<<<(unsigned)((npx + 255) / 256), 256, 0, st>>>(sum_rgbn, npx, num_rays, rgb_inout);
 }
 
 // Renderer.cpp:262-265 after the last pass (i + 1 == N), on the pixels this shard owns:
@@ -946,29 +1047,55 @@ void launch_bsdf(DMaterial m, const float* n_wi_wo, long long n, float* rgb, cud
   k_bsdf<<<(int)((n + 127) / 128), 128, 0, st>>>(m, n_wi_wo, n, rgb);
 }
 
+template <bool GSC>
 __global__ void __launch_bounds__(kBlock) k_knn(const DScene S, const float* __restrict__ q3, long long n, int k,
-                                                int exact, int* node_index, unsigned long long* counters) {
+                                                int exact, int* node_index, unsigned long long* counters,
+                                                unsigned long long* scratch) {
   extern __shared__ unsigned long long s_knn[];
-  long long i = (long long)blockIdx.x * kBlock + threadIdx.x;
-  if (i >= n) return;
-  unsigned long long* sc = s_knn + threadIdx.x;
-  unsigned long long visits = 0;
-  const float3 q = f3(q3[3 * i], q3[3 * i + 1], q3[3 * i + 2]);
-  if (exact > 0)
-    kd_knearest_exact(S, q, k, sc, (int*)(s_knn + k * kBlock) + threadIdx.x, kBlock, visits);
-  else if (exact < 0)
-    kd_knearest_heap(S, q, k, sc, (int*)(s_knn + k * kBlock) + threadIdx.x, kBlock, visits);
-  else if (kd_knearest_sorted(S, q, k, sc, (int*)(s_knn + k * kBlock) + threadIdx.x, kBlock, visits))
-    knn_exact_redo(S, q, k, sc, kBlock);
-  for (int j = 0; j < k; j++) node_index[i * k + j] = kd_index_of(sc[j * kBlock]);
-  atomicAdd(counters + kCntKdVisits, visits);
-  atomicAdd(counters + kCntKnn, 1ull);
+  unsigned long long* sc;
+  int cs;
+  int* kst;
+  if (GSC) {  // k > kKnnSharedMaxK: candidates in global memory, [slot][resident thread]
+    sc = scratch + (size_t)blockIdx.x * kBlock + threadIdx.x;
+    cs = (int)(gridDim.x * kBlock);
+    kst = (int*)s_knn + threadIdx.x;
+  } else {
+    sc = s_knn + threadIdx.x;
+    cs = kBlock;
+    kst = (int*)(s_knn + k * kBlock) + threadIdx.x;
+  }
+  unsigned long long visits = 0, queries = 0;
+  for (long long i = (long long)blockIdx.x * kBlock + threadIdx.x; i < n; i += (long long)gridDim.x * kBlock) {
+    const float3 q = f3(q3[3 * i], q3[3 * i + 1], q3[3 * i + 2]);
+    knn_query(S, q, k, exact, sc, cs, kst, visits);
+    for (int j = 0; j < k; j++) node_index[i * k + j] = kd_index_of(sc[(unsigned)j * (unsigned)cs]);
+    queries++;
+  }
+  if (queries) {
+    atomicAdd(counters + kCntKdVisits, visits);
+    atomicAdd(counters + kCntKnn, queries);
+  }
+}
+int knn_ctas_per_sm(int k, int kd_frames) {
+  const size_t sm = knn_smem_bytes(k, kd_frames);
+  int occ = 0;
+  if (k > kKnnSharedMaxK) {
+    cudaFuncSetAttribute(k_knn<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_knn<true>, kBlock, sm);
+  } else {
+    cudaFuncSetAttribute(k_knn<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_knn<false>, kBlock, sm);
+  }
+  return occ < 1 ? 1 : occ;
 }
 void launch_knn(const DScene& s, const float* q3, long long n, int k, int kd_frames, int exact, int* node_index,
-                unsigned long long* counters, cudaStream_t st) {
+                unsigned long long* counters, unsigned long long* scratch, int grid, cudaStream_t st) {
   const size_t sm = knn_smem_bytes(k, kd_frames);
-  cudaFuncSetAttribute(k_knn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-  k_knn<<<(int)((n + kBlock - 1) / kBlock), kBlock, sm, st>>>(s, q3, n, k, exact, node_index, counters);
+  if (grid < 1) grid = 1;
+  if (k > kKnnSharedMaxK)
+    k_knn<true><<<grid, kBlock, sm, st>>>(s, q3, n, k, exact, node_index, counters, scratch);
+  else
+    k_knn<false><<<grid, kBlock, sm, st>>>(s, q3, n, k, exact, node_index, counters, scratch);
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -986,7 +1113,7 @@ __global__ void __launch_bounds__(kBlock) k_emit(const DScene S, uint64_t seed_m
   for (long long q = (long long)blockIdx.x * kBlock + threadIdx.x; q < total; q += (long long)gridDim.x * kBlock) {
     const int li = (int)(q / npaths);
     const int path = first_path + (int)(q - (long long)li * npaths);
-    const DLight& L = S.lights[li];
+    const DLight& L = light_at(S, li);
     Rng g;
     g.init(stream_key(seed_mixed, kDomainPhoton, (uint64_t)li * (uint64_t)per_light + (uint64_t)path), 0);
     float3 o = light_rand_area_position(L, g);

@@ -15,14 +15,26 @@ enum QSlot { kQHits0 = 0, kQFetchNearest0 = 4, kQFetchAny0 = 8, kQNum = 12 };
 
 // Shadow rays / light contributions of compacted hit j live in a light-major blocked layout so that a
 // warp of the any-hit kernel gets 32 consecutive hit points aiming at ONE light (coherent rays):
-//   slot(j, l) = (j / 32) * 96 + l * 32 + (j % 32)            (3 lights per hit, kShadowLights)
-constexpr int kShadowLights = 3;
-__host__ __device__ __forceinline__ unsigned shadow_slot(unsigned j, unsigned l) {
-  return (j >> 5) * (32u * kShadowLights) + l * 32u + (j & 31u);
+//   slot(j, l) = (j / 32) * 32*nl + l * 32 + (j % 32)
+// nl = shadow slots per hit: the scene's light count for direct lighting (Renderer.cpp:49 loops over
+// scene.lightsources() of any length), 1 for the photon gather (one contribution, no shadow ray).
+__host__ __device__ __forceinline__ unsigned shadow_slot(unsigned j, unsigned l, unsigned nl) {
+  return (j >> 5) * (32u * nl) + l * 32u + (j & 31u);
 }
-__host__ __device__ __forceinline__ unsigned shadow_slots_for(unsigned hits) {
-  return ((hits + 31u) >> 5) * (32u * kShadowLights);
+__host__ __device__ __forceinline__ size_t shadow_slots_for(size_t hits, unsigned nl) {
+  return ((hits + 31u) >> 5) * (size_t)(32u * nl);
 }
+// hit index j of shadow slot s (inverse of shadow_slot over l)
+__host__ __device__ __forceinline__ unsigned shadow_slot_hit(unsigned s, unsigned nl) {
+  return (s / (32u * nl)) * 32u + (s & 31u);
+}
+
+// Kernel classes timed separately with CUDA events on the launching stream (rt_stats::kernel_ms): bench.py
+// picks the dominant one by its measured share of the step.
+enum KernelClass {
+  kKRaygen = 0, kKTraceNearest = 1, kKSort = 2, kKShade = 3, kKTraceAny = 4, kKCombine = 5, kKResolve = 6,
+  kKEmit = 7, kKOther = 8, kKNumClasses = 9
+};
 
 // One wavefront batch = `nsamp` consecutive samples of `npix` pixels; path p = s_local*npix + pixel_local.
 struct RenderArgs {
@@ -49,8 +61,10 @@ struct RenderArgs {
   float4* ray_o[2];  // ray queues, ping-pong by segment: (origin, path id) / (direction, -)
   float4* ray_d[2];
   float4* hit;       // per ray slot of the current segment: (t, u, v, triangle id | -1)
-  float4* sh_o;      // shadow rays, blocked layout (see shadow_slot)
-  float4* sh_d;
+  int nl;            // shadow slots per hit (see shadow_slot): number of lights, or 1 for the photon gather
+  int own_tri;       // 1: k_shade tests a shadow ray against the triangle it starts on before queueing it
+  float4* hit_p;     // per compacted hit j: the hit point = origin of its nl shadow rays
+  float4* sh_d;      // shadow ray directions, blocked layout (see shadow_slot); w != 0: already known occluded
   float4* contrib;   // radiance * bsdf of light l for hit j, same layout
   unsigned char* occ;  // any-hit result, same layout
   int* hit_path;     // compacted hit j -> path id
@@ -65,7 +79,11 @@ struct RenderArgs {
   float3 sort_inv_cell;      // kSortGrid / extent per axis
   unsigned int* q_count;
   unsigned long long* counters;
+  // k > kKnnSharedMaxK: the k-NN candidates of every resident thread live in global memory, [slot][thread]
+  unsigned long long* knn_scratch;
+  int knn_scratch_stride;  // threads the scratch was sized for (grid of the k-NN kernel * kBlock)
 };
+constexpr int kKnnSharedMaxK = 64;  // up to here the candidate rows fit in shared memory (2 CTAs/SM at 64)
 
 #ifndef RT_SORT_GRID
 #define RT_SORT_GRID 32
@@ -84,6 +102,10 @@ size_t trace_smem_bytes(int stack_depth);
 void launch_resolve(const float4* col0, int npix, int nsamp, float4* acc_rgb, int* acc_cnt, cudaStream_t st);
 void launch_scatter(const float4* acc_rgb, const int* acc_cnt, const int* pix_map, int npix, float* out_rgb,
                     int* out_cnt, cudaStream_t st);
+// sums + counter as one float4 per pixel (one reduce across GPUs instead of two)
+void launch_scatter_packed(const float4* acc_rgb, const int* acc_cnt, const int* pix_map, int npix, float4* out,
+                           cudaStream_t st);
+void launch_composite_packed(const float4* sum_rgbn, long long npx, int num_rays, float* rgb_inout, cudaStream_t st);
 // the final composite over the background on the device (rt_render): rgb_inout holds the background on entry
 void launch_composite_frame(const float* sum_rgb, const int* counter, long long npx, int num_rays, float* rgb_inout,
                             cudaStream_t st);
@@ -93,11 +115,14 @@ void launch_composite(const float4* acc_rgb, const int* acc_cnt, const int* pix_
 void launch_trace_rays(const DScene& s, const float4* ro, const float4* rd, unsigned n, float4* hits,
                        unsigned char* occluded, int any, int brute, int stack_depth, unsigned* fetch_counter,
                        int grid_ctas, cudaStream_t st);
+int shade_photon_ctas_per_sm(int mode, int k, int kd_frames);  // resident CTAs of the k-NN shade kernel
 void launch_bsdf(DMaterial m, const float* n_wi_wo, long long n, float* rgb, cudaStream_t st);
 // photon emission: path q = light*npaths + j traces path (first_path + j) of `light`
 void launch_emit(const DScene& s, uint64_t seed_mixed, int per_light, float light_pdf, int first_path, int npaths,
                  int brute, float4* out_a, float4* out_b, unsigned long long* counters, cudaStream_t st);
+// scratch: knn candidates in global memory when k > kKnnSharedMaxK (k * 8 bytes per thread of `grid_ctas` CTAs)
 void launch_knn(const DScene& s, const float* q3, long long n, int k, int kd_frames, int exact, int* node_index,
-                unsigned long long* counters, cudaStream_t st);
+                unsigned long long* counters, unsigned long long* scratch, int grid_ctas, cudaStream_t st);
+int knn_ctas_per_sm(int k, int kd_frames);
 
 }  // namespace rtb

@@ -172,11 +172,11 @@ struct DCamera {  // Camera.h:34-40
   float3 position, lower_left, horizontal, vertical;
 };
 
-constexpr int kMaxLights = 8;
+constexpr int kMaxLights = 8;     // lights kept in kernel-parameter space; further ones are read from lights_ext
 constexpr int kMaxRoots = 16;    // scenes with more meshes than this enter through the top-level tree
 constexpr int kStackDepth = 40;  // BVH traversal stack entries per ray (host checks bvh depth <= this)
 constexpr int kBlock = 128;      // threads per CTA of the wavefront kernels
-constexpr int kMaxK = 64;
+constexpr int kMaxK = 64;        // largest k of the ascending-array k-NN (its tie fallback keeps k candidates in local memory)
 constexpr int kKdStack = 32;     // kd-tree recursion depth bound (host checks)
 
 struct DScene {
@@ -187,6 +187,7 @@ struct DScene {
   const float4* __restrict__ nrm;       // per vertex
   const DMaterial* __restrict__ mats;   // per mesh
   DLight lights[kMaxLights];
+  const DLight* __restrict__ lights_ext;  // lights kMaxLights, kMaxLights+1, ... (device memory); null when <= kMaxLights
   int num_lights;
   int num_tris;
   DCamera cam;
@@ -203,6 +204,8 @@ struct HitRec {
   float t, u, v;
   int gid;  // global triangle index, scene order
 };
+// light l of the scene (Scene::lightsources()[l], any count: Renderer.cpp:49, PhotonMap.h:24)
+RT_DI const DLight& light_at(const DScene& S, int l) { return l < kMaxLights ? S.lights[l] : S.lights_ext[l - kMaxLights]; }
 
 // ------------------------------------------------------------------------------------------------
 // Ray.cpp:9-24  Moller-Trumbore with the absolute epsilon on det.  e1/e2 are the host-precomputed
@@ -446,14 +449,24 @@ RT_DI float3 normalize_color(float3 c) {
 }
 
 // Renderer.cpp:36,42-43,274-277: hit normal and hit point from barycentrics (w*A + u*B) + v*C
-RT_DI void hit_geometry(const DScene& S, const HitRec& h, float3& n, float3& P, int& mesh) {
+// The variant with p0/e1/e2 also returns the hit triangle in the form mt_intersect takes (Ray.cpp:11: e1 = p1 - p0,
+// e2 = p2 - p0, the same binary32 subtractions the traversal's triangle array holds).
+RT_DI void hit_geometry(const DScene& S, const HitRec& h, float3& n, float3& P, int& mesh, float3& p0, float3& e1,
+                        float3& e2) {
   int4 vi = __ldg(S.tri_vidx + h.gid);
   mesh = vi.w;
   float w = __fsub_rn(__fsub_rn(1.f, h.u), h.v);
   float3 n0 = f3(__ldg(S.nrm + vi.x)), n1 = f3(__ldg(S.nrm + vi.y)), n2 = f3(__ldg(S.nrm + vi.z));
-  float3 p0 = f3(__ldg(S.pos + vi.x)), p1 = f3(__ldg(S.pos + vi.y)), p2 = f3(__ldg(S.pos + vi.z));
+  p0 = f3(__ldg(S.pos + vi.x));
+  float3 p1 = f3(__ldg(S.pos + vi.y)), p2 = f3(__ldg(S.pos + vi.z));
   n = v_norm(v_add(v_add(v_scl(n0, w), v_scl(n1, h.u)), v_scl(n2, h.v)));
   P = v_add(v_add(v_scl(p0, w), v_scl(p1, h.u)), v_scl(p2, h.v));
+  e1 = v_sub(p1, p0);
+  e2 = v_sub(p2, p0);
+}
+RT_DI void hit_geometry(const DScene& S, const HitRec& h, float3& n, float3& P, int& mesh) {
+  float3 p0, e1, e2;
+  hit_geometry(S, h, n, P, mesh, p0, e1, e2);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -627,23 +640,23 @@ RT_DI unsigned long long kd_pack(float d, int idx) {  // distances are >= 0: the
 RT_DI float kd_dist_of(unsigned long long c) { return __uint_as_float((unsigned)(c >> 32)); }
 RT_DI int kd_index_of(unsigned long long c) { return (int)(unsigned)c; }
 
-// sc: k candidate slots (distance bits << 32 | node index, one 64-bit shared-memory access per move),
-// kst: 3 ints per frame (far begin, far end | next axis << 28, threshold bits); stride ks between a thread's slots.
-RT_DI bool kd_knearest_sorted(const DScene& S, float3 q, int k, unsigned long long* sc, int* kst, int ks,
+// sc: k candidate slots (distance bits << 32 | node index, one 64-bit access per move), stride cs between a thread's
+// slots; kst: 3 ints per frame (far begin, far end | next axis << 28, threshold bits), stride ks.
+RT_DI bool kd_knearest_sorted(const DScene& S, float3 q, int k, unsigned long long* sc, int cs, int* kst, int ks,
                               unsigned long long& visits) {
   bool tie = false;
   for (int j = 0; j < k; j++) {  // kdtree.h:186: the first k nodes of the array seed the candidates
     const unsigned dj = __float_as_uint(v_dist(f3(__ldg(S.kd_pos + j)), q));
     int m = j - 1;
     unsigned long long w = 0;
-    while (m >= 0 && (unsigned)((w = sc[m * ks]) >> 32) > dj) {
-      sc[(m + 1) * ks] = w;
+    while (m >= 0 && (unsigned)((w = sc[(unsigned)(m) * (unsigned)cs]) >> 32) > dj) {
+      sc[(unsigned)(m + 1) * (unsigned)cs] = w;
       m--;
     }
     if (m >= 0 && (unsigned)(w >> 32) == dj) tie = true;
-    sc[(m + 1) * ks] = ((unsigned long long)dj << 32) | (unsigned)j;
+    sc[(unsigned)(m + 1) * (unsigned)cs] = ((unsigned long long)dj << 32) | (unsigned)j;
   }
-  float best = kd_dist_of(sc[(k - 1) * ks]);  // m_bestdist (a distance, not squared)
+  float best = kd_dist_of(sc[(unsigned)(k - 1) * (unsigned)cs]);  // m_bestdist (a distance, not squared)
   int sp = 0, b = 0, e = S.kd_count, axis = 0;
   unsigned nv = 0;
   while (e > b) {
@@ -654,17 +667,17 @@ RT_DI bool kd_knearest_sorted(const DScene& S, float3 q, int k, unsigned long lo
     if (dnode < best) {
       // evict the largest; m_bestdist = the largest of the rest BEFORE the insertion (k == 1: libstdc++'s
       // front() after pop_heap is the evicted candidate itself), kdtree.h:93-96
-      best = kd_dist_of(sc[(k > 1 ? k - 2 : 0) * ks]);
+      best = kd_dist_of(sc[(unsigned)(k > 1 ? k - 2 : 0) * (unsigned)cs]);
       const unsigned dn = __float_as_uint(dnode);
       int m = k - 2;
       unsigned long long w = 0;
-      while (m >= 0 && (unsigned)((w = sc[m * ks]) >> 32) > dn) {
-        sc[(m + 1) * ks] = w;
+      while (m >= 0 && (unsigned)((w = sc[(unsigned)(m) * (unsigned)cs]) >> 32) > dn) {
+        sc[(unsigned)(m + 1) * (unsigned)cs] = w;
         m--;
       }
       // a tie with the evicted largest (old slot k-1) cannot matter: dnode < best <= it
       if (m >= 0 && (unsigned)(w >> 32) == dn) tie = true;
-      sc[(m + 1) * ks] = ((unsigned long long)dn << 32) | (unsigned)n;
+      sc[(unsigned)(m + 1) * (unsigned)cs] = ((unsigned long long)dn << 32) | (unsigned)n;
     }
     int nb = b, ne = b;  // empty
     if (best != 0.f) {   // kdtree.h:101: best == 0 returns without visiting the children
@@ -723,8 +736,8 @@ RT_DI bool kd_knearest_sorted(const DScene& S, float3 q, int k, unsigned long lo
 struct KdHeapP {
   unsigned long long* a;
   int hs;
-  RT_DI unsigned long long get(int j) const { return a[j * hs]; }
-  RT_DI void set(int j, unsigned long long w) { a[j * hs] = w; }
+  RT_DI unsigned long long get(int j) const { return a[(unsigned)j * (unsigned)hs]; }
+  RT_DI void set(int j, unsigned long long w) { a[(unsigned)j * (unsigned)hs] = w; }
   RT_DI static bool less(unsigned long long x, unsigned long long y) { return (unsigned)(x >> 32) < (unsigned)(y >> 32); }
   RT_DI void push_up(int hole, int top, unsigned long long v) {  // std::__push_heap
     int parent = (hole - 1) / 2;
@@ -779,9 +792,9 @@ struct KdHeapP {
     }
   }
 };
-RT_DI void kd_knearest_heap(const DScene& S, float3 q, int k, unsigned long long* sc, int* kst, int ks,
+RT_DI void kd_knearest_heap(const DScene& S, float3 q, int k, unsigned long long* sc, int cs, int* kst, int ks,
                             unsigned long long& visits) {
-  KdHeapP H{sc, ks};
+  KdHeapP H{sc, cs};
   for (int j = 0; j < k; j++) H.set(j, kd_pack(v_dist(f3(__ldg(S.kd_pos + j)), q), j));  // kdtree.h:186
   H.make(k);
   float best = kd_dist_of(H.get(0));  // m_bestdist
@@ -842,7 +855,7 @@ RT_DI void kd_knearest_heap(const DScene& S, float3 q, int k, unsigned long long
 // distance itself: a far side is skipped when every photon behind the plane is strictly farther than it.
 // Candidates are the same packed (distance bits << 32 | index) words, whose integer order IS (distance, index).
 // ------------------------------------------------------------------------------------------------
-RT_DI void kd_knearest_exact(const DScene& S, float3 q, int k, unsigned long long* sc, int* kst, int ks,
+RT_DI void kd_knearest_exact(const DScene& S, float3 q, int k, unsigned long long* sc, int cs, int* kst, int ks,
                              unsigned long long& visits) {
   int cnt = 0;
   unsigned long long worst = ~0ull;  // packed k-th candidate; all-ones while fewer than k are held
@@ -856,13 +869,13 @@ RT_DI void kd_knearest_exact(const DScene& S, float3 q, int k, unsigned long lon
     if (cand < worst) {
       int m = (cnt < k ? cnt : k - 1) - 1;  // last slot that stays
       unsigned long long w = 0;
-      while (m >= 0 && (w = sc[m * ks]) > cand) {
-        sc[(m + 1) * ks] = w;
+      while (m >= 0 && (w = sc[(unsigned)(m) * (unsigned)cs]) > cand) {
+        sc[(unsigned)(m + 1) * (unsigned)cs] = w;
         m--;
       }
-      sc[(m + 1) * ks] = cand;
+      sc[(unsigned)(m + 1) * (unsigned)cs] = cand;
       if (cnt < k) cnt++;
-      if (cnt == k) worst = sc[(k - 1) * ks];
+      if (cnt == k) worst = sc[(unsigned)(k - 1) * (unsigned)cs];
     }
     float pa = p.x, qa = q.x;
     if (axis == 1) pa = p.y, qa = q.y;

@@ -42,7 +42,14 @@ def test_struct_layouts_match_the_header():
     assert C.sizeof(_capi.rt_material) == 32 and C.sizeof(_capi.rt_light) == 84 and C.sizeof(_capi.rt_camera) == 48
     assert C.sizeof(_capi.rt_params) == 64 and _capi.rt_params.seed.offset == 24
     assert C.sizeof(_capi.rt_scene) == 16 + 7 * 8 + 48
-    assert _capi.rt_stats.device_ms.offset == 64 and C.sizeof(_capi.rt_stats) == 136
+    assert _capi.rt_stats.device_ms.offset == 64 and C.sizeof(_capi.rt_stats) == 136 + 2 * 8 * len(_capi.KERNEL_CLASSES)
+    # ... and the library's own sizeof of every struct (rt_abi_sizes) agrees with the ctypes mirrors
+    sizes = np.zeros(9, np.int32)
+    assert _capi.load().rt_abi_sizes(_capi.ptr(sizes), 9) == 0
+    ray, hit = np.dtype([("o", np.float32, 3), ("d", np.float32, 3)]), np.dtype([("t", np.int32), ("uvt", np.float32, 3)])
+    mirrors = [C.sizeof(_capi.rt_material), C.sizeof(_capi.rt_light), C.sizeof(_capi.rt_camera), C.sizeof(_capi.rt_scene),
+               C.sizeof(_capi.rt_params), ray.itemsize, hit.itemsize, 28, C.sizeof(_capi.rt_stats)]
+    assert sizes.tolist() == mirrors, (sizes.tolist(), mirrors)
 
 
 def test_no_cpu_fallback():
@@ -66,7 +73,7 @@ def test_parameter_validation():
     scene = rt.Scene.load(scene_path("stock"))
     cs = scene._as_c()
     ctx = C.c_void_p()
-    for kw, text in ((dict(width=0), "width"), (dict(num_photons=10, k=0), "k must"), (dict(num_photons=10, k=65), "k must"),
+    for kw, text in ((dict(width=0), "width"), (dict(num_photons=10, k=0), "k must"), (dict(num_photons=10, k=_capi.RT_MAX_K + 1), "k must"),
                      (dict(shard_count=2, shard_rank=2), "shard_rank"), (dict(num_rays=4, sample_first=3, sample_count=2), "sample")):
         base = dict(width=8, height=8, num_rays=1, mode=0)
         base.update(kw)
