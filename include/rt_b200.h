@@ -230,6 +230,17 @@ int rt_photons_per_light(const rt_ctx* ctx, int32_t* out);
 int rt_emit_photons(rt_ctx* ctx, int32_t first_path, int32_t num_paths, rt_photon* out, int64_t capacity,
                     int64_t* per_light_counts, int32_t* depth_histogram20);
 int rt_set_photons(rt_ctx* ctx, const rt_photon* photons, int64_t n);
+/* The same with the particles staying in DEVICE memory of ctx's GPU (7 floats each, Particle's layout), for the
+ * multi-GPU path: every rank emits its share (rt_emit_photons_device: stored particles compacted on the device in
+ * (light, path) order, per-light counts to the host), the shards are all-gathered with NCCL where they lie (rank r's
+ * shard at gathered_device + r*stride*7), rt_splice_photons_device rearranges them on the device into the order of the
+ * single-process list (counts[r*L + l] = particles of light l in rank r's shard), and rt_set_photons_device installs
+ * it with ONE device->host copy for the host kd-tree build (none in the device-built exact mode). */
+int rt_emit_photons_device(rt_ctx* ctx, int32_t first_path, int32_t num_paths, float* out7_device, int64_t capacity,
+                           int64_t* per_light_counts, int32_t* depth_histogram20);
+int rt_splice_photons_device(rt_ctx* ctx, const float* gathered_device, int32_t world, int64_t stride,
+                             const int64_t* counts, float* out7_device, int64_t capacity, int64_t* total);
+int rt_set_photons_device(rt_ctx* ctx, const float* photons7_device, int64_t n);
 int rt_build_photon_map(rt_ctx* ctx); /* emit all + set, as Renderer.cpp:209-213 */
 int rt_get_photons(rt_ctx* ctx, rt_photon* out, int64_t capacity, int64_t* count);
 /* kdtree::knearest (source/kdtree.h:87-107,180-195) for n query points (3 floats each): indices into
@@ -241,6 +252,10 @@ int rt_get_kdtree(rt_ctx* ctx, rt_photon* nodes, int32_t* left, int32_t* right, 
 /* Which pixels (y*W + x) a shard owns, in the order the wavefront processes them (pure host function,
  * needs no device): call with out = NULL to get the count. */
 int rt_shard_pixels(const rt_params* params, int32_t* out, int64_t capacity, int64_t* count);
+
+/* Tooling hook: cudaProfilerStart (on != 0) / cudaProfilerStop, so that `ncu --profile-from-start off` captures
+ * exactly the frames a script brackets (scripts/profile_frame.py). */
+int rt_profiler_range(int on);
 
 int rt_get_stats(rt_ctx* ctx, rt_stats* out);
 int rt_reset_stats(rt_ctx* ctx);

@@ -341,6 +341,45 @@ def converged_mean():
          mean_per_seed=mean_seed.astype(np.float32), seed_rmse=np.array(seed_rmse))
 
 
+def light_variants():
+    """Scenes with 1 and 5 light sources (Scene::lightsources() may hold any number: Scene.h:14-26, Renderer.cpp:49,
+    PhotonMap.h:19-24) and a k = 100 gather (kdtree::knearest accepts any k <= nodes, kdtree.h:180-183).  The light
+    bases come from the reference's own LightSource constructor; renders are the reference's, shared streams."""
+    ref = O.RefOracle()
+    base = ref.create_scene(420, 420)
+    extra = np.array([[0.9, 1.2, 0.4, 1.0, 0.9, 0.7, 0.0, 0.0, 0.0, 0.85, 0.05],
+                      [-0.7, 0.9, 1.2, 0.6, 0.8, 1.0, 0.1, 0.0, -0.2, 0.85, 0.02]], np.float32)
+    win = (100, 150, 228, 214)
+    for name, ctor in (("stock_1light", base.lights_ctor[2:3]), ("stock_5lights", np.concatenate([base.lights_ctor, extra]))):
+        flat = O.FlatScene(base.pos, base.nrm, base.tri, base.mesh_tri_off, base.mesh_vtx_off, base.mats,
+                           np.zeros((len(ctor), 21), np.float32), ctor, base.cam, 420, 420)
+        ref.set_scene(flat)
+        flat = ref.flatten(420, 420)  # bases as the reference's constructor computed them (LightSource.h:29-32)
+        flat.save(os.path.join(GOLD, "scenes", f"{name}.rtscene"))
+        ref.set_scene(flat)
+        out = {}
+        for mode, N in ((0, 1), (1, 3)):
+            r = ref.render(N, mode, SEED, window=win, want_samples=True)
+            out[f"samples_m{mode}"], out[f"found_m{mode}"] = r["samples"], r["found"]
+        pm = ref.photon_map_create(3000, SEED)
+        plist, hist = pm.get()
+        out["photons"], out["photon_hist"] = plist, hist
+        save(f"render_{name}_win.npz", window=np.array(win), **out)
+    # k = 100 on the stock scene's 3000-photon list: query results and a gather window
+    ref.create_scene(420, 420)
+    pm = ref.photon_map_create(3000, SEED)
+    plist, _ = pm.get()
+    g = np.random.default_rng(77)
+    q = np.concatenate([g.uniform(-1.5, 1.5, (300, 3)), plist[g.integers(0, len(plist), 100), :3]]).astype(np.float32)
+    out = dict(queries=q)
+    for k in (65, 100, 300):
+        res, _ = pm.knn(q, k)
+        out[f"knn_{k}"] = res[:, :, :3]
+    r = ref.render(1, 0, SEED, num_photons=3000, k=100, photon_map=pm, window=(100, 150, 164, 182), want_samples=True)
+    out["window"], out["samples_m0_k100"], out["found_m0_k100"] = np.array((100, 150, 164, 182)), r["samples"], r["found"]
+    save("knn_large_k.npz", **out)
+
+
 ALL = dict(scenes=scenes, rng=rng, sampling=sampling, bsdf=bsdf, trace=trace, photons=photons,
            render_light=render_light, stock_binary=stock_binary)
 
@@ -352,6 +391,7 @@ if __name__ == "__main__":
     O.build(ref=True)
     names = [n for n in a.only.split(",") if n] or list(ALL)
     for n in names:
-        (ALL | dict(render_heavy=render_heavy, headline_windows=headline_windows, converged_mean=converged_mean))[n]()
+        (ALL | dict(render_heavy=render_heavy, headline_windows=headline_windows, converged_mean=converged_mean,
+                                                    light_variants=light_variants))[n]()
     if a.heavy and "render_heavy" not in names:
         render_heavy()

@@ -399,6 +399,28 @@ class Renderer:
                                              _capi.ptr(hist)))
         return out[:int(counts.sum())].copy(), counts[:self.scene.L], hist
 
+    def emit_photons_device(self, first_path, num_paths, out7_ptr: int, capacity: int):
+        """rt_emit_photons_device: the stored particles stay on the GPU, compacted in (light, path) order at
+        `out7_ptr` ([capacity,7] float32 device memory).  Returns (per_light_counts[L], depth_hist[20])."""
+        counts = np.zeros(max(self.scene.L, 1), np.int64)
+        hist = np.zeros(20, np.int32)
+        _capi.check(self.lib.rt_emit_photons_device(self._ctx, int(first_path), int(num_paths), C.c_void_p(out7_ptr),
+                                                    int(capacity), _capi.ptr(counts), _capi.ptr(hist)))
+        return counts[:self.scene.L], hist
+
+    def splice_photons_device(self, gathered_ptr: int, world: int, stride: int, counts, out7_ptr: int, capacity: int):
+        """rt_splice_photons_device: all-gathered shards -> the single-process (light, path) order, on the device.
+        counts: [world, L] particles of light l in rank r's shard.  Returns the total."""
+        cnt = np.ascontiguousarray(counts, np.int64).reshape(world, -1)
+        total = C.c_int64()
+        _capi.check(self.lib.rt_splice_photons_device(self._ctx, C.c_void_p(gathered_ptr), int(world), int(stride),
+                                                      _capi.ptr(cnt), C.c_void_p(out7_ptr), int(capacity),
+                                                      C.byref(total)))
+        return total.value
+
+    def set_photons_device(self, photons7_ptr: int, n: int):
+        _capi.check(self.lib.rt_set_photons_device(self._ctx, C.c_void_p(photons7_ptr), int(n)))
+
     def set_photons(self, photons7):
         a = _capi.f32(photons7).reshape(-1, 7)
         _capi.check(self.lib.rt_set_photons(self._ctx, _capi.ptr(a), len(a)))

@@ -95,11 +95,15 @@ SYMBOLS = {
     "rt_photons_per_light": (C.c_int, [_vp, _vp]),
     "rt_emit_photons": (C.c_int, [_vp, _i32, _i32, _vp, _i64, _vp, _vp]),
     "rt_set_photons": (C.c_int, [_vp, _vp, _i64]),
+    "rt_emit_photons_device": (C.c_int, [_vp, _i32, _i32, _vp, _i64, _vp, _vp]),
+    "rt_splice_photons_device": (C.c_int, [_vp, _vp, _i32, _i64, _vp, _vp, _i64, _vp]),
+    "rt_set_photons_device": (C.c_int, [_vp, _vp, _i64]),
     "rt_build_photon_map": (C.c_int, [_vp]),
     "rt_get_photons": (C.c_int, [_vp, _vp, _i64, _vp]),
     "rt_knn": (C.c_int, [_vp, _vp, _i64, _i32, _vp]),
     "rt_get_kdtree": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64]),
     "rt_shard_pixels": (C.c_int, [C.POINTER(rt_params), _vp, _i64, _vp]),
+    "rt_profiler_range": (C.c_int, [C.c_int]),
     "rt_get_stats": (C.c_int, [_vp, C.POINTER(rt_stats)]),
     "rt_reset_stats": (C.c_int, [_vp]),
     "rt_get_bvh": (C.c_int, [_vp, _vp, _i64, _vp, _vp]),

@@ -2,6 +2,7 @@
 //
 // No CPU fallback lives here: every entry point needs a CUDA device and fails with RT_ERR_NO_DEVICE /
 // RT_ERR_CUDA otherwise.  Nothing under oracle/ is linked or called.
+#include <cuda_profiler_api.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -1159,90 +1160,114 @@ int rt_photons_per_light(const rt_ctx* c, int32_t* out) {
   return RT_OK;
 }
 
-int rt_emit_photons(rt_ctx* c, int32_t first_path, int32_t num_paths, rt_photon* out, int64_t capacity,
-                    int64_t* per_light_counts, int32_t* depth_histogram20) {
-  int rc = bind(c);
-  if (rc) return rc;
+// Emission + ordered compaction on the device.  out7_dev: capacity particles of 7 floats (device memory of c's GPU).
+static int emit_to_device(rt_ctx* c, int32_t first_path, int32_t num_paths, float* out7_dev, int64_t capacity,
+                          int64_t* per_light_counts, int32_t* depth_histogram20, int64_t* stored,
+                          bool count_only = false) {
   float light_pdf = 0.f;
   const int per_light = photons_per_light(c, &light_pdf);
   if (first_path < 0) first_path = 0;
-  int last = num_paths < 0 ? per_light : std::min(per_light, first_path + num_paths);
-  int npaths = std::max(0, last - first_path);
+  const int last = num_paths < 0 ? per_light : std::min(per_light, first_path + num_paths);
+  const int npaths = std::max(0, last - first_path);
   if (per_light_counts)
     for (int l = 0; l < c->L; l++) per_light_counts[l] = 0;
   if (depth_histogram20)
     for (int i = 0; i < 20; i++) depth_histogram20[i] = 0;
+  if (stored) *stored = 0;
   if (npaths == 0 || c->L == 0) return RT_OK;
   const size_t total = (size_t)c->L * npaths;
+  const int nb = photon_compact_blocks((long long)total);
   DevBuf<float4> d_a, d_b;
+  DevBuf<unsigned> d_blk, d_hist;
+  DevBuf<unsigned long long> d_lc;
+  std::vector<unsigned long long> h_lc(c->L);
+  unsigned h_hist[20], h_total = 0;
+  float ms = 0.f;
   cudaError_t e = d_a.ensure(total);
   if (e == cudaSuccess) e = d_b.ensure(total);
-  std::vector<float4> ha(total), hb(total);
-  float ms = 0.f;
+  if (e == cudaSuccess) e = d_blk.ensure((size_t)nb + 1);
+  if (e == cudaSuccess) e = d_hist.ensure(20);
+  if (e == cudaSuccess) e = d_lc.ensure((size_t)c->L);
+  if (e == cudaSuccess) e = cudaMemsetAsync(d_hist.p, 0, 20 * sizeof(unsigned), c->stream);
+  if (e == cudaSuccess) e = cudaMemsetAsync(d_lc.p, 0, (size_t)c->L * sizeof(unsigned long long), c->stream);
   if (e == cudaSuccess) {
     cudaEventRecord(c->ev0, c->stream);
     launch_emit(c->scene, mix64(c->params.seed + kGolden), per_light, light_pdf, first_path, npaths,
                 (c->params.flags & RT_FLAG_BRUTE_FORCE) ? 1 : 0, d_a.p, d_b.p, c->d_counters.p, c->stream);
     cudaEventRecord(c->ev1, c->stream);
-    c->stats.kernel_launches++;
+    launch_photon_compact(d_a.p, d_b.p, (long long)total, npaths, d_blk.p, d_lc.p, d_hist.p, out7_dev, capacity,
+                          c->stream);
+    c->stats.kernel_launches += 4;
     c->stats.kernel_count[kKEmit]++;
-    e = cudaStreamSynchronize(c->stream);
+    e = cudaMemcpyAsync(h_lc.data(), d_lc.p, (size_t)c->L * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h_hist, d_hist.p, sizeof(h_hist), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&h_total, d_blk.p + nb, sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (e == cudaSuccess) e = cudaGetLastError();
     if (e == cudaSuccess) cudaEventElapsedTime(&ms, c->ev0, c->ev1);
-    c->stats.kernel_ms[kKEmit] = ms;
   }
-  if (e == cudaSuccess) e = cudaMemcpy(ha.data(), d_a.p, total * sizeof(float4), cudaMemcpyDeviceToHost);
-  if (e == cudaSuccess) e = cudaMemcpy(hb.data(), d_b.p, total * sizeof(float4), cudaMemcpyDeviceToHost);
   d_a.release();
   d_b.release();
+  d_blk.release();
+  d_hist.release();
+  d_lc.release();
   if (e != cudaSuccess) return fail(RT_ERR_CUDA, cudaGetErrorString(e));
   c->stats.photon_ms = ms;
-  // stable compaction in (light, path) order == the order PhotonMap.h:94-96,109-111 appends in
-  int64_t count = 0;
-  for (size_t q = 0; q < total; q++) {
-    int status;
-    std::memcpy(&status, &hb[q].w, 4);
-    int hist = status >> 8;
-    if (hist > 0 && hist <= 20 && depth_histogram20) depth_histogram20[hist - 1]++;
-    if (!(status & 1)) continue;
-    if (count < capacity && out) {
-      rt_photon& ph = out[count];
-      ph.position[0] = ha[q].x;
-      ph.position[1] = ha[q].y;
-      ph.position[2] = ha[q].z;
-      ph.direction[0] = hb[q].x;
-      ph.direction[1] = hb[q].y;
-      ph.direction[2] = hb[q].z;
-      ph.weight = ha[q].w;
-    }
-    count++;
-    if (per_light_counts) per_light_counts[q / npaths]++;
-  }
-  if (out && count > capacity) return fail(RT_ERR_INVALID, "photon output capacity too small");
+  c->stats.kernel_ms[kKEmit] = ms;
+  if (per_light_counts)
+    for (int l = 0; l < c->L; l++) per_light_counts[l] = (int64_t)h_lc[l];
+  if (depth_histogram20)
+    for (int i = 0; i < 20; i++) depth_histogram20[i] = (int32_t)h_hist[i];
+  if (stored) *stored = (int64_t)h_total;
+  if (!count_only && (int64_t)h_total > capacity) return fail(RT_ERR_INVALID, "photon output capacity too small");
   return pull_counters(c);
 }
 
-int rt_set_photons(rt_ctx* c, const rt_photon* photons, int64_t n) {
+int rt_emit_photons_device(rt_ctx* c, int32_t first_path, int32_t num_paths, float* out7_device, int64_t capacity,
+                           int64_t* per_light_counts, int32_t* depth_histogram20) {
   int rc = bind(c);
   if (rc) return rc;
-  if (n < 0 || (n > 0 && !photons)) return fail(RT_ERR_INVALID, "bad photon list");
-  if (n >= (1 << 28)) return fail(RT_ERR_INVALID, "too many photons");
-  static_assert(sizeof(rt_photon) == 28, "rt_photon must match Particle (28 bytes)");
-  c->kd_nodes7.assign((const float*)photons, (const float*)photons + 7 * n);
+  if (!out7_device || capacity < 0) return fail(RT_ERR_INVALID, "bad device output");
+  return emit_to_device(c, first_path, num_paths, out7_device, capacity, per_light_counts, depth_histogram20, nullptr);
+}
+
+int rt_emit_photons(rt_ctx* c, int32_t first_path, int32_t num_paths, rt_photon* out, int64_t capacity,
+                    int64_t* per_light_counts, int32_t* depth_histogram20) {
+  int rc = bind(c);
+  if (rc) return rc;
+  const int per_light = photons_per_light(c, nullptr);
+  const int64_t dev_cap = out ? std::max<int64_t>(0, std::min<int64_t>(capacity, (int64_t)per_light * std::max(c->L, 0))) : 0;
+  DevBuf<float> d_out;
+  CU(d_out.ensure(7 * (size_t)std::max<int64_t>(dev_cap, 1)));
+  int64_t stored = 0;
+  // without an output buffer only the counts are wanted: the compaction writes nothing past capacity 0
+  rc = emit_to_device(c, first_path, num_paths, d_out.p, dev_cap, per_light_counts, depth_histogram20, &stored, !out);
+  if (rc == RT_OK && out && stored > 0) {
+    cudaError_t e = cudaMemcpyAsync(out, d_out.p, sizeof(float) * 7 * (size_t)stored, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) rc = fail(RT_ERR_CUDA, cudaGetErrorString(e));
+  }
+  d_out.release();
+  return rc;
+}
+
+// shared tail of rt_set_photons / rt_set_photons_device: c->kd_nodes7 holds the list in emission order
+static int install_photons(rt_ctx* c, int64_t n) {
   const double t_kd0 = now_ms();
   build_kdtree(c->kd_nodes7, &c->kd_height);
   c->stats.kd_build_ms = now_ms() - t_kd0;
   if (c->kd_height > kKdStack) return fail(RT_ERR_INVALID, "kd-tree deeper than the device stack");
-  std::vector<float4> hp(std::max<int64_t>(n, 1)), hd(std::max<int64_t>(n, 1));
-  for (int64_t i = 0; i < n; i++) {
-    const float* a = &c->kd_nodes7[7 * i];
-    hp[i] = make_float4(a[0], a[1], a[2], a[6]);
-    hd[i] = make_float4(a[3], a[4], a[5], 0.f);
+  DevBuf<float> d_p7;
+  CU(d_p7.ensure(7 * (size_t)std::max<int64_t>(n, 1)));
+  CU(c->d_kd_pos.ensure((size_t)std::max<int64_t>(n, 1)));
+  CU(c->d_kd_dir.ensure((size_t)std::max<int64_t>(n, 1)));
+  if (n > 0) {  // 28 bytes per particle up (not two padded float4 arrays), unpacked on the device
+    CU(cudaMemcpyAsync(d_p7.p, c->kd_nodes7.data(), sizeof(float) * 7 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    launch_photon_unpack(d_p7.p, n, c->d_kd_pos.p, c->d_kd_dir.p, c->stream);
+    c->stats.kernel_launches++;
   }
-  CU(c->d_kd_pos.ensure(hp.size()));
-  CU(c->d_kd_dir.ensure(hd.size()));
-  CU(cudaMemcpyAsync(c->d_kd_pos.p, hp.data(), hp.size() * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
-  CU(cudaMemcpyAsync(c->d_kd_dir.p, hd.data(), hd.size() * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
   CU(cudaStreamSynchronize(c->stream));
+  d_p7.release();
   c->scene.kd_pos = c->d_kd_pos.p;
   c->scene.kd_dir = c->d_kd_dir.p;
   c->scene.kd_count = (int)n;
@@ -1253,16 +1278,82 @@ int rt_set_photons(rt_ctx* c, const rt_photon* photons, int64_t n) {
   return RT_OK;
 }
 
+int rt_set_photons(rt_ctx* c, const rt_photon* photons, int64_t n) {
+  int rc = bind(c);
+  if (rc) return rc;
+  if (n < 0 || (n > 0 && !photons)) return fail(RT_ERR_INVALID, "bad photon list");
+  if (n >= (1 << 28)) return fail(RT_ERR_INVALID, "too many photons");
+  static_assert(sizeof(rt_photon) == 28, "rt_photon must match Particle (28 bytes)");
+  c->kd_nodes7.assign((const float*)photons, (const float*)photons + 7 * n);
+  return install_photons(c, n);
+}
+
+int rt_set_photons_device(rt_ctx* c, const float* photons7_device, int64_t n) {
+  int rc = bind(c);
+  if (rc) return rc;
+  if (n < 0 || (n > 0 && !photons7_device)) return fail(RT_ERR_INVALID, "bad photon list");
+  if (n >= (1 << 28)) return fail(RT_ERR_INVALID, "too many photons");
+  // the kd-tree's shape is libstdc++'s nth_element: ONE device->host copy for the host build
+  c->kd_nodes7.resize(7 * (size_t)n);
+  if (n > 0) {
+    CU(cudaMemcpyAsync(c->kd_nodes7.data(), photons7_device, sizeof(float) * 7 * (size_t)n, cudaMemcpyDeviceToHost,
+                       c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+  }
+  return install_photons(c, n);
+}
+
+int rt_splice_photons_device(rt_ctx* c, const float* gathered_device, int32_t world, int64_t stride,
+                             const int64_t* counts, float* out7_device, int64_t capacity, int64_t* total_out) {
+  int rc = bind(c);
+  if (rc) return rc;
+  if (!gathered_device || !counts || !out7_device || !total_out || world < 1 || stride < 0)
+    return fail(RT_ERR_INVALID, "bad argument");
+  const int L = c->L;
+  std::vector<long long> seg_src, seg_dst;
+  std::vector<long long> rank_off((size_t)world, 0);  // running offset inside every rank's shard
+  long long total = 0;
+  for (int l = 0; l < L; l++)
+    for (int r = 0; r < world; r++) {
+      const long long n = counts[(size_t)r * L + l];
+      if (n < 0 || rank_off[r] + n > stride) return fail(RT_ERR_INVALID, "shard counts exceed the shard stride");
+      if (n > 0) {
+        seg_src.push_back((long long)r * stride + rank_off[r]);
+        seg_dst.push_back(total);
+      }
+      rank_off[r] += n;
+      total += n;
+    }
+  *total_out = total;
+  if (total > capacity) return fail(RT_ERR_INVALID, "photon output capacity too small");
+  if (total == 0) return RT_OK;
+  seg_dst.push_back(total);
+  const int nseg = (int)seg_src.size();
+  DevBuf<long long> d_seg;
+  CU(d_seg.ensure((size_t)2 * nseg + 1));
+  CU(cudaMemcpyAsync(d_seg.p, seg_src.data(), sizeof(long long) * nseg, cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(d_seg.p + nseg, seg_dst.data(), sizeof(long long) * (nseg + 1), cudaMemcpyHostToDevice, c->stream));
+  launch_photon_splice(gathered_device, d_seg.p, d_seg.p + nseg, nseg, total, out7_device, c->stream);
+  c->stats.kernel_launches++;
+  cudaError_t e = cudaStreamSynchronize(c->stream);
+  d_seg.release();
+  if (e != cudaSuccess) return fail(RT_ERR_CUDA, cudaGetErrorString(e));
+  return RT_OK;
+}
+
 int rt_build_photon_map(rt_ctx* c) {
   int rc = bind(c);
   if (rc) return rc;
+  // emission and ordered compaction on the device, one device->host copy of the stored particles for the kd build
   const int per_light = photons_per_light(c, nullptr);
-  std::vector<rt_photon> list((size_t)std::max(1, per_light * c->L));
-  std::vector<int64_t> counts(std::max(c->L, 1));
-  if ((rc = rt_emit_photons(c, 0, -1, list.data(), (int64_t)list.size(), counts.data(), nullptr))) return rc;
-  int64_t n = 0;
-  for (int l = 0; l < c->L; l++) n += counts[l];
-  return rt_set_photons(c, list.data(), n);
+  const int64_t cap = std::max<int64_t>(1, (int64_t)per_light * c->L);
+  DevBuf<float> d_list;
+  CU(d_list.ensure(7 * (size_t)cap));
+  int64_t stored = 0;
+  rc = emit_to_device(c, 0, -1, d_list.p, cap, nullptr, nullptr, &stored);
+  if (rc == RT_OK) rc = rt_set_photons_device(c, d_list.p, stored);
+  d_list.release();
+  return rc;
 }
 
 int rt_get_photons(rt_ctx* c, rt_photon* out, int64_t capacity, int64_t* count) {
@@ -1331,6 +1422,11 @@ int rt_shard_pixels(const rt_params* p, int32_t* out, int64_t capacity, int64_t*
     if (capacity < (int64_t)map.size()) return fail(RT_ERR_INVALID, "capacity too small");
     std::memcpy(out, map.data(), map.size() * sizeof(int));
   }
+  return RT_OK;
+}
+
+int rt_profiler_range(int on) {
+  CU(on ? cudaProfilerStart() : cudaProfilerStop());
   return RT_OK;
 }
 

@@ -1172,4 +1172,138 @@ void launch_emit(const DScene& s, uint64_t seed_mixed, int per_light, float ligh
                                          counters);
 }
 
+
+// ----------------------------------------------------------------------------------------------
+// Device-resident photon list (multi-GPU path): the particles k_emit stored are compacted in
+// (light, path) order -- the order PhotonMap.h:94-96,109-111 appends in -- without leaving the GPU, so that the
+// NCCL all-gather can read them where they are.  Three small kernels: per-block counts (+ per-light counts and the
+// Russian-roulette depth histogram), a one-block scan of the block counts, the ordered write.
+// ----------------------------------------------------------------------------------------------
+constexpr int kCompactBlock = 1024;
+__global__ void __launch_bounds__(kCompactBlock) k_photon_count(const float4* __restrict__ out_b, long long total,
+                                                                int npaths, unsigned* block_count,
+                                                                unsigned long long* light_count, unsigned* hist20) {
+  __shared__ unsigned s_warp[kCompactBlock / 32];
+  const long long q = (long long)blockIdx.x * kCompactBlock + threadIdx.x;
+  int status = 0;
+  if (q < total) status = __float_as_int(out_b[q].w);
+  const bool stored = (status & 1) != 0;
+  const int hist = status >> 8;
+  if (hist > 0 && hist <= 20) atomicAdd(hist20 + hist - 1, 1u);
+  const unsigned m = __ballot_sync(kFull, stored);
+  if (stored) {  // per-light counts: one atomic per warp when the whole warp sits in one light (almost always)
+    const int li = (int)(q / npaths);
+    const unsigned peers = __match_any_sync(m, li);
+    if ((threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1)) atomicAdd(light_count + li, (unsigned long long)__popc(peers));
+  }
+  if ((threadIdx.x & 31) == 0) s_warp[threadIdx.x >> 5] = __popc(m);
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    unsigned v = s_warp[threadIdx.x];
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(kFull, v, off);
+    if (threadIdx.x == 0) block_count[blockIdx.x] = v;
+  }
+}
+// exclusive scan of nb counters in place by one CTA; total -> counts[nb]
+__global__ void __launch_bounds__(1024) k_scan_u32(unsigned* counts, int nb) {
+  __shared__ unsigned s[1024];
+  unsigned carry = 0;
+  for (int base = 0; base < nb; base += 1024) {
+    const int i = base + threadIdx.x;
+    const unsigned v = i < nb ? counts[i] : 0u;
+    s[threadIdx.x] = v;
+    __syncthreads();
+    for (int off = 1; off < 1024; off <<= 1) {
+      const unsigned add = threadIdx.x >= off ? s[threadIdx.x - off] : 0u;
+      __syncthreads();
+      s[threadIdx.x] += add;
+      __syncthreads();
+    }
+    if (i < nb) counts[i] = carry + s[threadIdx.x] - v;
+    const unsigned tot = s[1023];
+    __syncthreads();
+    carry += tot;
+  }
+  if (threadIdx.x == 0) counts[nb] = carry;
+}
+__global__ void __launch_bounds__(kCompactBlock) k_photon_compact(const float4* __restrict__ out_a,
+                                                                  const float4* __restrict__ out_b, long long total,
+                                                                  const unsigned* __restrict__ block_offset, float* out7,
+                                                                  long long capacity) {
+  __shared__ unsigned s_warp[kCompactBlock / 32];
+  const long long q = (long long)blockIdx.x * kCompactBlock + threadIdx.x;
+  float4 a = make_float4(0, 0, 0, 0), b = make_float4(0, 0, 0, 0);
+  bool stored = false;
+  if (q < total) {
+    b = out_b[q];
+    stored = (__float_as_int(b.w) & 1) != 0;
+    if (stored) a = out_a[q];
+  }
+  const unsigned m = __ballot_sync(kFull, stored);
+  const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  if (lane == 0) s_warp[warp] = __popc(m);
+  __syncthreads();
+  if (threadIdx.x < 32) {  // exclusive scan of the 32 warp counts
+    const unsigned v = s_warp[threadIdx.x];
+    unsigned inc = v;
+    for (int off = 1; off < 32; off <<= 1) {
+      const unsigned o = __shfl_up_sync(kFull, inc, off);
+      if (threadIdx.x >= (unsigned)off) inc += o;
+    }
+    s_warp[threadIdx.x] = inc - v;
+  }
+  __syncthreads();
+  if (stored) {
+    const long long dst = (long long)block_offset[blockIdx.x] + s_warp[warp] + __popc(m & ((1u << lane) - 1u));
+    if (dst < capacity) {
+      float* o = out7 + 7 * dst;  // Particle{position, incomeDirection, weight}, Particle.h:33-35
+      o[0] = a.x, o[1] = a.y, o[2] = a.z, o[3] = b.x, o[4] = b.y, o[5] = b.z, o[6] = a.w;
+    }
+  }
+}
+int photon_compact_blocks(long long total) { return (int)((total + kCompactBlock - 1) / kCompactBlock); }
+void launch_photon_compact(const float4* out_a, const float4* out_b, long long total, int npaths, unsigned* block_count,
+                           unsigned long long* light_count, unsigned* hist20, float* out7, long long capacity,
+                           cudaStream_t st) {
+  const int nb = photon_compact_blocks(total);
+  if (nb < 1) return;
+  k_photon_count<<<nb, kCompactBlock, 0, st>>>(out_b, total, npaths, block_count, light_count, hist20);
+  k_scan_u32<<<1, 1024, 0, st>>>(block_count, nb);
+  k_photon_compact<<<nb, kCompactBlock, 0, st>>>(out_a, out_b, total, block_count, out7, capacity);
+}
+
+// Splice the all-gathered shards into the single-process order: for every light, rank 0's particles, then rank 1's, ...
+// seg_src[i] / seg_dst[i]: first particle of segment i = (light, rank) in the gathered buffer / in the output
+// (seg_dst has one more entry: the total); segments are few (lights x ranks), found by a linear scan.
+__global__ void k_photon_splice(const float* __restrict__ gathered, const long long* __restrict__ seg_src,
+                                const long long* __restrict__ seg_dst, int nseg, float* out7) {
+  const long long total = seg_dst[nseg];
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < 7 * total; i += (long long)gridDim.x * blockDim.x) {
+    const long long p = i / 7;
+    const int c = (int)(i - 7 * p);
+    int s = 0;
+    while (s + 1 < nseg && seg_dst[s + 1] <= p) s++;
+    out7[i] = gathered[7 * (seg_src[s] + (p - seg_dst[s])) + c];
+  }
+}
+void launch_photon_splice(const float* gathered, const long long* seg_src, const long long* seg_dst, int nseg,
+                          long long total, float* out7, cudaStream_t st) {
+  if (total < 1) return;
+  long long blocks = (7 * total + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  k_photon_splice<<<(int)blocks, 256, 0, st>>>(gathered, seg_src, seg_dst, nseg, out7);
+}
+// particles (7 floats each) in kd order -> the two float4 arrays the gather reads
+__global__ void k_photon_unpack(const float* __restrict__ p7, long long n, float4* kd_pos, float4* kd_dir) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float* a = p7 + 7 * i;
+  kd_pos[i] = make_float4(a[0], a[1], a[2], a[6]);
+  kd_dir[i] = make_float4(a[3], a[4], a[5], 0.f);
+}
+void launch_photon_unpack(const float* p7, long long n, float4* kd_pos, float4* kd_dir, cudaStream_t st) {
+  if (n < 1) return;
+  k_photon_unpack<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p7, n, kd_pos, kd_dir);
+}
+
 }  // namespace rtb

@@ -120,6 +120,14 @@ void launch_bsdf(DMaterial m, const float* n_wi_wo, long long n, float* rgb, cud
 // photon emission: path q = light*npaths + j traces path (first_path + j) of `light`
 void launch_emit(const DScene& s, uint64_t seed_mixed, int per_light, float light_pdf, int first_path, int npaths,
                  int brute, float4* out_a, float4* out_b, unsigned long long* counters, cudaStream_t st);
+// device-resident photon list: ordered compaction of k_emit's output, splice of all-gathered shards, unpack for the gather
+int photon_compact_blocks(long long total);
+void launch_photon_compact(const float4* out_a, const float4* out_b, long long total, int npaths, unsigned* block_count,
+                           unsigned long long* light_count, unsigned* hist20, float* out7, long long capacity,
+                           cudaStream_t st);
+void launch_photon_splice(const float* gathered, const long long* seg_src, const long long* seg_dst, int nseg,
+                          long long total, float* out7, cudaStream_t st);
+void launch_photon_unpack(const float* p7, long long n, float4* kd_pos, float4* kd_dir, cudaStream_t st);
 // scratch: knn candidates in global memory when k > kKnnSharedMaxK (k * 8 bytes per thread of `grid_ctas` CTAs)
 void launch_knn(const DScene& s, const float* q3, long long n, int k, int kd_frames, int exact, int* node_index,
                 unsigned long long* counters, unsigned long long* scratch, int grid_ctas, cudaStream_t st);

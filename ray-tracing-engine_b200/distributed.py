@@ -70,6 +70,43 @@ def gather_photons(local_photons: np.ndarray, per_light_counts: np.ndarray, devi
     return np.concatenate(parts) if parts else np.zeros((0, 7), np.float32)
 
 
+def gather_photons_device(renderer, device, group=None):
+    """The same on the GPU, where the particles are: every rank emits and compacts its share on the device, the
+    per-light counts (world x L int64) and then the padded shards themselves are all-gathered with NCCL straight
+    from device memory, a splice kernel rearranges them into the single-process (light, path) order, and the list is
+    installed with ONE device->host copy (the kd-tree build is libstdc++'s nth_element on the host).
+    Returns (list as a [N,7] CUDA tensor, N)."""
+    import torch
+    import torch.distributed as dist
+
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    per, L = renderer.photons_per_light(), renderer.scene.L
+    first, count = path_range(per, rank, world)
+    cap = max(1, max(path_range(per, r, world)[1] for r in range(world)) * max(L, 1))
+    local = torch.empty((cap, 7), dtype=torch.float32, device=device)
+    counts, _ = renderer.emit_photons_device(first, count, local.data_ptr(), cap)  # synchronous: `local` is complete
+    counts_t = torch.as_tensor(np.asarray(counts, np.int64), device=device)
+    all_counts = torch.empty((world, max(L, 1)), dtype=torch.int64, device=device)
+    dist.all_gather_into_tensor(all_counts, counts_t.reshape(1, -1) if L else torch.zeros((1, 1), dtype=torch.int64, device=device), group=group)
+    gathered = torch.empty((world * cap, 7), dtype=torch.float32, device=device)
+    dist.all_gather_into_tensor(gathered, local, group=group)
+    all_counts = all_counts.cpu().numpy()[:, :L]  # also waits for the collectives (NCCL stream) before the splice
+    torch.cuda.synchronize(device)
+    total = int(all_counts.sum())
+    out = torch.empty((max(total, 1), 7), dtype=torch.float32, device=device)
+    got = renderer.splice_photons_device(gathered.data_ptr(), world, cap, all_counts, out.data_ptr(), max(total, 1))
+    assert got == total
+    return out, total
+
+
+def reduce_packed(packed, dst=0, group=None):
+    """Sum-reduce the packed fp32 frame {sum r, g, b, counter} to rank `dst`: one collective per frame."""
+    import torch.distributed as dist
+
+    dist.reduce(packed, dst, op=dist.ReduceOp.SUM, group=group)
+    return packed
+
+
 def reduce_frame(sum_rgb, counter, dst=0, group=None):
     """Sum-reduce the fp32 sums and int32 counters (torch tensors, any device) to rank `dst`."""
     import torch.distributed as dist
@@ -84,11 +121,15 @@ def build_photon_map_distributed(renderer, device=None, group=None):
     import torch.distributed as dist
 
     rank, world = dist.get_rank(group), dist.get_world_size(group)
+    if device is not None and str(device).startswith("cuda"):  # the particles never leave the GPUs until the kd build
+        out, total = gather_photons_device(renderer, device, group)
+        renderer.set_photons_device(out.data_ptr(), total)
+        return total
     first, count = path_range(renderer.photons_per_light(), rank, world)
     local, counts, _ = renderer.emit_photons(first, count)
     full = gather_photons(local, counts, device=device, group=group)
     renderer.set_photons(full)
-    return full
+    return len(full)
 
 
 def render_distributed(scene, num_rays, mode, num_photons=0, k=5, *, background, seed=1, shard="tile", device=None,
@@ -108,19 +149,22 @@ def render_distributed(scene, num_rays, mode, num_photons=0, k=5, *, background,
     if num_photons > 0:
         build_photon_map_distributed(r, device=device, group=group)
     H, W = r.height, r.width
-    sum_t = torch.zeros((H, W, 3), dtype=torch.float32, device=device)
-    cnt_t = torch.zeros((H, W), dtype=torch.int32, device=device)
-    if sum_t.is_cuda:
-        torch.cuda.synchronize(sum_t.device)  # torch's fill kernels vs the context's own stream
-    r.render_accumulate_device(sum_t.data_ptr(), cnt_t.data_ptr())
-    reduce_frame(sum_t, cnt_t, 0, group)
+    on_gpu = device is not None and str(device).startswith("cuda")
     out = None
-    if rank == 0:
-        if sum_t.is_cuda:  # composite on the device, one D2H of the frame
+    if on_gpu:  # sums and counter as one packed frame: a single reduce, composite on rank 0's GPU, one D2H
+        packed = torch.empty((H, W, 4), dtype=torch.float32, device=device)
+        torch.cuda.synchronize(device)
+        r.render_accumulate_packed_device(packed.data_ptr())
+        reduce_packed(packed, 0, group)
+        if rank == 0:
             # the reduce runs on NCCL's stream and the composite on the context's own: wait for the collective first
-            torch.cuda.synchronize(sum_t.device)
-            out = r.composite_device(num_rays, sum_t.data_ptr(), cnt_t.data_ptr(), background)
-        else:              # gloo tests: host tensors
+            torch.cuda.synchronize(device)
+            out = r.composite_packed_device(num_rays, packed.data_ptr(), background)
+    else:       # host tensors (gloo): separate sums and counters
+        sum_np, cnt_np = r.render_accumulate()
+        sum_t, cnt_t = torch.from_numpy(sum_np), torch.from_numpy(cnt_np)
+        reduce_frame(sum_t, cnt_t, 0, group)
+        if rank == 0:
             out = Renderer.composite(num_rays, sum_t.numpy(), cnt_t.numpy(), background)
     r.close()
     return out

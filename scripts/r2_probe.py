@@ -1,0 +1,62 @@
+"""Round-2 probes on one GPU (device time from CUDA events inside the library, best of 3 frames each):
+  own    RT_OWN_TRI=0/1 on the cfg2 frame (own-triangle pre-test of shadow rays in k_shade)
+  batch  samples_per_batch sweep on the cfg2 frame (does an L2-sized wavefront batch pay?)
+  cfg4   -m 0 -N 1 -p 500000 -k 50 end to end: emission, kd build, render (BASELINE configs[3]; reference: 15 s)
+usage: python scripts/r2_probe.py own batch cfg4"""
+import json, os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
+import numpy as np
+import ray_tracing_engine_b200 as rt
+
+def scene(name):
+    s = rt.Scene.load(os.path.join(ROOT, "tests/golden/scenes", name + ".rtscene"))
+    s.w = s.h = 420
+    return s
+
+def frames(r, n=3):
+    s, c = r.render_accumulate()
+    best, per = 1e9, None
+    for _ in range(n):
+        r.reset_stats()
+        s, c = r.render_accumulate()
+        st = r.stats()
+        if st["device_ms"] < best:
+            best, per = st["device_ms"], st
+    return best, per, float(s.astype(np.float64).sum()), int(c.sum())
+
+what = sys.argv[1:] or ["own", "batch", "cfg4"]
+ex = scene("example")
+if "own" in what:
+    for v in ("0", "1"):
+        os.environ["RT_OWN_TRI"] = v
+        r = rt.Renderer(ex, 128, 1, seed=1)
+        ms, st, chk, hits = frames(r)
+        print(json.dumps(dict(probe="own_tri", RT_OWN_TRI=v, frame_ms=round(ms, 3), grays=round(st["rays"] / ms / 1e6, 3),
+                              kernel_ms={k: round(x, 3) for k, x in st["kernel_ms"].items()}, checksum=chk, hits=hits)), flush=True)
+        r.close()
+    os.environ.pop("RT_OWN_TRI")
+if "batch" in what:
+    for spb in (128, 64, 32, 16, 8, 4, 2, 1):
+        r = rt.Renderer(ex, 128, 1, seed=1, samples_per_batch=spb)
+        t = time.perf_counter()
+        ms, st, chk, hits = frames(r, 2)
+        wall = (time.perf_counter() - t) / 3
+        print(json.dumps(dict(probe="batch", samples_per_batch=spb, state_MB=round(spb * 176400 * 282 / 1e6), frame_ms=round(ms, 3),
+                              host_wall_ms=round(1e3 * wall, 2), launches=st["kernel_launches"],
+                              kernel_ms={k: round(x, 3) for k, x in st["kernel_ms"].items()}, checksum=chk)), flush=True)
+        r.close()
+if "cfg4" in what:
+    st_scene = scene("stock")
+    for it in range(3):
+        t0 = time.perf_counter()
+        r = rt.Renderer(st_scene, 1, 0, None, 500000, 50, seed=1)
+        img = rt.Image(420, 420).fillBackground()
+        r.render(img)
+        wall = time.perf_counter() - t0
+        st = r.stats()
+        print(json.dumps(dict(probe="cfg4_e2e", iteration=it, wall_ms=round(1e3 * wall, 2), create_ms=round(st["create_ms"], 2),
+                              emit_ms=round(st["photon_ms"], 3), kd_build_ms=round(st["kd_build_ms"], 2),
+                              render_device_ms=round(st["device_ms"], 3), photons=st["photons_stored"],
+                              photon_rays=st["photon_rays"], knn_queries=st["knn_queries"], kd_visits=st["kd_visits"],
+                              kernel_ms={k: round(x, 3) for k, x in st["kernel_ms"].items()}, mean=float(img.pixels.mean()))), flush=True)
+        r.close()

@@ -172,9 +172,9 @@ def test_render_m1_windows(rt, gold, case, name, N):
     rgb, found = r.render_samples(window=tuple(g["window"]))
     assert (found == g["found"]).all(), "primary hits are transcendental-free and must match exactly"
     # bounce directions go through asin/sin/cos: a last-bit difference there can flip a t~1e-7 shadow
-    # decision, so we require >= 97 % of the samples identical and a small mean difference.
+    # decision, so we require >= 99 % of the samples identical and a small mean difference.
     frac = _sample_agreement(rgb, g["samples"])
-    assert frac >= 0.97, frac
+    assert frac >= 0.99, frac
     assert abs(float(rgb.mean()) - float(g["samples"].mean())) < 5e-3
 
 
@@ -210,7 +210,7 @@ def test_render_matches_port_oracle_other_seed_and_size(rt, O):
         if mode == 0:
             assert beq(rgb, want["samples"])
         else:
-            assert _sample_agreement(rgb, want["samples"]) >= 0.97
+            assert _sample_agreement(rgb, want["samples"]) >= 0.99
         s, c = r.render_accumulate()
         assert (c == want["counter"]).all()
         if mode == 0:
@@ -328,7 +328,7 @@ def test_photon_render_on_shared_list(rt, gold, case, N, mode, k):
         frac = (rgb.view(np.uint32) == g["samples"].view(np.uint32)).all(axis=-1).mean()
         assert frac >= 0.999, frac
     else:
-        assert _sample_agreement(rgb, g["samples"]) >= 0.97
+        assert _sample_agreement(rgb, g["samples"]) >= 0.99
 
 
 def test_photon_render_full_pipeline_cfg4_like(rt, gold):
