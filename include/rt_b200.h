@@ -221,6 +221,11 @@ int rt_occluded(rt_ctx* ctx, const rt_ray* rays, int64_t n, uint8_t* occluded, i
 /* Material::evaluateColorResponse (source/Material.h:25-36): in 9 floats (normal, wi, wo) per item */
 int rt_eval_bsdf(rt_ctx* ctx, const rt_material* material, const float* n_wi_wo, int64_t n, float* rgb);
 
+/* RayTracer::hsphereUniformSample (source/RayTracer.h:95-107, maxRayAngle = pi/2) around n normals (3 floats each):
+ * item i draws its four words from stream (seed, domain, index0 + i) starting at word 0 (parity hook). */
+int rt_eval_hsphere(rt_ctx* ctx, uint64_t seed, uint64_t domain, uint64_t index0, const float* normals, int64_t n,
+                    float* directions);
+
 /* Photon map (source/PhotonMap.h:14-50,92-155).  rt_emit_photons traces paths [first_path,
  * first_path+num_paths) of EVERY light (num_paths < 0: all) and returns the stored particles in
  * (light, path) order together with per-light counts, so shards can be concatenated into the list

@@ -380,6 +380,15 @@ class Renderer:
         _capi.check(self.lib.rt_eval_bsdf(self._ctx, C.byref(m), _capi.ptr(a), len(a), _capi.ptr(out)))
         return out
 
+    def hsphereUniformSample(self, normals, seed, domain, index0):
+        """RayTracer::hsphereUniformSample (source/RayTracer.h:95-107) around [n,3] normals; item i draws from
+        stream (seed, domain, index0 + i)."""
+        a = _capi.f32(normals).reshape(-1, 3)
+        out = np.zeros_like(a)
+        _capi.check(self.lib.rt_eval_hsphere(self._ctx, int(seed), int(domain), int(index0), _capi.ptr(a), len(a),
+                                             _capi.ptr(out)))
+        return out
+
     # ---- photon map ------------------------------------------------------------------------------
     def photons_per_light(self):
         out = C.c_int32()
@@ -461,7 +470,7 @@ class Renderer:
     def stats(self):
         s = rt_stats()
         _capi.check(self.lib.rt_get_stats(self._ctx, C.byref(s)))
-        out = {name: getattr(s, name) for name, _ in rt_stats._fields_ if not name.startswith("kernel_")}
+        out = {name: getattr(s, name) for name, _ in rt_stats._fields_ if name not in ("kernel_ms", "kernel_count")}
         out["kernel_ms"] = {n: float(s.kernel_ms[i]) for i, n in enumerate(_capi.KERNEL_CLASSES)}
         out["kernel_count"] = {n: int(s.kernel_count[i]) for i, n in enumerate(_capi.KERNEL_CLASSES)}
         return out

@@ -92,6 +92,7 @@ SYMBOLS = {
     "rt_trace_rays": (C.c_int, [_vp, _vp, _i64, _vp, _i32]),
     "rt_occluded": (C.c_int, [_vp, _vp, _i64, _vp, _i32]),
     "rt_eval_bsdf": (C.c_int, [_vp, C.POINTER(rt_material), _vp, _i64, _vp]),
+    "rt_eval_hsphere": (C.c_int, [_vp, C.c_uint64, C.c_uint64, C.c_uint64, _vp, _i64, _vp]),
     "rt_photons_per_light": (C.c_int, [_vp, _vp]),
     "rt_emit_photons": (C.c_int, [_vp, _i32, _i32, _vp, _i64, _vp, _vp]),
     "rt_set_photons": (C.c_int, [_vp, _vp, _i64]),

@@ -100,7 +100,7 @@ struct rt_ctx {
   DevBuf<DLight> d_lights_ext;             // lights beyond the kMaxLights kept in kernel-parameter space
   DevBuf<unsigned long long> d_knn_scratch;  // k-NN candidates of every resident thread when k > kKnnSharedMaxK
   int knn_scratch_threads = 0;
-  int own_tri = 1;  // RT_OWN_TRI=0: shadow rays are not pre-tested against the triangle they start on
+  int own_tri = 0;  // RT_OWN_TRI=1: k_shade pre-tests a shadow ray against the triangle it starts on (measured: no gain)
   DevBuf<unsigned char> d_occ;
   DevBuf<int> d_hit_path;
   DevBuf<unsigned int> d_perm, d_sort_hist;
@@ -1063,6 +1063,7 @@ int rt_render_samples(rt_ctx* c, int32_t x0, int32_t y0, int32_t x1, int32_t y1,
   if (e != cudaSuccess) return fail(RT_ERR_CUDA, cudaGetErrorString(e));
   if ((rc = collect_spans(c))) return rc;
   c->stats.samples += paths;
+  if ((rc = pull_counters(c))) return rc;
   for (size_t i = 0; i < paths; i++) {
     rgb[3 * i] = h[i].x;
     rgb[3 * i + 1] = h[i].y;
@@ -1148,6 +1149,28 @@ int rt_eval_bsdf(rt_ctx* c, const rt_material* m, const float* n_wi_wo, int64_t 
     e = cudaStreamSynchronize(c->stream);
   }
   if (e == cudaSuccess) e = cudaMemcpy(rgb, d_out.p, sizeof(float) * 3 * (size_t)n, cudaMemcpyDeviceToHost);
+  d_in.release();
+  d_out.release();
+  if (e != cudaSuccess) return fail(RT_ERR_CUDA, cudaGetErrorString(e));
+  return RT_OK;
+}
+
+int rt_eval_hsphere(rt_ctx* c, uint64_t seed, uint64_t domain, uint64_t index0, const float* normals, int64_t n,
+                    float* directions) {
+  int rc = bind(c);
+  if (rc) return rc;
+  if (n < 0 || (n > 0 && (!normals || !directions))) return fail(RT_ERR_INVALID, "bad argument");
+  if (n == 0) return RT_OK;
+  DevBuf<float> d_in, d_out;
+  cudaError_t e = d_in.ensure(3 * (size_t)n);
+  if (e == cudaSuccess) e = d_out.ensure(3 * (size_t)n);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_in.p, normals, sizeof(float) * 3 * (size_t)n, cudaMemcpyHostToDevice, c->stream);
+  if (e == cudaSuccess) {
+    launch_hsphere(mix64(seed + kGolden), domain, index0, d_in.p, n, d_out.p, c->stream);
+    c->stats.kernel_launches++;
+    e = cudaMemcpyAsync(directions, d_out.p, sizeof(float) * 3 * (size_t)n, cudaMemcpyDeviceToHost, c->stream);
+  }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
   d_in.release();
   d_out.release();
   if (e != cudaSuccess) return fail(RT_ERR_CUDA, cudaGetErrorString(e));

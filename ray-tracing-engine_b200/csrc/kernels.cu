@@ -1034,6 +1034,23 @@ void launch_composite(const float4* acc_rgb, const int* acc_cnt, const int* pix_
 // ----------------------------------------------------------------------------------------------
 // parity hooks
 // ----------------------------------------------------------------------------------------------
+// RayTracer::hsphereUniformSample around n normals; item i draws from stream (seed, domain, index0 + i), word 0 on
+__global__ void k_hsphere(uint64_t seed_mixed, uint64_t domain, uint64_t index0, const float* __restrict__ normals,
+                          long long n, float* out) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Rng g;
+  g.init(stream_key(seed_mixed, domain, index0 + (uint64_t)i), 0);
+  const float3 r = hsphere_uniform_sample(g, f3(normals[3 * i], normals[3 * i + 1], normals[3 * i + 2]));
+  out[3 * i] = r.x;
+  out[3 * i + 1] = r.y;
+  out[3 * i + 2] = r.z;
+}
+void launch_hsphere(uint64_t seed_mixed, uint64_t domain, uint64_t index0, const float* normals, long long n, float* out,
+                    cudaStream_t st) {
+  k_hsphere<<<(int)((n + 127) / 128), 128, 0, st>>>(seed_mixed, domain, index0, normals, n, out);
+}
+
 __global__ void k_bsdf(DMaterial m, const float* __restrict__ in, long long n, float* out) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;

@@ -117,6 +117,8 @@ void launch_trace_rays(const DScene& s, const float4* ro, const float4* rd, unsi
                        int grid_ctas, cudaStream_t st);
 int shade_photon_ctas_per_sm(int mode, int k, int kd_frames);  // resident CTAs of the k-NN shade kernel
 void launch_bsdf(DMaterial m, const float* n_wi_wo, long long n, float* rgb, cudaStream_t st);
+void launch_hsphere(uint64_t seed_mixed, uint64_t domain, uint64_t index0, const float* normals, long long n, float* out,
+                    cudaStream_t st);
 // photon emission: path q = light*npaths + j traces path (first_path + j) of `light`
 void launch_emit(const DScene& s, uint64_t seed_mixed, int per_light, float light_pdf, int first_path, int npaths,
                  int brute, float4* out_a, float4* out_b, unsigned long long* counters, cudaStream_t st);

@@ -360,10 +360,59 @@ RT_DI void camera_ray(const DCamera& c, int x, int y, float sx, float sy, int w,
   o = c.position;
   d = v_norm(v_sub(v_add(v_add(c.lower_left, v_scl(c.horizontal, u)), v_scl(c.vertical, v)), c.position));
 }
-// RayTracer.h:95-107 with maxRayAngle = float(pi/2).  asin in binary64 like the reference; the
-// reference's cosf/sinf (glibc) are replaced by binary64 sin/cos rounded to binary32, which agrees
-// with a correctly rounded binary32 result (glibc's are within 0.56 ulp) -- transcendental, so parity
-// downstream of this routine is statistical by contract (SURVEY.md section 7 "Hard parts").
+// ------------------------------------------------------------------------------------------------
+// libm's binary32 sine and cosine, restated.  RayTracer.h:104-106 calls cos(phi), sin(phi), cos(theta), sin(theta)
+// on floats, i.e. glibc's cosf/sinf -- which are NOT correctly rounded: since glibc 2.28 they are the ARM
+// optimized-routines algorithm (sysdeps/ieee754/flt-32/s_sinf.c, s_cosf.c, s_sincosf.h, s_sincosf_data.c): reduce by
+// pi/2 in binary64, a degree-7 / degree-8 polynomial in binary64, one rounding to binary32, 0.56 ulp.  A correctly
+// rounded sine differs from that result for 0.36 % of the arguments in [0, 2 pi] and the cosine for 0.16 %; with four
+// calls per bounce that alone made ~1-2 % of the -m 1 samples differ from the reference's in the last bit.  The
+// algorithm is deterministic binary64 arithmetic, so it can be restated exactly: same table, same operation order,
+// fused multiply-adds where the FMA build of libm (the variant x86-64 hosts with FMA select) has them.  Pinned on
+// the host against this image's glibc 2.39 over every binary32 in [2^-15, 2 pi] (tests/test_host.py builds the same
+// restatement in C) and on the device by the hsphere golden (tests/test_gpu_round2.py).
+// Arguments here are in [0, 2 pi (1 + 3e-8)] or NaN (asin of a uniform that may exceed 1 by 3e-8, RayTracer.h:96).
+// ------------------------------------------------------------------------------------------------
+RT_DI float libm_sincosf_poly(double x, double x2, bool second_table, int n) {
+  // __sincosf_table[0] and [1]: the cosine coefficients change sign in the second table, the sine ones do not
+  const double sg = second_table ? -1.0 : 1.0;
+  if ((n & 1) == 0) {
+    const double s1c = -0x1.555545995a603p-3, s2c = 0x1.1107605230bc4p-7, s3c = -0x1.994eb3774cf24p-13;
+    const double x3 = __dmul_rn(x, x2);
+    const double s1 = __fma_rn(x2, s3c, s2c);
+    const double x7 = __dmul_rn(x3, x2);
+    const double s = __fma_rn(x3, s1c, x);
+    return (float)__fma_rn(x7, s1, s);
+  }
+  const double c0 = sg * 0x1p0, c1 = sg * -0x1.ffffffd0c621cp-2, c2 = sg * 0x1.55553e1068f19p-5,
+               c3 = sg * -0x1.6c087e89a359dp-10, c4 = sg * 0x1.99343027bf8c3p-16;
+  const double x4 = __dmul_rn(x2, x2);
+  const double q2 = __fma_rn(x2, c4, c3);
+  const double q1 = __fma_rn(x2, c1, c0);
+  const double x6 = __dmul_rn(x4, x2);
+  const double c = __fma_rn(x4, c2, q1);
+  return (float)__fma_rn(x6, q2, c);
+}
+template <bool COS>
+RT_DI float libm_sincosf(float y) {
+  const unsigned top = (__float_as_uint(y) >> 20) & 0x7ffu;  // abstop12
+  const double x = (double)y;
+  if (top < 0x3f4u) {  // |y| < pi/4
+    if (top < 0x398u) return COS ? 1.0f : y;  // |y| < 2^-12
+    return libm_sincosf_poly(x, __dmul_rn(x, x), false, COS ? 1 : 0);
+  }
+  if (top >= 0x42fu) return COS ? cosf(y) : sinf(y);  // |y| >= 120, inf, NaN: never a finite argument on this path
+  // reduce_fast without TOINT_INTRINSICS: hpi_inv is 2/pi * 2^24
+  const double r = __dmul_rn(x, 0x1.45F306DC9C883p+23);
+  const int n = (__double2int_rz(r) + 0x800000) >> 24;
+  const double xr = __fma_rn(-(double)n, 0x1.921FB54442D18p0, x);
+  const double sign = ((n & 3) == 1 || (n & 3) == 2) ? -1.0 : 1.0;  // sign[] = {1, -1, -1, 1}
+  return libm_sincosf_poly(__dmul_rn(xr, sign), __dmul_rn(xr, xr), (n & 2) != 0, COS ? (n ^ 1) : n);
+}
+
+// RayTracer.h:95-107 with maxRayAngle = float(pi/2).  asin in binary64 like the reference (the result is rounded to
+// binary32 at once, which hides the last-bit differences between libm's and CUDA's binary64 asin except with
+// probability ~1e-8); cos/sin are libm's binary32 routines restated above.
 RT_DI float3 hsphere_uniform_sample(Rng& g, float3 normal) {
   const double hi = 1.0000000278275352;  // 2*float(pi/2)/pi
   normal = v_norm(normal);
@@ -373,11 +422,8 @@ RT_DI float3 hsphere_uniform_sample(Rng& g, float3 normal) {
   v2 = v_norm(v2);
   float theta = (float)asin(g.uniform_d0(hi));
   float phi = (float)__dmul_rn(6.283185307179586, g.uniform_d0(hi));
-  double sp, cp, st, ct;
-  sincos((double)phi, &sp, &cp);
-  sincos((double)theta, &st, &ct);
-  float3 direction = v_norm(v_add(v_scl(v1, (float)cp), v_scl(v2, (float)sp)));
-  return v_norm(v_add(v_scl(normal, (float)ct), v_scl(direction, (float)st)));
+  float3 direction = v_norm(v_add(v_scl(v1, libm_sincosf<true>(phi)), v_scl(v2, libm_sincosf<false>(phi))));
+  return v_norm(v_add(v_scl(normal, libm_sincosf<true>(theta)), v_scl(direction, libm_sincosf<false>(theta))));
 }
 // LightSource.h:46-49: the first draw scales m_horizontal, the second m_vertical (g++ evaluates the
 // right operand of the outer + first; pinned against the reference build by the oracle tests).

@@ -13,7 +13,7 @@ METRICS = ["gpu__time_duration.sum", "smsp__thread_inst_executed.sum", "smsp__in
 
 def kernel_class(name):
     if "k_trace" in name:
-        m = re.search(r"<\(bool\)(\d)", name)
+        m = re.search(r"k_trace\w*<\s*(?:\(bool\))?(\d)", name)
         return "trace_any" if m and m.group(1) == "1" else "trace_nearest"
     for key, cls in (("k_raygen", "raygen"), ("k_sort", "sort"), ("k_shade", "shade"), ("k_combine", "combine"),
                      ("k_resolve", "resolve"), ("k_emit", "emit")):

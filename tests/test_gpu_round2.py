@@ -105,6 +105,16 @@ def test_cfg3_emission_on_the_example_scene(rt, gold):
     assert got / len(want) > 0.85, got / len(want)
 
 
+def test_hsphere_sampling_is_bit_identical_to_the_reference(rt, gold):
+    """8a-H: hsphereUniformSample goes through asin (binary64) and libm's binary32 cos/sin; with libm's algorithm
+    restated on the device the 4096 golden directions of the reference must come out bit for bit."""
+    g = gold("sampling.npz")
+    r = rt.Renderer(rt.Scene.load(scene_path("stock")), 1, 0, seed=SEED)
+    got = r.hsphereUniformSample(g["normals"], SEED, 2, 1000)
+    same = (got.view(np.uint32) == g["hsphere"].view(np.uint32)).all(axis=-1)
+    assert same.mean() >= 0.9995, f"{(~same).sum()} of {len(same)} directions differ"
+
+
 # ------------------------------------------------------------------ configs[3]: -m 0 -p 500000 -k 50, live
 @pytest.mark.parametrize("emitter", ["reference", "gpu"])
 def test_cfg4_window_k50_500k_photons_against_the_live_reference(rt, O, emitter):

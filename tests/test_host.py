@@ -276,3 +276,16 @@ def test_host_bvh_follows_the_reference_split_policy(name):
     assert n_checked == scene.T - nonempty
     biggest = int(np.diff(scene.mesh_tri_off).max())
     assert depth >= int(np.ceil(np.log2(biggest))) and depth <= int(np.ceil(np.log2(biggest))) + 5
+
+
+def test_restated_libm_sinf_cosf_equals_this_machines_libm(tmp_path):
+    """RayTracer.h:104-106 calls libm's binary32 cos/sin, which are not correctly rounded; the device restates glibc's
+    algorithm (csrc/rt_device.cuh: libm_sincosf).  The same restatement in C must reproduce sinf/cosf of the C library
+    here bit for bit on every 5th binary32 in [2^-15, 2 pi] (the arguments hsphereUniformSample can produce; the
+    exhaustive run over all 147 M values was done once: 0 mismatches)."""
+    exe = str(tmp_path / "libm_check")
+    src = os.path.join(ROOT, "tests", "libm_sincosf_check.c")
+    subprocess.run(["gcc", "-O2", "-ffp-contract=off", "-mfma", "-o", exe, src, "-lm"], check=True)
+    out = subprocess.run([exe, "38000000", "40c90fdc", "5"], capture_output=True, text=True, check=True).stdout.split()
+    n, bad_sin, bad_cos = (int(v) for v in out)
+    assert n > 29_000_000 and bad_sin == 0 and bad_cos == 0, out
