@@ -219,6 +219,17 @@ def photons():
     save("photons.npz", **out)
 
 
+def pointcloud():
+    """PhotonMap::saveToPCD (PhotonMap.h:59-84): the reference's own writer on the first 64 golden photons plus a few
+    values that exercise the stream formatting (exponents, negative zero, integers)."""
+    ref = O.RefOracle()
+    plist = np.load(os.path.join(GOLD, "photons.npz"))["list"][:64].copy()
+    plist[0, :6] = [1.0, -0.0, 1e-7, 123456.789, -2.5e10, 0.1]
+    np.save(os.path.join(GOLD, "pointcloud_input.npy"), plist)
+    ref.save_pcd(plist, os.path.join(GOLD, "pointcloud_golden.pcd"))
+    log("wrote pointcloud_golden.pcd", os.path.getsize(os.path.join(GOLD, "pointcloud_golden.pcd")), "bytes")
+
+
 def stock_binary():
     """md5 of the unmodified reference program's own output (stock RNG) -- guards oracle drift."""
     build = os.path.join(HERE, "_ref", "build")
@@ -392,6 +403,6 @@ if __name__ == "__main__":
     names = [n for n in a.only.split(",") if n] or list(ALL)
     for n in names:
         (ALL | dict(render_heavy=render_heavy, headline_windows=headline_windows, converged_mean=converged_mean,
-                                                    light_variants=light_variants))[n]()
+                                                    light_variants=light_variants, pointcloud=pointcloud))[n]()
     if a.heavy and "render_heavy" not in names:
         render_heavy()

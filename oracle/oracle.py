@@ -438,6 +438,12 @@ class RefOracle(_Oracle):
         self.lib.ref_load_off(path.encode(), _p(cnt), _p(pos), _p(nrm), _p(tri))
         return pos, nrm, tri
 
+    def save_pcd(self, particles7, path):
+        """PhotonMap::saveToPCD (PhotonMap.h:59-84) on a particle list."""
+        a = _c(particles7, _f).reshape(-1, 7)
+        self.lib.ref_save_pcd.restype, self.lib.ref_save_pcd.argtypes = None, [C.c_void_p, C.c_int64, C.c_char_p]
+        self.lib.ref_save_pcd(_p(a), len(a), path.encode())
+
     def save_ppm(self, rgb, path):
         h, w, _ = rgb.shape
         self.lib.ref_save_ppm(w, h, _p(_c(rgb, _f)), path.encode())

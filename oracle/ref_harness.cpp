@@ -603,6 +603,17 @@ void ref_save_ppm(int w, int h, const float* rgb, const char* path) {
   image.savePPM(path);
 }
 
+// PhotonMap::saveToPCD (PhotonMap.h:59-84) on a given particle list (7 floats each).
+void ref_save_pcd(const float* particles, int64_t n, const char* path) {
+  Quiet q;
+  PhotonMap pm;
+  for (int64_t i = 0; i < n; i++) {
+    const float* a = particles + 7 * i;
+    pm.m_list.push_back(Particle(Vec3f(a[0], a[1], a[2]), Vec3f(a[3], a[4], a[5]), a[6]));
+  }
+  pm.saveToPCD(path);
+}
+
 uint64_t ref_words_drawn(void) { return g_words_drawn; }
 
 }  // extern "C"

@@ -86,13 +86,14 @@ class Scene:
                 a.tofile(fh)
 
     @classmethod
-    def build(cls, width, height, mesh_dir="../meshes", input_off=None, subdivisions=0):
+    def build(cls, width, height, mesh_dir="../meshes", input_off=None, subdivisions=0, cache_dir=None):
         """The scene main() assembles (source/Main.cpp:165-208), built by the C++ host code
         (host/scene_host.cpp through lib/librt_host.so): Cornell box, 3 lights, the two meshes loaded
-        from `mesh_dir`; `input_off` replaces cube_tri.off; `subdivisions` midpoint-subdivides it."""
+        from `mesh_dir`; `input_off` ("a.off" or "a.off,b.off,...") replaces cube_tri.off (and cube_tri2.off, then
+        appends further meshes); `subdivisions` midpoint-subdivides the first; `cache_dir` enables the binary OFF cache."""
         lib = _host_lib()
-        h = lib.rth_scene_create(str(mesh_dir).encode(), (input_off or "").encode(), int(subdivisions), int(width),
-                                 int(height))
+        h = lib.rth_scene_create_cached(str(mesh_dir).encode(), (input_off or "").encode(), int(subdivisions),
+                                        int(width), int(height), (cache_dir or "").encode())
         if not h:
             raise RuntimeError(lib.rth_last_error().decode(errors="replace"))
         try:
@@ -158,6 +159,9 @@ def _host_lib():
         lib.rth_last_error.restype = C.c_char_p
         lib.rth_scene_create.restype = vp
         lib.rth_scene_create.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_int]
+        lib.rth_scene_create_cached.restype = vp
+        lib.rth_scene_create_cached.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_char_p]
+        lib.rth_save_pcd.argtypes = [C.c_char_p, vp, C.c_int64]
         lib.rth_scene_destroy.argtypes = [vp]
         lib.rth_scene_counts.argtypes = [vp, vp]
         lib.rth_scene_get.argtypes = [vp] * 9
@@ -459,12 +463,7 @@ class Renderer:
         """PhotonMap::saveToPCD (source/PhotonMap.h:59-84).  The reference's own call writes a
         header-only file (it runs before render and on a shadowed member); we write the real map."""
         nodes = self.kdtree()[0] if self.params.num_photons > 0 else np.zeros((0, 7), np.float32)
-        with open(filename, "w") as fh:
-            fh.write("VERSION .7\nFIELDS x y z normal_x normal_y normal_z\nSIZE 4 4 4 4 4 4\nTYPE F F F F F F\n"
-                     f"COUNT 1 1 1 1 1 1\nWIDTH {len(nodes)}\nHEIGHT 1\nVIEWPOINT 0 0 0 1 0 0 0\n"
-                     f"POINTS {len(nodes)}\nDATA ascii\n")
-            for p in nodes:
-                fh.write(" ".join(f"{v:g}" for v in p[:6]) + " \n")
+        save_pcd(filename, nodes)
 
     # ---- introspection ---------------------------------------------------------------------------
     def stats(self):
@@ -490,6 +489,12 @@ class Renderer:
         nodes = np.zeros((n.value, 16), np.float32)
         _capi.check(self.lib.rt_get_bvh(self._ctx, _capi.ptr(nodes), n.value, C.byref(n), C.byref(d)))
         return nodes, d.value
+
+
+def save_pcd(filename, photons7):
+    """PhotonMap::saveToPCD (source/PhotonMap.h:59-84) through the C++ host writer (the CLI's own)."""
+    a = np.ascontiguousarray(photons7, np.float32).reshape(-1, 7)
+    _host_lib().rth_save_pcd(str(filename).encode(), _capi.ptr(a), len(a))
 
 
 def device_count():

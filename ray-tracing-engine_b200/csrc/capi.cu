@@ -548,7 +548,7 @@ int render_to_device(rt_ctx* c, float* out_rgb_dev, int* out_cnt_dev, float* com
     }
     size_t free_b = 0, total_b = 0;
     CU(cudaMemGetInfo(&free_b, &total_b));
-    if (getenv("RT_TEST_OOM_ONCE")) free_b = std::min<size_t>(free_b, (size_t)64 << 20);  // force several batches
+    if (getenv("RT_TEST_OOM_ONCE")) free_b = std::min<size_t>(free_b, (size_t)16 << 20);  // force several batches
     c->auto_paths = std::max<size_t>(1, std::min<size_t>(free_b / 2 / bytes_per_path(nl), max_paths));
     spb = (int)std::max<size_t>(1, std::min<size_t>(c->auto_paths / std::max(c->npix, 1), 1 << 20));
     spb = std::max(1, std::min(spb, std::max(samp_end - samp_first, 1)));

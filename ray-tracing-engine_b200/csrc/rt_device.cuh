@@ -393,21 +393,35 @@ RT_DI float libm_sincosf_poly(double x, double x2, bool second_table, int n) {
   const double c = __fma_rn(x4, c2, q1);
   return (float)__fma_rn(x6, q2, c);
 }
-template <bool COS>
-RT_DI float libm_sincosf(float y) {
+// sinf(y) and cosf(y) of ONE argument: both calls reduce y the same way (same n, same remainder), so the reduction is
+// shared and only the two polynomials differ -- bit for bit what two separate libm calls return.
+RT_DI void libm_sincosf(float y, float& sin_y, float& cos_y) {
   const unsigned top = (__float_as_uint(y) >> 20) & 0x7ffu;  // abstop12
   const double x = (double)y;
   if (top < 0x3f4u) {  // |y| < pi/4
-    if (top < 0x398u) return COS ? 1.0f : y;  // |y| < 2^-12
-    return libm_sincosf_poly(x, __dmul_rn(x, x), false, COS ? 1 : 0);
+    if (top < 0x398u) {  // |y| < 2^-12
+      sin_y = y;
+      cos_y = 1.0f;
+      return;
+    }
+    const double x2 = __dmul_rn(x, x);
+    sin_y = libm_sincosf_poly(x, x2, false, 0);
+    cos_y = libm_sincosf_poly(x, x2, false, 1);
+    return;
   }
-  if (top >= 0x42fu) return COS ? cosf(y) : sinf(y);  // |y| >= 120, inf, NaN: never a finite argument on this path
+  if (top >= 0x42fu) {  // |y| >= 120, inf, NaN: never a finite argument on this path
+    sin_y = sinf(y);
+    cos_y = cosf(y);
+    return;
+  }
   // reduce_fast without TOINT_INTRINSICS: hpi_inv is 2/pi * 2^24
   const double r = __dmul_rn(x, 0x1.45F306DC9C883p+23);
   const int n = (__double2int_rz(r) + 0x800000) >> 24;
   const double xr = __fma_rn(-(double)n, 0x1.921FB54442D18p0, x);
   const double sign = ((n & 3) == 1 || (n & 3) == 2) ? -1.0 : 1.0;  // sign[] = {1, -1, -1, 1}
-  return libm_sincosf_poly(__dmul_rn(xr, sign), __dmul_rn(xr, xr), (n & 2) != 0, COS ? (n ^ 1) : n);
+  const double xs = __dmul_rn(xr, sign), x2 = __dmul_rn(xr, xr);
+  sin_y = libm_sincosf_poly(xs, x2, (n & 2) != 0, n);
+  cos_y = libm_sincosf_poly(xs, x2, (n & 2) != 0, n ^ 1);
 }
 
 // RayTracer.h:95-107 with maxRayAngle = float(pi/2).  asin in binary64 like the reference (the result is rounded to
@@ -422,8 +436,11 @@ RT_DI float3 hsphere_uniform_sample(Rng& g, float3 normal) {
   v2 = v_norm(v2);
   float theta = (float)asin(g.uniform_d0(hi));
   float phi = (float)__dmul_rn(6.283185307179586, g.uniform_d0(hi));
-  float3 direction = v_norm(v_add(v_scl(v1, libm_sincosf<true>(phi)), v_scl(v2, libm_sincosf<false>(phi))));
-  return v_norm(v_add(v_scl(normal, libm_sincosf<true>(theta)), v_scl(direction, libm_sincosf<false>(theta))));
+  float sp, cp, st, ct;
+  libm_sincosf(phi, sp, cp);
+  libm_sincosf(theta, st, ct);
+  float3 direction = v_norm(v_add(v_scl(v1, cp), v_scl(v2, sp)));
+  return v_norm(v_add(v_scl(normal, ct), v_scl(direction, st)));
 }
 // LightSource.h:46-49: the first draw scales m_horizontal, the second m_vertical (g++ evaluates the
 // right operand of the outer + first; pinned against the reference build by the oracle tests).
@@ -680,6 +697,17 @@ RT_DI void kd_knearest(const DScene& S, float3 q, int k, KdHeap& H, int* kst, in
 // exactly the reference's (tests: test_kdtree_and_knn_match_reference, test_knn_parity_at_scale).
 // sd/si: k slots, kst: 3 ints per frame, all with stride ks between a thread's consecutive slots.
 // ------------------------------------------------------------------------------------------------
+// Vec3::dist (Vec3.h:216-218) is sqrt(dot(a - b, a - b)); the k-NN loops compare distances, and a correctly rounded
+// square root costs ~10 instructions per visited node.  kd_dist2 is the argument of that square root (same operation
+// order), and kd_reject_from(best) a bound B with:  d2 >= B  =>  sqrt_rn(d2) >= best  (B = best*best rounded UP is
+// >= best^2, sqrt is monotone and sqrt_rn(best^2) = best).  So `dist < best` is false without taking the root
+// whenever d2 >= B; only the candidates that can actually enter pay for the root and the exact comparison.
+RT_DI float kd_dist2(float3 p, float3 q) {
+  const float3 a = v_sub(p, q);
+  return v_dot(a, a);
+}
+RT_DI float kd_reject_from(float best) { return __fmul_ru(best, best); }
+
 RT_DI unsigned long long kd_pack(float d, int idx) {  // distances are >= 0: their bit patterns order like the values
   return ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)idx;
 }
@@ -703,17 +731,20 @@ RT_DI bool kd_knearest_sorted(const DScene& S, float3 q, int k, unsigned long lo
     sc[(unsigned)(m + 1) * (unsigned)cs] = ((unsigned long long)dj << 32) | (unsigned)j;
   }
   float best = kd_dist_of(sc[(unsigned)(k - 1) * (unsigned)cs]);  // m_bestdist (a distance, not squared)
+  float reject2 = kd_reject_from(best);
   int sp = 0, b = 0, e = S.kd_count, axis = 0;
   unsigned nv = 0;
   while (e > b) {
     const int n = b + (e - b) / 2;
     nv++;
     const float4 p = __ldg(S.kd_pos + n);
-    const float dnode = v_dist(f3(p), q);
-    if (dnode < best) {
+    const float d2 = kd_dist2(f3(p), q);
+    float dnode;
+    if (d2 < reject2 && (dnode = __fsqrt_rn(d2)) < best) {
       // evict the largest; m_bestdist = the largest of the rest BEFORE the insertion (k == 1: libstdc++'s
       // front() after pop_heap is the evicted candidate itself), kdtree.h:93-96
       best = kd_dist_of(sc[(unsigned)(k > 1 ? k - 2 : 0) * (unsigned)cs]);
+      reject2 = kd_reject_from(best);
       const unsigned dn = __float_as_uint(dnode);
       int m = k - 2;
       unsigned long long w = 0;
@@ -746,7 +777,7 @@ RT_DI bool kd_knearest_sorted(const DScene& S, float3 q, int k, unsigned long lo
         // For k >= 2 m_bestdist never grows (it is the second largest candidate and candidates only get
         // closer), so a far side that is already skippable now is not pushed at all.  (k == 1: m_bestdist is
         // the distance of the candidate evicted LAST, which can go up again.)
-        const float t_sq = __double2float_rd(__dmul_rn((double)dx, (double)dx));
+        const float t_sq = __fmul_rd(dx, dx);  // the largest binary32 <= dx*dx (the binary64 square is exact)
         const float t_pl = __fmul_rn(fabsf(dx), 0.9999995f);
         const float thr = fmaxf(t_sq, t_pl);
         if (best > thr || k == 1) {
@@ -844,16 +875,19 @@ RT_DI void kd_knearest_heap(const DScene& S, float3 q, int k, unsigned long long
   for (int j = 0; j < k; j++) H.set(j, kd_pack(v_dist(f3(__ldg(S.kd_pos + j)), q), j));  // kdtree.h:186
   H.make(k);
   float best = kd_dist_of(H.get(0));  // m_bestdist
+  float reject2 = kd_reject_from(best);
   int sp = 0, b = 0, e = S.kd_count, axis = 0;
   unsigned nv = 0;
   while (e > b) {
     const int n = b + (e - b) / 2;
     nv++;
     const float4 p = __ldg(S.kd_pos + n);
-    const float dnode = v_dist(f3(p), q);
-    if (dnode < best) {  // kdtree.h:92-99
+    const float d2 = kd_dist2(f3(p), q);
+    float dnode;
+    if (d2 < reject2 && (dnode = __fsqrt_rn(d2)) < best) {  // kdtree.h:92-99
       H.pop(k);
       best = kd_dist_of(H.get(0));  // the new top BEFORE the insertion (for k == 1: the evicted candidate itself)
+      reject2 = kd_reject_from(best);
       H.push_up(k - 1, 0, kd_pack(dnode, n));
     }
     int nb = b, ne = b;
@@ -868,7 +902,7 @@ RT_DI void kd_knearest_heap(const DScene& S, float3 q, int k, unsigned long long
       const int fb = left_near ? n + 1 : b, fe = left_near ? e : n;
       axis = axis == 2 ? 0 : axis + 1;
       if (fe > fb) {
-        const float t_sq = __double2float_rd(__dmul_rn((double)dx, (double)dx));
+        const float t_sq = __fmul_rd(dx, dx);  // the largest binary32 <= dx*dx (the binary64 square is exact)
         const float t_pl = __fmul_rn(fabsf(dx), 0.9999995f);
         const float thr = fmaxf(t_sq, t_pl);
         if (best > thr || k == 1) {
@@ -905,13 +939,16 @@ RT_DI void kd_knearest_exact(const DScene& S, float3 q, int k, unsigned long lon
                              unsigned long long& visits) {
   int cnt = 0;
   unsigned long long worst = ~0ull;  // packed k-th candidate; all-ones while fewer than k are held
+  float reject2 = INFINITY;          // d2 >= reject2  =>  the distance is above the k-th one (see kd_reject_from)
   int sp = 0, b = 0, e = S.kd_count, axis = 0;
   unsigned nv = 0;
   while (e > b) {
     const int n = b + (e - b) / 2;
     nv++;
     const float4 p = __ldg(S.kd_pos + n);
-    const unsigned long long cand = kd_pack(v_dist(f3(p), q), n);
+    const float d2 = kd_dist2(f3(p), q);
+    unsigned long long cand = ~0ull;
+    if (!(d2 >= reject2)) cand = kd_pack(__fsqrt_rn(d2), n);  // (a NaN distance goes the slow way, as before)
     if (cand < worst) {
       int m = (cnt < k ? cnt : k - 1) - 1;  // last slot that stays
       unsigned long long w = 0;
@@ -921,7 +958,11 @@ RT_DI void kd_knearest_exact(const DScene& S, float3 q, int k, unsigned long lon
       }
       sc[(unsigned)(m + 1) * (unsigned)cs] = cand;
       if (cnt < k) cnt++;
-      if (cnt == k) worst = sc[(unsigned)(k - 1) * (unsigned)cs];
+      if (cnt == k) {
+        worst = sc[(unsigned)(k - 1) * (unsigned)cs];
+        // a tie with the k-th distance can still enter on its index: reject only from the next binary32 up
+        reject2 = kd_reject_from(__uint_as_float(__float_as_uint(kd_dist_of(worst)) + 1u));
+      }
     }
     float pa = p.x, qa = q.x;
     if (axis == 1) pa = p.y, qa = q.y;

@@ -1,6 +1,7 @@
 // command_line.h -- the reference's command line (source/CommandLine.h:9-102): same flags, defaults,
-// banner and error texts.  Additive options (absent = stock behaviour): -i/-input <file.off> replaces
-// ../meshes/cube_tri.off, -meshdir <dir>, -subdiv <n>, -seed <n>, -device <n>, -brute, -update <n> (rewrite
+// banner and error texts.  Additive options (absent = stock behaviour): -i/-input <a.off>[,<b.off>[,...]] replaces
+// ../meshes/cube_tri.off (and cube_tri2.off, then appends further meshes), -meshdir <dir>, -cache <dir> (binary OFF
+// cache), -subdiv <n>, -seed <n>, -device <n>, -brute, -update <n> (rewrite
 // update.ppm every n sample passes as the reference does after every pass, Renderer.cpp:268-269; 0 = at the end),
 // -p6 1 (binary P6 output instead of ASCII P3, same quantisation).
 #pragma once
@@ -13,7 +14,7 @@ struct CommandLine {
   size_t width = 380, height = 270, numRays = 16, mode = 0, numPhotons = 0, k = 5;  // CommandLine.h:11-18
   std::string outputFilename = "output.ppm";
   // additive
-  std::string input, meshDir = "../meshes";
+  std::string input, meshDir = "../meshes", cacheDir;  // -cache <dir>: binary OFF cache (off by default)
   int subdiv = 0, device = 0, update = 0;
   bool knnExact = false;  // -knn exact: canonical exact k nearest photons (RT_FLAG_KNN_EXACT) instead of the
                           // reference's kdtree::knearest (default, "-knn reference")
@@ -29,7 +30,7 @@ struct CommandLine {
                  "tracing)>][-p/-numPhotons <number of photons for a photon map. If "
                  "defined, photon map-based rendering is used.>][-k <number of "
                  "neighbours in photon mapping. Use only with -p/-numPhotons>]"
-                 "[-i/-input <mesh.off>][-meshdir <dir>][-subdiv <n>][-seed <n>][-device <n>][-brute 1][-update <n>][-p6 1][-knn reference|exact]"
+                 "[-i/-input <mesh.off>[,<mesh2.off>...]][-meshdir <dir>][-cache <dir>][-subdiv <n>][-seed <n>][-device <n>][-brute 1][-update <n>][-p6 1][-knn reference|exact]"
               << std::endl;
   }
 
@@ -52,6 +53,7 @@ struct CommandLine {
       else if (a == "-k") k = std::atoi(argv[++i]);
       else if (a == "-i" || a == "-input") input = argv[++i];
       else if (a == "-meshdir") meshDir = argv[++i];
+      else if (a == "-cache") cacheDir = argv[++i];
       else if (a == "-subdiv") subdiv = std::atoi(argv[++i]);
       else if (a == "-seed") seed = std::strtoull(argv[++i], nullptr, 10);
       else if (a == "-device") device = std::atoi(argv[++i]);

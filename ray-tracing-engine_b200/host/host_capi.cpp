@@ -14,12 +14,14 @@ extern "C" {
 
 const char* rth_last_error(void) { return g_err.c_str(); }
 
-void* rth_scene_create(const char* mesh_dir, const char* input_off, int subdivisions, int width, int height) {
+static void* scene_create(const char* mesh_dir, const char* input_off, int subdivisions, int width, int height,
+                          const char* cache_dir) {
   rth::HostScene* s = new rth::HostScene();
   try {
     rth::SceneOptions opt;
     if (mesh_dir && mesh_dir[0]) opt.mesh_dir = mesh_dir;
     if (input_off) opt.input_off = input_off;
+    if (cache_dir) opt.cache_dir = cache_dir;
     opt.subdivisions = subdivisions;
     rth::build_reference_scene(width, height, opt, *s);
   } catch (const std::exception& e) {
@@ -28,6 +30,14 @@ void* rth_scene_create(const char* mesh_dir, const char* input_off, int subdivis
     return nullptr;
   }
   return s;
+}
+void* rth_scene_create(const char* mesh_dir, const char* input_off, int subdivisions, int width, int height) {
+  return scene_create(mesh_dir, input_off, subdivisions, width, height, nullptr);
+}
+// the same with the binary OFF cache (SceneOptions::cache_dir); input_off may be a comma-separated list
+void* rth_scene_create_cached(const char* mesh_dir, const char* input_off, int subdivisions, int width, int height,
+                              const char* cache_dir) {
+  return scene_create(mesh_dir, input_off, subdivisions, width, height, cache_dir);
 }
 void rth_scene_destroy(void* h) { delete static_cast<rth::HostScene*>(h); }
 void rth_scene_counts(void* h, int32_t out[4]) {
@@ -82,6 +92,13 @@ void rth_background(int width, int height, float* rgb) {
 void rth_save_ppm(const char* path, int width, int height, const float* rgb) {
   std::vector<float> v(rgb, rgb + (size_t)width * height * 3);
   rth::save_ppm(path, width, height, v);
+}
+
+// PhotonMap::saveToPCD (source/PhotonMap.h:59-84) for n particles of 7 floats
+void rth_save_pcd(const char* path, const float* photons7, int64_t n) {
+  std::vector<rt_photon> v((size_t)n);
+  std::memcpy(v.data(), photons7, sizeof(rt_photon) * (size_t)n);
+  rth::save_pcd(path, v);
 }
 
 void rth_save_ppm_binary(const char* path, int width, int height, const float* rgb) {

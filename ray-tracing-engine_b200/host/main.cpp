@@ -41,6 +41,7 @@ int main(int argc, char** argv) {
     opt.mesh_dir = args.meshDir;
     opt.input_off = args.input;
     opt.subdivisions = args.subdiv;
+    opt.cache_dir = args.cacheDir;
     rth::build_reference_scene((int)args.width, (int)args.height, opt, scene);
   } catch (const std::exception& e) {
     std::cerr << e.what() << std::endl;  // Main.cpp:188-191

@@ -9,7 +9,9 @@
 #include <fstream>
 #include <iostream>
 #include <map>
+#include <sstream>
 #include <stdexcept>
+#include <sys/stat.h>
 
 namespace rth {
 namespace {
@@ -94,6 +96,57 @@ void HostMesh::load_off(const std::string& filename) {
     throw std::runtime_error(std::string("Error Loading OFF file: ") + e.what());  // Mesh.h:84-88
   }
   recompute_normals();
+}
+
+bool HostMesh::load_off_cached(const std::string& filename, int subdivisions, const std::string& cache_dir) {
+  auto plain = [&]() {
+    load_off(filename);
+    for (int i = 0; i < subdivisions; i++) subdivide();
+  };
+  struct stat st;
+  if (cache_dir.empty() || stat(filename.c_str(), &st) != 0) {  // no cache, or let load_off report the missing file
+    plain();
+    return false;
+  }
+  std::string base = filename.substr(filename.find_last_of('/') == std::string::npos ? 0 : filename.find_last_of('/') + 1);
+  std::ostringstream name;
+  name << cache_dir << "/" << base << "." << (long long)st.st_size << "." << (long long)st.st_mtime << ".s" << subdivisions
+       << ".offbin";
+  const char magic[8] = {'O', 'F', 'F', 'B', 'I', 'N', '0', '1'};
+  {
+    std::ifstream in(name.str().c_str(), std::ios::binary);
+    char m[8];
+    uint64_t nv = 0, nt = 0;
+    if (in && in.read(m, 8) && std::equal(m, m + 8, magic) && in.read((char*)&nv, 8) && in.read((char*)&nt, 8) &&
+        nv < (1ull << 31) && nt < (1ull << 31)) {
+      positions.resize(nv);
+      normals.resize(nv);
+      triangles.resize(3 * nt);
+      in.read((char*)positions.data(), (std::streamsize)(nv * sizeof(Float3)));
+      in.read((char*)normals.data(), (std::streamsize)(nv * sizeof(Float3)));
+      in.read((char*)triangles.data(), (std::streamsize)(3 * nt * sizeof(int32_t)));
+      if (in && in.peek() == std::ifstream::traits_type::eof()) return true;
+    }
+  }
+  plain();
+  mkdir(cache_dir.c_str(), 0755);  // best effort: a cache that cannot be written is only slower
+  const std::string tmp = name.str() + ".tmp";
+  std::ofstream out(tmp.c_str(), std::ios::binary);
+  if (out) {
+    const uint64_t nv = positions.size(), nt = triangles.size() / 3;
+    out.write(magic, 8);
+    out.write((const char*)&nv, 8);
+    out.write((const char*)&nt, 8);
+    out.write((const char*)positions.data(), (std::streamsize)(nv * sizeof(Float3)));
+    out.write((const char*)normals.data(), (std::streamsize)(nv * sizeof(Float3)));
+    out.write((const char*)triangles.data(), (std::streamsize)(3 * nt * sizeof(int32_t)));
+    out.close();
+    if (out)
+      std::rename(tmp.c_str(), name.str().c_str());
+    else
+      std::remove(tmp.c_str());
+  }
+  return false;
 }
 
 void HostMesh::recompute_normals() {
@@ -224,10 +277,21 @@ void build_reference_scene(int width, int height, const SceneOptions& opt, HostS
   right_wall.material = material(0.6f, 0.3f, {0.3f, 0.9f, 0.3f}, walls_f0);
   cube.material = material(0.1f, 0.1f, {0.9f, 0.9f, 0.9f}, {1.0f, 0.86f, 0.57f});
   cube2.material = material(0.8f, 0.9f, {0.4f, 0.4f, 0.9f}, {(float)0.3, (float)0.3, (float)0.3});
-  // Main.cpp:184-191
-  cube.load_off(opt.input_off.empty() ? opt.mesh_dir + "/cube_tri.off" : opt.input_off);
-  cube2.load_off(opt.mesh_dir + "/cube_tri2.off");
-  for (int i = 0; i < opt.subdivisions; i++) cube.subdivide();
+  // Main.cpp:184-191; -i a.off,b.off,...: the list replaces mesh_cube, mesh_cube2 and appends further meshes
+  std::vector<std::string> inputs;
+  {
+    std::stringstream list(opt.input_off);
+    std::string item;
+    while (std::getline(list, item, ','))
+      if (!item.empty()) inputs.push_back(item);
+  }
+  cube.load_off_cached(inputs.size() > 0 ? inputs[0] : opt.mesh_dir + "/cube_tri.off", opt.subdivisions, opt.cache_dir);
+  cube2.load_off_cached(inputs.size() > 1 ? inputs[1] : opt.mesh_dir + "/cube_tri2.off", 0, opt.cache_dir);
+  std::vector<HostMesh> more(inputs.size() > 2 ? inputs.size() - 2 : 0);
+  for (size_t i = 0; i < more.size(); i++) {
+    more[i].material = (i % 2 == 0) ? cube.material : cube2.material;
+    more[i].load_off_cached(inputs[i + 2], 0, opt.cache_dir);
+  }
   // Main.cpp:39-86,194-196
   const float b = 1.51f, c = 1.5f;
   add_plane(walls, {b, -1.f, b}, {b, -1.f, -b}, {-b, -1.f, b}, {-b, -1.f, -b}, {0.f, 1.f, 0.f});    // ground
@@ -244,6 +308,10 @@ void build_reference_scene(int width, int height, const SceneOptions& opt, HostS
   out.add_mesh(right_wall);
   out.add_mesh(cube);
   out.add_mesh(cube2);
+  for (size_t i = 0; i < more.size(); i++) {
+    more[i].rotate_y((float)((i % 2 == 0 ? 1.0 : -1.0) * (M_PI / 4.5f)));
+    out.add_mesh(more[i]);
+  }
 }
 
 void fill_background(int width, int height, std::vector<float>& rgb) {

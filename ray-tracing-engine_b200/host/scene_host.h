@@ -27,6 +27,12 @@ struct HostMesh {
   // where the reference skips them, normals recomputed.  Throws std::runtime_error with the
   // reference's messages.
   void load_off(const std::string& filename);
+  // load_off + `subdivisions` midpoint subdivisions through a binary cache: `<cache_dir>/<name>.<size>.<mtime>.s<n>.offbin`
+  // holds the loaded mesh (positions, normals, triangles as raw binary32 / int32 -- exactly what load_off and subdivide
+  // produce, so a cached load is bit-identical) and is (re)written whenever it is missing or the .off file changed.
+  // An empty cache_dir means no cache.  Parsing 23 MB of ASCII and subdividing to 1.2 M triangles takes seconds; the
+  // cached load is one read.  Returns true when the mesh came from the cache.
+  bool load_off_cached(const std::string& filename, int subdivisions, const std::string& cache_dir);
   // Mesh::recomputeNormals (source/Mesh.h:45-55): sum of UNIT face normals per vertex, normalised.
   void recompute_normals();
   // rotationY (source/Main.cpp:88-99): positions only -- the reference leaves the normals unrotated.
@@ -54,8 +60,12 @@ rt_light make_light(Float3 position, Float3 color, Float3 direction, float inten
 
 struct SceneOptions {
   std::string mesh_dir = "../meshes";  // the reference resolves ../meshes/ from its cwd (Main.cpp:186-187)
-  std::string input_off;               // replaces cube_tri.off as mesh_cube when non-empty
-  int subdivisions = 0;                // midpoint subdivisions applied to the input mesh
+  // -i a.off[,b.off[,c.off...]]: the first file replaces cube_tri.off as mesh_cube, the second cube_tri2.off as
+  // mesh_cube2; further files are appended after them as additional meshes, alternating the two cubes' materials and
+  // rotations (Main.cpp:139-144,201-202) in scene order -- mesh order is the tie-break order of rayTrace
+  std::string input_off;
+  int subdivisions = 0;                // midpoint subdivisions applied to the FIRST input mesh
+  std::string cache_dir;               // binary OFF cache directory ("" = off); see HostMesh::load_off_cached
 };
 // The scene main() assembles (source/Main.cpp:165-208): camera, 3 lights, Cornell box, two meshes.
 void build_reference_scene(int width, int height, const SceneOptions& opt, HostScene& out);

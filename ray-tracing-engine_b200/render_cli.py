@@ -4,7 +4,7 @@
         -m ray_tracing_engine_b200.render_cli -width 1920 -height 1080 -m 1 -N 1024 -i ../meshes/example.off
 
 Same flags and defaults as `bin/RayTracer` (-w/-width, -h/-height, -o/-output, -N/-n/-numRays, -m/-mode,
--p/-numPhotons, -k; additive: -i/-input, -meshdir, -subdiv, -seed, -p6, -shard tile|sample).  The scene is assembled by
+-p/-numPhotons, -k; additive: -i/-input a.off[,b.off...], -meshdir, -cache, -subdiv, -seed, -p6, -shard tile|sample).  The scene is assembled by
 the C++ host code (lib/librt_host.so), every rank renders its share (interleaved 16x16 tiles --
 bit-identical to one GPU -- or sample-index ranges), photons are emitted sharded and all-gathered, the frame is
 sum-reduced to rank 0 over NCCL, composited on its GPU and written as output.ppm.  Without torchrun it renders on one GPU.
@@ -18,11 +18,11 @@ import time
 
 def parse(argv):
     a = dict(width=380, height=270, numRays=16, mode=0, numPhotons=0, k=5, output="output.ppm", input=None,
-             meshdir="../meshes", subdiv=0, seed=1, p6=0, shard="tile")
+             meshdir="../meshes", subdiv=0, seed=1, p6=0, shard="tile", cache=None)
     names = {"-w": "width", "-width": "width", "-h": "height", "-height": "height", "-o": "output", "-output": "output",
              "-N": "numRays", "-n": "numRays", "-numRays": "numRays", "-m": "mode", "-mode": "mode", "-p": "numPhotons",
              "-numPhotons": "numPhotons", "-k": "k", "-i": "input", "-input": "input", "-meshdir": "meshdir",
-             "-subdiv": "subdiv", "-seed": "seed", "-p6": "p6", "-shard": "shard"}
+             "-subdiv": "subdiv", "-seed": "seed", "-p6": "p6", "-shard": "shard", "-cache": "cache"}
     i = 0
     while i < len(argv):
         flag = argv[i]
@@ -31,7 +31,7 @@ def parse(argv):
         if flag not in names:
             raise SystemExit(f"Unknown argument <{flag}>")
         key, val = names[flag], argv[i + 1]
-        a[key] = val if key in ("output", "input", "meshdir", "shard") else int(val)
+        a[key] = val if key in ("output", "input", "meshdir", "shard", "cache") else int(val)
         i += 2
     if a["mode"] != 1:
         a["mode"] = 0  # CommandLine.h:84-87
@@ -56,7 +56,7 @@ def main(argv=None):
     if own_group:
         dist.init_process_group("nccl", device_id=dev)
     t0 = time.time()
-    scene = rt.Scene.build(a["width"], a["height"], a["meshdir"], a["input"], a["subdiv"])
+    scene = rt.Scene.build(a["width"], a["height"], a["meshdir"], a["input"], a["subdiv"], a["cache"])
     background = rt.Image(a["width"], a["height"]).fillBackground().pixels
     if world > 1:
         img = D.render_distributed(scene, a["numRays"], a["mode"], a["numPhotons"], a["k"], background=background,

@@ -289,3 +289,56 @@ def test_restated_libm_sinf_cosf_equals_this_machines_libm(tmp_path):
     out = subprocess.run([exe, "38000000", "40c90fdc", "5"], capture_output=True, text=True, check=True).stdout.split()
     n, bad_sin, bad_cos = (int(v) for v in out)
     assert n > 29_000_000 and bad_sin == 0 and bad_cos == 0, out
+
+
+def test_pointcloud_writer_matches_the_references(tmp_path):
+    """PhotonMap::saveToPCD (PhotonMap.h:59-84): the C++ host writer (the CLI's own, also behind
+    Renderer.savePhotonMap) produces byte for byte the file the reference's writer produced for the same particles
+    (tests/golden/pointcloud_golden.pcd, generated by oracle/gen_golden.py: pointcloud) -- and, where the reference
+    build is present, what it produces right now."""
+    plist = np.load(os.path.join(GOLD, "pointcloud_input.npy"))
+    out = str(tmp_path / "ours.pcd")
+    rt.save_pcd(out, plist)
+    want = open(os.path.join(GOLD, "pointcloud_golden.pcd"), "rb").read()
+    assert open(out, "rb").read() == want
+    from oracle import oracle as O
+    if O.have_ref():
+        live = str(tmp_path / "ref.pcd")
+        O.RefOracle().save_pcd(plist, live)
+        assert open(live, "rb").read() == want
+    rt.save_pcd(out, np.zeros((0, 7), np.float32))  # the reference's own call writes this header-only file (164 bytes)
+    assert len(open(out, "rb").read()) == 164
+
+
+@needs_meshes
+def test_input_list_and_binary_off_cache(tmp_path):
+    """-i a.off,b.off,c.off: the first two replace mesh_cube / mesh_cube2, further ones are appended in order; the
+    binary OFF cache returns bit-identical meshes, is keyed by file size + mtime + subdivisions, and survives a
+    corrupt cache file."""
+    low, cube, cube2 = (os.path.join(MESHES, f) for f in ("example_low_res.off", "cube_tri.off", "cube_tri2.off"))
+    stock = rt.Scene.build(64, 64, MESHES)
+    one = rt.Scene.build(64, 64, MESHES, low)
+    assert one.M == 5 and one.T == stock.T - 12 + 1200
+    same = rt.Scene.build(64, 64, MESHES, f"{cube},{cube2}")
+    assert beq(same.pos, stock.pos) and (same.tri == stock.tri).all() and beq(same.nrm, stock.nrm)
+    three = rt.Scene.build(64, 64, MESHES, f"{low},{cube2},{cube}")
+    assert three.M == 6 and three.T == one.T + 12
+    assert beq(three.pos[:one.V], one.pos) and (three.tri[:one.T] == one.tri).all()
+    # the appended mesh gets mesh_cube's material and rotation: it is the stock scene's mesh 3
+    a, b = stock.mesh_vtx_off[3], stock.mesh_vtx_off[4]
+    assert beq(three.pos[one.V:], stock.pos[a:b]) and beq(three.mats[5], stock.mats[3])
+    # cache: first build writes, second reads; both equal the uncached build
+    cache = str(tmp_path / "cache")
+    plain = rt.Scene.build(64, 64, MESHES, low, 2)
+    first = rt.Scene.build(64, 64, MESHES, low, 2, cache)
+    files = sorted(os.listdir(cache))
+    assert len(files) == 2 and all(f.endswith(".offbin") for f in files) and any(".s2." in f for f in files)
+    second = rt.Scene.build(64, 64, MESHES, low, 2, cache)
+    for s in (first, second):
+        assert beq(s.pos, plain.pos) and beq(s.nrm, plain.nrm) and (s.tri == plain.tri).all()
+    with open(os.path.join(cache, [f for f in files if ".s2." in f][0]), "r+b") as fh:  # truncate: must be re-parsed
+        fh.truncate(100)
+    third = rt.Scene.build(64, 64, MESHES, low, 2, cache)
+    assert beq(third.pos, plain.pos) and (third.tri == plain.tri).all()
+    with pytest.raises(RuntimeError):
+        rt.Scene.build(64, 64, MESHES, "/nonexistent/x.off", 0, cache)

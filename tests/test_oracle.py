@@ -154,6 +154,59 @@ def test_photon_render_golden(gold):
         assert beq(r["samples"], g["samples"]) and beq(r["found"], g["found"])
 
 
+@pytest.mark.parametrize("name", ["stock_1light", "stock_5lights"])
+def test_other_light_counts_golden(gold, name):
+    """Round 2: scenes with 1 and 5 lights (Renderer.cpp:49 and PhotonMap.h:24 loop over any number): the
+    restatement reproduces the reference's samples and its emitted photon list bit for bit."""
+    g = gold(f"render_{name}_win.npz")
+    port = port_for(name)
+    for mode, N in ((0, 1), (1, 3)):
+        r = port.render(N, mode, SEED, window=tuple(g["window"]), want_samples=True)
+        assert beq(r["samples"], g[f"samples_m{mode}"]) and (r["found"] == g[f"found_m{mode}"]).all()
+    plist, hist = port.photon_map_create(3000, SEED).get()
+    assert beq(plist, g["photons"]) and (hist == g["photon_hist"]).all()
+
+
+def test_large_k_golden(gold):
+    """kdtree::knearest for k beyond 64 (kdtree.h:180-183 accepts any k <= nodes)."""
+    g, ph = gold("knn_large_k.npz"), gold("photons.npz")
+    pm = port_for("stock").photon_map_from_list(ph["list"])
+    for k in (65, 100, 300):
+        out, _ = pm.knn(g["queries"], k)
+        assert beq(out[:, :, :3], g[f"knn_{k}"]), k
+
+
+def test_headline_window_golden_sums(gold):
+    """The N = 128 headline windows (example.off scene): the restatement reproduces a 16-sample slice of the cfg2
+    window bit for bit (the whole window is ~25 CPU-minutes; the GPU tests check all 128 samples)."""
+    g = gold("render_example_m1_N128_win.npz")
+    x0, y0, x1, y1 = (int(v) for v in g["window"])
+    port = port_for("example")
+    r = port.render(128, 1, SEED, window=(x0, y0, x0 + 8, y0 + 8), samples=(0, 16), want_samples=True, threads=8)
+    b = np.ascontiguousarray(r["samples"], np.float32).view(np.uint32).astype(np.uint64)
+    h = (b[..., 0] * np.uint64(0x9E3779B1) ^ b[..., 1]) * np.uint64(0x85EBCA77) ^ b[..., 2]
+    h ^= h >> np.uint64(29)
+    h = (h * np.uint64(0xC2B2AE3D)) & np.uint64(0xFFFFFFFFFFFF)
+    h16 = ((h >> np.uint64(24)) & np.uint64(0xFFFF)).astype(np.uint16)
+    assert (h16 == g["hash16"][:16, :8, :8]).all()
+
+
+def test_restatement_agrees_with_the_independent_converged_mean(gold):
+    """SURVEY.md section 4 test 5 on the CPU side: the restatement with the counter-based streams (N = 128, an
+    unrelated seed) against the reference's converged mean from its OWN serial engine (N = 2048 x 3 seeds).  Nothing is
+    shared, so the difference is Monte-Carlo noise of known size: RMSE within +-6 % of sqrt(var (1/128 + 1/6144))."""
+    g = gold("converged_stock_m1_105.npz")
+    flat = O.FlatScene.load(scene_path("stock"))
+    flat.w = flat.h = int(g["W"][0])
+    r = O.PortOracle(flat).render(128, 1, 777, threads=8)
+    diff = r["sum_rgb"].astype(np.float64) / 128.0 - g["mean"]
+    expected = float(np.sqrt(g["var"].astype(np.float64).mean() * (1 / 128 + 1 / 6144)))
+    rmse = float(np.sqrt((diff ** 2).mean()))
+    assert 0.94 * expected <= rmse <= 1.06 * expected, (rmse, expected)
+    assert abs(float(diff.mean())) <= 4 * expected / flat.w
+    assert np.abs(r["counter"] / 128.0 - g["hit_fraction"]).max() == 0.0
+
+
 def test_stock_md5_recorded():
     txt = open(os.path.join(GOLD, "stock_binary_md5.txt")).read()
     assert txt.startswith("036d13f6d213e36061f97b32db7ba3fe")  # SURVEY.md section 4
