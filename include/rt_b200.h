@@ -268,6 +268,12 @@ int rt_reset_stats(rt_ctx* ctx);
 int rt_get_bvh(rt_ctx* ctx, float* nodes16, int64_t capacity_nodes, int32_t* num_nodes, int32_t* depth);
 /* leaf slot -> global triangle index of the context's BVH (num_triangles ints) */
 int rt_get_bvh_slots(rt_ctx* ctx, int32_t* slot_triangle, int64_t capacity);
+/* The host-side kd-tree builder alone (pure host function, needs no device): photons7_inout holds n particles in
+ * emission order on entry and the node array of kdtree::make_tree (source/kdtree.h:60-69, in-order layout) on exit.
+ * canonical = 0: libstdc++'s std::nth_element with the reference's comparator -- the reference's own tree;
+ * canonical != 0: the tree of the exact k-NN mode (photons ordered by (coordinate, list index)), the one the device
+ * builder (csrc/kd_build.cu) produces; orig_index (nullable) receives the list index of every node. */
+int rt_build_kdtree_host(float* photons7_inout, int64_t n, int32_t canonical, int32_t* orig_index, int32_t* height);
 /* The host-side BVH builder alone (pure host function, needs no device): the split policy of
  * BVH::from_triangles (source/BVH.h:100-161) per mesh plus the top-level join, exactly what rt_create uploads.
  * nodes16: capacity_nodes*16 floats (layout in csrc/host_build.h); slot_triangle: num_triangles ints

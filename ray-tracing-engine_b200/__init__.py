@@ -497,6 +497,16 @@ def save_pcd(filename, photons7):
     _host_lib().rth_save_pcd(str(filename).encode(), _capi.ptr(a), len(a))
 
 
+def build_kdtree_host(photons7, canonical=False):
+    """The host kd-tree builder alone (no device needed): (nodes [n,7] in kdtree::make_tree's array order, list index
+    of every node or None, height).  canonical=True: the tree of the exact k-NN mode (see rt_build_kdtree_host)."""
+    a = np.ascontiguousarray(photons7, np.float32).reshape(-1, 7).copy()
+    orig = np.zeros(len(a), np.int32)
+    h = C.c_int32()
+    _capi.check(_capi.load().rt_build_kdtree_host(_capi.ptr(a), len(a), 1 if canonical else 0, _capi.ptr(orig), C.byref(h)))
+    return a, (orig if canonical else None), h.value
+
+
 def device_count():
     return _capi.load().rt_device_count()
 

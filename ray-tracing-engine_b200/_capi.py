@@ -109,6 +109,7 @@ SYMBOLS = {
     "rt_reset_stats": (C.c_int, [_vp]),
     "rt_get_bvh": (C.c_int, [_vp, _vp, _i64, _vp, _vp]),
     "rt_get_bvh_slots": (C.c_int, [_vp, _vp, _i64]),
+    "rt_build_kdtree_host": (C.c_int, [_vp, _i64, _i32, _vp, _vp]),
     "rt_build_bvh_host": (C.c_int, [C.POINTER(rt_scene), C.c_float, _vp, _i64, _vp, _vp, _vp]),
 }
 

@@ -20,6 +20,7 @@
 #include "../../include/rt_b200.h"
 #include "bvh_build.h"
 #include "host_build.h"
+#include "kd_build.h"
 #include "kernels.h"
 
 using namespace rtb;
@@ -85,7 +86,11 @@ struct rt_ctx {
   Bvh bvh;
   bool bvh_on_device = false;  // built by csrc/bvh_build.cu: bvh.nodes holds only the top-level join on the host
   // photon map
-  std::vector<float> kd_nodes7;
+  std::vector<float> kd_nodes7;   // host copy of the kd-ordered nodes (lazily fetched when the tree was built on the device)
+  bool kd_host_valid = true;
+  int64_t kd_n = 0;
+  DevBuf<int> d_kd_orig;           // device-built tree: list index of the photon at every array position
+  bool kd_on_device = false;
   DevBuf<float4> d_kd_pos, d_kd_dir;
   int kd_height = 0;
   bool photon_map_built = false;
@@ -672,6 +677,7 @@ int rt_destroy(rt_ctx* c) {
   c->d_hit_path.release();
   c->d_lights_ext.release();
   c->d_knn_scratch.release();
+  c->d_kd_orig.release();
   c->d_perm.release();
   c->d_sorted.release();
   c->d_sort_hist.release();
@@ -1274,10 +1280,69 @@ int rt_emit_photons(rt_ctx* c, int32_t first_path, int32_t num_paths, rt_photon*
   return rc;
 }
 
+// The canonical tree of the exact k-NN mode (RT_FLAG_KNN_EXACT) is built on the device (csrc/kd_build.cu) unless
+// RT_KD_BUILD=host; the reference-exact gather needs libstdc++'s nth_element tie placement and always builds on the host.
+static bool kd_build_on_device(const rt_ctx* c) {
+  if (!(c->params.flags & RT_FLAG_KNN_EXACT)) return false;
+  const char* e = getenv("RT_KD_BUILD");
+  return !(e && std::string(e) == "host");
+}
+static void kd_installed(rt_ctx* c, int64_t n) {
+  c->scene.kd_pos = c->d_kd_pos.p;
+  c->scene.kd_dir = c->d_kd_dir.p;
+  c->scene.kd_count = (int)n;
+  c->kd_n = n;
+  c->stats.photons_stored = n;
+  c->photon_map_built = true;
+  c->photon_map_seed = c->params.seed;
+  c->photon_map_requested = c->params.num_photons;
+}
+// the list (emission order, 7 floats per particle) is in device memory: build the canonical tree there
+static int install_photons_device_build(rt_ctx* c, const float* d_p7, int64_t n) {
+  const double t0 = now_ms();
+  CU(c->d_kd_pos.ensure((size_t)std::max<int64_t>(n, 1)));
+  CU(c->d_kd_dir.ensure((size_t)std::max<int64_t>(n, 1)));
+  CU(c->d_kd_orig.ensure((size_t)std::max<int64_t>(n, 1)));
+  std::string err;
+  long long launches = 0;
+  if (!build_kdtree_device(d_p7, (int)n, c->d_kd_pos.p, c->d_kd_dir.p, c->d_kd_orig.p, c->stream, &c->kd_height, &launches, err))
+    return fail(RT_ERR_CUDA, "device kd-tree build failed: " + err);
+  CU(cudaStreamSynchronize(c->stream));
+  c->stats.kernel_launches += (uint64_t)launches;
+  c->stats.kd_build_ms = now_ms() - t0;
+  if (c->kd_height > kKdStack) return fail(RT_ERR_INVALID, "kd-tree deeper than the device stack");
+  c->kd_on_device = true;
+  c->kd_host_valid = false;  // rt_get_photons / rt_get_kdtree fetch the nodes on demand
+  c->kd_nodes7.clear();
+  kd_installed(c, n);
+  return RT_OK;
+}
+// host copy of the kd-ordered nodes for rt_get_photons / rt_get_kdtree
+static int ensure_kd_host(rt_ctx* c) {
+  if (c->kd_host_valid) return RT_OK;
+  const int64_t n = c->kd_n;
+  std::vector<float4> hp((size_t)std::max<int64_t>(n, 1)), hd((size_t)std::max<int64_t>(n, 1));
+  if (n > 0) {
+    CU(cudaMemcpyAsync(hp.data(), c->d_kd_pos.p, sizeof(float4) * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(hd.data(), c->d_kd_dir.p, sizeof(float4) * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+  }
+  c->kd_nodes7.resize(7 * (size_t)n);
+  for (int64_t i = 0; i < n; i++) {
+    float* a = &c->kd_nodes7[7 * (size_t)i];
+    a[0] = hp[i].x, a[1] = hp[i].y, a[2] = hp[i].z, a[3] = hd[i].x, a[4] = hd[i].y, a[5] = hd[i].z, a[6] = hp[i].w;
+  }
+  c->kd_host_valid = true;
+  return RT_OK;
+}
+
 // shared tail of rt_set_photons / rt_set_photons_device: c->kd_nodes7 holds the list in emission order
 static int install_photons(rt_ctx* c, int64_t n) {
   const double t_kd0 = now_ms();
-  build_kdtree(c->kd_nodes7, &c->kd_height);
+  if (c->params.flags & RT_FLAG_KNN_EXACT)  // the canonical tree (RT_KD_BUILD=host; the device builder makes the same one)
+    build_kdtree_canonical(c->kd_nodes7, &c->kd_height, nullptr);
+  else
+    build_kdtree(c->kd_nodes7, &c->kd_height);
   c->stats.kd_build_ms = now_ms() - t_kd0;
   if (c->kd_height > kKdStack) return fail(RT_ERR_INVALID, "kd-tree deeper than the device stack");
   DevBuf<float> d_p7;
@@ -1291,13 +1356,9 @@ static int install_photons(rt_ctx* c, int64_t n) {
   }
   CU(cudaStreamSynchronize(c->stream));
   d_p7.release();
-  c->scene.kd_pos = c->d_kd_pos.p;
-  c->scene.kd_dir = c->d_kd_dir.p;
-  c->scene.kd_count = (int)n;
-  c->stats.photons_stored = n;
-  c->photon_map_built = true;
-  c->photon_map_seed = c->params.seed;
-  c->photon_map_requested = c->params.num_photons;
+  c->kd_on_device = false;
+  c->kd_host_valid = true;
+  kd_installed(c, n);
   return RT_OK;
 }
 
@@ -1307,6 +1368,14 @@ int rt_set_photons(rt_ctx* c, const rt_photon* photons, int64_t n) {
   if (n < 0 || (n > 0 && !photons)) return fail(RT_ERR_INVALID, "bad photon list");
   if (n >= (1 << 28)) return fail(RT_ERR_INVALID, "too many photons");
   static_assert(sizeof(rt_photon) == 28, "rt_photon must match Particle (28 bytes)");
+  if (kd_build_on_device(c)) {
+    DevBuf<float> d_p7;
+    CU(d_p7.ensure(7 * (size_t)std::max<int64_t>(n, 1)));
+    if (n > 0) CU(cudaMemcpyAsync(d_p7.p, photons, sizeof(float) * 7 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    rc = install_photons_device_build(c, d_p7.p, n);
+    d_p7.release();
+    return rc;
+  }
   c->kd_nodes7.assign((const float*)photons, (const float*)photons + 7 * n);
   return install_photons(c, n);
 }
@@ -1316,6 +1385,7 @@ int rt_set_photons_device(rt_ctx* c, const float* photons7_device, int64_t n) {
   if (rc) return rc;
   if (n < 0 || (n > 0 && !photons7_device)) return fail(RT_ERR_INVALID, "bad photon list");
   if (n >= (1 << 28)) return fail(RT_ERR_INVALID, "too many photons");
+  if (kd_build_on_device(c)) return install_photons_device_build(c, photons7_device, n);  // nothing leaves the GPU
   // the kd-tree's shape is libstdc++'s nth_element: ONE device->host copy for the host build
   c->kd_nodes7.resize(7 * (size_t)n);
   if (n > 0) {
@@ -1381,6 +1451,9 @@ int rt_build_photon_map(rt_ctx* c) {
 
 int rt_get_photons(rt_ctx* c, rt_photon* out, int64_t capacity, int64_t* count) {
   if (!c || !count) return fail(RT_ERR_INVALID, "null argument");
+  int rc0 = bind(c);
+  if (rc0) return rc0;
+  if ((rc0 = ensure_kd_host(c))) return rc0;
   int64_t n = (int64_t)c->kd_nodes7.size() / 7;
   *count = n;
   if (out) {
@@ -1392,6 +1465,9 @@ int rt_get_photons(rt_ctx* c, rt_photon* out, int64_t capacity, int64_t* count) 
 
 int rt_get_kdtree(rt_ctx* c, rt_photon* nodes, int32_t* left, int32_t* right, int32_t* root, int64_t capacity) {
   if (!c || !root) return fail(RT_ERR_INVALID, "null argument");
+  int rc0 = bind(c);
+  if (rc0) return rc0;
+  if ((rc0 = ensure_kd_host(c))) return rc0;
   int64_t n = (int64_t)c->kd_nodes7.size() / 7;
   if (capacity < n) return fail(RT_ERR_INVALID, "capacity too small");
   if (nodes) std::memcpy(nodes, c->kd_nodes7.data(), sizeof(float) * 7 * (size_t)n);
@@ -1492,6 +1568,20 @@ int rt_build_bvh_host(const rt_scene* s, float pad_fraction, float* nodes16, int
   if (capacity_nodes < n) return fail(RT_ERR_INVALID, "capacity too small");
   std::memcpy(nodes16, bvh.nodes.data(), bvh.nodes.size() * sizeof(float));
   if (slot_triangle) std::memcpy(slot_triangle, bvh.slot_tri.data(), bvh.slot_tri.size() * sizeof(int32_t));
+  return RT_OK;
+}
+int rt_build_kdtree_host(float* photons7_inout, int64_t n, int32_t canonical, int32_t* orig_index, int32_t* height) {
+  if (n < 0 || (n > 0 && !photons7_inout) || n >= (1 << 28)) return fail(RT_ERR_INVALID, "bad photon list");
+  std::vector<float> v(photons7_inout, photons7_inout + 7 * n);
+  std::vector<int32_t> orig;
+  int h = 0;
+  if (canonical)
+    build_kdtree_canonical(v, &h, &orig);
+  else
+    build_kdtree(v, &h);
+  std::memcpy(photons7_inout, v.data(), sizeof(float) * 7 * (size_t)n);
+  if (orig_index && canonical) std::memcpy(orig_index, orig.data(), sizeof(int32_t) * (size_t)n);
+  if (height) *height = h;
   return RT_OK;
 }
 int rt_get_bvh_slots(rt_ctx* c, int32_t* slot_triangle, int64_t capacity) {

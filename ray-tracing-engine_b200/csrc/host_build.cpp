@@ -318,6 +318,48 @@ void build_top_level(int n_roots, const float* boxes6, const int32_t* refs, floa
   out.depth = B.max_depth.load() + 1;
 }
 
+namespace {
+struct KdItemIdx {
+  float v[7];
+  int32_t idx;
+};
+int make_tree_canonical(KdItemIdx* nodes, size_t begin, size_t end, size_t index, int fork_levels) {
+  if (end <= begin) return 0;
+  size_t n = begin + (end - begin) / 2;
+  std::nth_element(nodes + begin, nodes + n, nodes + end, [index](const KdItemIdx& a, const KdItemIdx& b) {
+    return a.v[index] < b.v[index] || (a.v[index] == b.v[index] && a.idx < b.idx);
+  });
+  index = (index + 1) % 3;
+  int hl = 0, hr = 0;
+  if (fork_levels > 0 && end - begin > 16384) {
+    std::thread t([&]() { hl = make_tree_canonical(nodes, begin, n, index, fork_levels - 1); });
+    hr = make_tree_canonical(nodes, n + 1, end, index, fork_levels - 1);
+    t.join();
+  } else {
+    hl = make_tree_canonical(nodes, begin, n, index, 0);
+    hr = make_tree_canonical(nodes, n + 1, end, index, 0);
+  }
+  return 1 + std::max(hl, hr);
+}
+}  // namespace
+
+void build_kdtree_canonical(std::vector<float>& photons7, int* height_out, std::vector<int32_t>* orig_out) {
+  const size_t n = photons7.size() / 7;
+  std::vector<KdItemIdx> items(n);
+  for (size_t i = 0; i < n; i++) {
+    std::memcpy(items[i].v, &photons7[7 * i], 28);
+    items[i].idx = (int32_t)i;
+  }
+  unsigned hw = std::thread::hardware_concurrency();
+  int h = make_tree_canonical(items.data(), 0, n, 0, hw >= 16 ? 4 : hw >= 8 ? 3 : hw >= 4 ? 2 : hw >= 2 ? 1 : 0);
+  if (orig_out) orig_out->resize(n);
+  for (size_t i = 0; i < n; i++) {
+    std::memcpy(&photons7[7 * i], items[i].v, 28);
+    if (orig_out) (*orig_out)[i] = items[i].idx;
+  }
+  if (height_out) *height_out = h;
+}
+
 void build_kdtree(std::vector<float>& photons7, int* height_out) {
   static_assert(sizeof(KdItem) == 28, "Particle is 28 bytes");
   size_t n = photons7.size() / 7;

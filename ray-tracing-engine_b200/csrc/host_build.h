@@ -55,6 +55,10 @@ void build_top_level(int n_roots, const float* boxes6, const int32_t* refs, floa
 // node at begin+(end-begin)/2 after std::nth_element on the cycling axis; the array ends in the
 // tree's in-order layout and the links are implied by the ranges.  photons: 7 floats each.
 void build_kdtree(std::vector<float>& photons7, int* height_out);
+// The canonical tree of the exact k-NN mode: the same procedure with the photons of a range ordered by
+// (coordinate, index in the emitted list) -- a total order, so the array is a function of the list alone and the device
+// builder (csrc/kd_build.cu) produces the identical one.  orig_out[i] = list index of the photon at array position i.
+void build_kdtree_canonical(std::vector<float>& photons7, int* height_out, std::vector<int32_t>* orig_out);
 // explicit links for inspection (rt_get_kdtree)
 void kdtree_links(int64_t n, std::vector<int32_t>& left, std::vector<int32_t>& right, int32_t* root);
 

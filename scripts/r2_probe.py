@@ -25,6 +25,28 @@ def frames(r, n=3):
     return best, per, float(s.astype(np.float64).sum()), int(c.sum())
 
 what = sys.argv[1:] or ["own", "batch", "cfg4"]
+if "kd" in what:  # kd-tree build: host nth_element (reference tree), host canonical, device canonical
+    st_scene = scene("stock")
+    for photons in (50000, 500000):
+        for label, flags, env in (("host reference tree", 0, None), ("host canonical", rt.RT_FLAG_KNN_EXACT, "host"),
+                                  ("device canonical", rt.RT_FLAG_KNN_EXACT, None)):
+            if env:
+                os.environ["RT_KD_BUILD"] = env
+            else:
+                os.environ.pop("RT_KD_BUILD", None)
+            r = rt.Renderer(st_scene, 1, 0, None, photons, 10, seed=1, flags=flags)
+            best = 1e9
+            for _ in range(4):
+                t0 = time.perf_counter()
+                r.build_photon_map()
+                wall = 1e3 * (time.perf_counter() - t0)
+                st = r.stats()
+                best = min(best, st["kd_build_ms"])
+            print(json.dumps(dict(probe="kd_build", photons=photons, stored=st["photons_stored"], builder=label,
+                                  kd_build_ms=round(best, 3), build_photon_map_wall_ms=round(wall, 2),
+                                  emit_ms=round(st["photon_ms"], 3))), flush=True)
+            r.close()
+    os.environ.pop("RT_KD_BUILD", None)
 ex = scene("example")
 if "own" in what:
     for v in ("0", "1"):

@@ -306,3 +306,42 @@ def test_kernel_class_times_cover_the_device_time(rt):
     assert 0.8 * st["device_ms"] <= total <= 1.02 * st["device_ms"], (total, st["device_ms"])
     assert st["kernel_count"]["trace_nearest"] == 3 and st["kernel_count"]["trace_any"] == 3
     assert st["kernel_count"]["sort"] == 6 and sum(st["kernel_count"].values()) == st["kernel_launches"]
+
+
+# ------------------------------------------------------------------ device kd-tree build
+def test_device_kdtree_build_equals_the_canonical_host_build(rt, gold, monkeypatch):
+    """RT_FLAG_KNN_EXACT: the kd-tree is built on the device (csrc/kd_build.cu: three sorted orders, median split of
+    every range of a level at once).  Its node array must be bit-identical to the canonical host builder's
+    (rt_build_kdtree_host, photons ordered by (coordinate, list index)) -- on the golden list, on a list with many
+    exactly equal coordinates, and on the 357 k photons of BASELINE configs[3] -- and the exact k nearest photons are
+    the same through either tree."""
+    scene = rt.Scene.load(scene_path("stock"))
+    g = gold("photons.npz")
+    ties = g["list"].copy()
+    ties[200:900, 1] = ties[200, 1]
+    ties[50:60] = ties[50]  # identical photons
+    big = rt.Renderer(scene, 1, 0, None, 500000, 50, seed=SEED).emit_photons()[0]
+    q = g["queries"][:1000]
+    for plist in (g["list"], ties, g["list"][:1], g["list"][:2], big):
+        want, orig, h = rt.build_kdtree_host(plist, canonical=True)
+        monkeypatch.delenv("RT_KD_BUILD", raising=False)
+        r = rt.Renderer(scene, 1, 0, None, 3000, min(10, len(plist)), seed=SEED, flags=rt.RT_FLAG_KNN_EXACT)
+        r.set_photons(plist)
+        nodes, left, right, root = r.kdtree()
+        assert beq(nodes, want), f"{(nodes != want).any(axis=1).sum()} of {len(want)} nodes differ"
+        assert root == len(plist) // 2
+        monkeypatch.setenv("RT_KD_BUILD", "host")
+        rh = rt.Renderer(scene, 1, 0, None, 3000, min(10, len(plist)), seed=SEED, flags=rt.RT_FLAG_KNN_EXACT)
+        rh.set_photons(plist)
+        assert beq(rh.kdtree()[0], want)
+        k = min(10, len(plist))
+        assert (r.knearest(q, k) == rh.knearest(q, k)).all()
+        r.close(); rh.close()
+    monkeypatch.delenv("RT_KD_BUILD", raising=False)
+    # the whole exact-mode pipeline stays on the device: emission -> compaction -> kd build -> gather
+    a = rt.Renderer(scene, 1, 0, None, 50000, 10, seed=SEED, width=96, height=64, flags=rt.RT_FLAG_KNN_EXACT)
+    monkeypatch.setenv("RT_KD_BUILD", "host")
+    b = rt.Renderer(scene, 1, 0, None, 50000, 10, seed=SEED, width=96, height=64, flags=rt.RT_FLAG_KNN_EXACT)
+    (sa, ca), (sb, cb) = a.render_accumulate(), b.render_accumulate()
+    assert beq(sa, sb) and (ca == cb).all()
+    assert a.stats()["kd_build_ms"] > 0 and a.stats()["photons_stored"] == b.stats()["photons_stored"]

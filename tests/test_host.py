@@ -342,3 +342,26 @@ def test_input_list_and_binary_off_cache(tmp_path):
     assert beq(third.pos, plain.pos) and (third.tri == plain.tri).all()
     with pytest.raises(RuntimeError):
         rt.Scene.build(64, 64, MESHES, "/nonexistent/x.off", 0, cache)
+
+
+def test_host_kdtree_builders(gold):
+    """rt_build_kdtree_host: (1) the default builder reproduces the reference's own tree (kdtree::make_tree with
+    libstdc++'s nth_element) on the golden photon list; (2) the canonical builder of the exact k-NN mode is a valid
+    median-split kd-tree, orders equal coordinates by list index, and does not depend on the input order of ties."""
+    g = gold("photons.npz")
+    nodes, _, h = rt.build_kdtree_host(g["list"])
+    assert beq(nodes, g["nodes"]) and h == int(np.floor(np.log2(len(nodes)))) + 1
+    lst = g["list"].copy()
+    lst[100:400, 0] = lst[100, 0]  # many equal x coordinates
+    can, orig, h2 = rt.build_kdtree_host(lst, canonical=True)
+    assert h2 == h and sorted(orig.tolist()) == list(range(len(lst))) and beq(can, lst[orig])
+
+    def check(b, e, axis):
+        if e <= b:
+            return
+        n = b + (e - b) // 2
+        key = lambda i: (can[i, axis], orig[i])
+        assert all(key(i) < key(n) for i in range(b, n)) and all(key(n) < key(i) for i in range(n + 1, e))
+        check(b, n, (axis + 1) % 3)
+        check(n + 1, e, (axis + 1) % 3)
+    check(0, len(can), 0)
