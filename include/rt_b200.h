@@ -122,13 +122,14 @@ enum {
   RT_KERNEL_RAYGEN = 0,        /* k_raygen                                                      */
   RT_KERNEL_TRACE_NEAREST = 1, /* k_trace_sp8u3<nearest>                                        */
   RT_KERNEL_SORT = 2,          /* k_sort_count / k_sort_scan / k_sort_scatter                   */
-  RT_KERNEL_SHADE = 3,         /* k_shade (direct lighting, or the k-nearest-photon gather)     */
+  RT_KERNEL_SHADE = 3,         /* k_shade (direct lighting / photon shading)                    */
   RT_KERNEL_TRACE_ANY = 4,     /* k_trace_sp8u3<any-hit> over the shadow rays                   */
   RT_KERNEL_COMBINE = 5,       /* k_combine                                                     */
   RT_KERNEL_RESOLVE = 6,       /* k_resolve                                                     */
   RT_KERNEL_EMIT = 7,          /* k_emit (photon emission)                                      */
   RT_KERNEL_OTHER = 8,         /* scatter / composite                                           */
-  RT_NUM_KERNEL_CLASSES = 9
+  RT_KERNEL_GATHER = 9,        /* k_knn_gather (persistent k-nearest-photon gather)             */
+  RT_NUM_KERNEL_CLASSES = 10
 };
 
 typedef struct rt_stats {

@@ -20,7 +20,7 @@ RT_FLAG_BRUTE_FORCE = 1
 RT_FLAG_KNN_EXACT = 2
 RT_MAX_K = 4096
 RT_MAX_LIGHTS = 4096
-KERNEL_CLASSES = ("raygen", "trace_nearest", "sort", "shade", "trace_any", "combine", "resolve", "emit", "other")
+KERNEL_CLASSES = ("raygen", "trace_nearest", "sort", "shade", "trace_any", "combine", "resolve", "emit", "other", "gather")
 
 
 class RtError(RuntimeError):

@@ -105,6 +105,7 @@ struct rt_ctx {
   DevBuf<DLight> d_lights_ext;             // lights beyond the kMaxLights kept in kernel-parameter space
   DevBuf<unsigned long long> d_knn_scratch;  // k-NN candidates of every resident thread when k > kKnnSharedMaxK
   int knn_scratch_threads = 0;
+  int knn_gather = 1;  // RT_KNN_GATHER=0: the photon queries run inside k_shade instead of the persistent gather kernel
   int own_tri = 0;  // RT_OWN_TRI=1: k_shade pre-tests a shadow ray against the triangle it starts on (measured: no gain)
   DevBuf<unsigned char> d_occ;
   DevBuf<int> d_hit_path;
@@ -325,6 +326,9 @@ void fill_args(rt_ctx* c, RenderArgs& a, const int* pix_map, int npix, bool use_
   a.own_tri = c->own_tri;
   a.hit_p = c->d_hit_p.p;
   a.sh_d = c->d_sh_d.p;
+  // the persistent gather handles the two reference-exact flavours; its result array reuses the (unused in photon
+  // mode) shadow-ray direction buffer: one float4 per ray slot
+  a.knn_out = (use_photons && c->knn_gather && a.knn_exact <= 0) ? c->d_sh_d.p : nullptr;
   a.knn_scratch = c->d_knn_scratch.p;
   a.knn_scratch_stride = c->knn_scratch_threads;
   a.contrib = c->d_contrib.p;
@@ -402,6 +406,7 @@ int run_batch(rt_ctx* c, RenderArgs& a, int s0, int nsamp) {
     SPAN(kKTraceNearest, 1, launch_trace_nearest(a, seg, grid, c->stream));
     if ((seg > 0 || a.photon) && a.perm)  // spatial order: shadow-ray coherence / k-NN traversal coherence
       SPAN(kKSort, 3, launch_sort_hits(a, seg, c->stream));
+    if (a.photon && a.knn_out) SPAN(kKGather, 1, launch_knn_gather(a, seg, c->stream));
     SPAN(kKShade, 1, launch_shade(a, seg, std::max(grid_shade, 1), c->stream));
     if (!a.photon && a.nl > 0) SPAN(kKTraceAny, 1, launch_trace_any(a, seg, grid, c->stream));
     SPAN(kKCombine, 1, launch_combine(a, seg, std::max(grid_shade, 1), c->stream));
@@ -481,8 +486,10 @@ int prepare_photons(rt_ctx* c) {
 // wavefront buffers (and the k-NN scratch) for `paths` path slots, with the batch-size fallback of the auto mode
 int prepare_batch_buffers(rt_ctx* c, bool use_photons) {
   if (!use_photons || c->params.k <= kKnnSharedMaxK) return RT_OK;
-  const int ctas = c->num_sms * shade_photon_ctas_per_sm(c->params.mode == 1 ? 1 : 0, c->params.k, c->kd_height + 1);
-  return ensure_knn_scratch(c, c->params.k, ctas * kBlock);
+  const int flavour = knn_flavour(c->params);
+  int per_sm = shade_photon_ctas_per_sm(c->params.mode == 1 ? 1 : 0, c->params.k, c->kd_height + 1);
+  if (flavour <= 0) per_sm = std::max(per_sm, knn_gather_ctas_per_sm(c->params.k, c->kd_height + 1, flavour < 0 ? 1 : 0));
+  return ensure_knn_scratch(c, c->params.k, c->num_sms * per_sm * kBlock);
 }
 
 // the whole render: batches of samples -> ordered accumulation -> scatter into full-frame buffers
@@ -784,6 +791,7 @@ int rt_create(const rt_scene* s, const rt_params* p, int device, rt_ctx** out) {
   }
   if (const char* e = getenv("RT_SORT_HITS")) c->sort_hits = atoi(e);
   if (const char* e = getenv("RT_OWN_TRI")) c->own_tri = atoi(e) != 0;
+  if (const char* e = getenv("RT_KNN_GATHER")) c->knn_gather = atoi(e) != 0;
   if (!(extent < 1e8f)) {  // keeps lo * safe_inv(d) finite in the slab test (rt_device.cuh)
     rt_destroy(c);
     return fail(RT_ERR_INVALID, "scene coordinates must be finite and smaller than 1e8");

@@ -690,25 +690,145 @@ RT_DI void knn_query(const DScene& S, float3 P, int k, int exact, unsigned long 
     knn_exact_redo(S, P, k, sc, ks);
 }
 
+// Renderer.cpp:88-103 from the gathered photons: r = distance of the k-th, avg = sum of the k incomeDirections in
+// ascending distance; radiance = k (the sum of k ones, exact in binary32) / (pi r^2) / numPhotons * 100
+RT_DI float4 gather_result(const DScene& S, int k, const unsigned long long* sc, int ks) {
+  const float r = kd_dist_of(sc[(unsigned)(k - 1) * (unsigned)ks]);  // farthest of the k (ascending distance)
+  float3 avg = f3(0.f, 0.f, 0.f);
+  for (int j = 0; j < k; j++) avg = v_add(avg, f3(__ldg(S.kd_dir + kd_index_of(sc[(unsigned)j * (unsigned)ks]))));
+  return make_float4(avg.x, avg.y, avg.z, r);
+}
+RT_DI float3 shade_photon_from(float4 g, float3 dir, float3 n, const DMaterial& m, int k, int num_photons) {
+  const float r = g.w;
+  float area = (float)__dmul_rn(__dmul_rn(3.141592653589793, (double)r), (double)r);
+  float rad = __fmul_rn(__fdiv_rn(__fdiv_rn((float)k, area), (float)num_photons), 100.f);
+  float3 bsdf = evaluate_color_response(m, n, v_norm(f3(g)), v_neg(dir));
+  return v_scl(bsdf, rad);
+}
 RT_DI float3 shade_photon(const DScene& S, float3 dir, float3 n, float3 P, const DMaterial& m, int k, int num_photons,
                           int exact, unsigned long long* sc, int ks, int* kst, unsigned long long& visits) {
   knn_query(S, P, k, exact, sc, ks, kst, visits);
-  float r = kd_dist_of(sc[(unsigned)(k - 1) * (unsigned)ks]);  // farthest of the k (candidates are in ascending distance)
-  float area = (float)__dmul_rn(__dmul_rn(3.141592653589793, (double)r), (double)r);
-  float3 avg = f3(0.f, 0.f, 0.f);
-  float cnt = 0.f;
-  for (int j = 0; j < k; j++) {
-    avg = v_add(avg, f3(__ldg(S.kd_dir + kd_index_of(sc[(unsigned)j * (unsigned)ks]))));
-    cnt = __fadd_rn(cnt, 1.f);
-  }
-  float rad = __fmul_rn(__fdiv_rn(__fdiv_rn(cnt, area), (float)num_photons), 100.f);
-  float3 bsdf = evaluate_color_response(m, n, v_norm(avg), v_neg(dir));
-  return v_scl(bsdf, rad);
+  return shade_photon_from(gather_result(S, k, sc, ks), dir, n, m, k, num_photons);
 }
 // dynamic shared memory of the kernels that run the k-NN: `frames` stack frames of 3 ints per thread, and -- up to
 // k = kKnnSharedMaxK -- the k candidate (distance, index) pairs; beyond that the candidates live in global memory
 size_t knn_smem_bytes(int k, int frames) {
   return (size_t)((k <= kKnnSharedMaxK ? 2 * k : 0) + 3 * frames) * kBlock * sizeof(int);
+}
+
+// ----------------------------------------------------------------------------------------------
+// k_knn_gather: the k-nearest-photon queries of a segment's hit points as their own persistent kernel.
+// ncu on the query inside k_shade (profiles/r2_knn_sass.txt): the traversal loop ran with 24 of 32 lanes (a warp's 32
+// queries take 60-140 node visits each and the warp waits for the longest), the candidate insertion with 13 and the
+// stack unwind with 7.  Here a query is a resumable state machine (KdQuery): every lane advances its own query by
+// one node per round, a lane whose query is complete writes its result -- the sum of the k incomeDirections in
+// ascending distance and the distance of the k-th, all the shading needs (Renderer.cpp:88-97) -- and the warp
+// refills its idle lanes from the queue when fewer than kGatherRefillBelow are live, like k_trace does with rays.
+// The queue is the sorted payload of the segment (hit points binned by Morton cell: neighbouring lanes walk the same
+// part of the tree); slots whose ray missed are skipped.
+// ----------------------------------------------------------------------------------------------
+constexpr int kGatherRefillBelow = 24;
+template <int POLICY, bool GSC>
+__global__ void __launch_bounds__(kBlock, 6) k_knn_gather(const RenderArgs A, const int seg) {
+  extern __shared__ unsigned long long s_knn[];
+  const DScene& S = A.scene;
+  const unsigned n = seg == 0 ? (unsigned)A.npix * (unsigned)A.nsamp : A.q_count[kQHits0 + seg - 1];
+  unsigned* fetch = A.q_count + kQFetchAny0 + seg;  // photon mode casts no shadow rays: the any-hit cursor is free
+  const unsigned lane = threadIdx.x & 31u, lt_mask = (1u << lane) - 1u;
+  const int k = A.k;
+  unsigned long long* sc;
+  int cs;
+  int* kst;
+  if (GSC) {
+    sc = A.knn_scratch + (size_t)blockIdx.x * kBlock + threadIdx.x;
+    cs = A.knn_scratch_stride;
+    kst = (int*)s_knn + threadIdx.x;
+  } else {
+    sc = s_knn + threadIdx.x;
+    cs = kBlock;
+    kst = (int*)(s_knn + k * kBlock) + threadIdx.x;
+  }
+  KdQuery<POLICY> Q;
+  Q.nv = 0;
+  unsigned slot = 0, n_knn = 0;
+  unsigned long long n_visits = 0;
+  bool live = false, exhausted = false;
+  for (;;) {
+    const unsigned need_mask = __ballot_sync(kFull, !live);
+    if (!exhausted && need_mask) {
+      const unsigned cnt = __popc(need_mask);
+      unsigned base = 0;
+      if (lane == 0) base = atomicAdd(fetch, cnt);
+      base = __shfl_sync(kFull, base, 0);
+      if (base + cnt >= n) exhausted = true;
+      if (!live) {
+        const unsigned my = base + __popc(need_mask & lt_mask);
+        if (my < n) {
+          const float4 hr = A.perm != nullptr ? A.sorted[2 * (size_t)my] : A.hit[my];
+          HitRec h;
+          h.t = hr.x, h.u = hr.y, h.v = hr.z, h.gid = __float_as_int(hr.w);
+          if (h.gid >= 0) {
+            slot = my;
+            Q.init(S, hit_point(S, h), k, sc, cs);
+            live = true;
+            n_knn++;
+          }
+        }
+      }
+    }
+    if (__ballot_sync(kFull, live) == 0) {
+      if (exhausted) break;
+      continue;
+    }
+    for (;;) {
+      if (live && !Q.step(S, k, sc, cs, kst, kBlock)) {  // this lane's query is complete
+        if (POLICY == 0 && Q.tie) knn_exact_redo(S, Q.q, k, sc, cs);
+        Q.finish(k, sc, cs);
+        A.knn_out[slot] = gather_result(S, k, sc, cs);
+        n_visits += Q.nv;
+        live = false;
+      }
+      const unsigned live_mask = __ballot_sync(kFull, live);
+      if (live_mask == 0) break;
+      if (!exhausted && __popc(live_mask) < kGatherRefillBelow) break;
+    }
+  }
+  for (int off = 16; off > 0; off >>= 1) {
+    n_knn += __shfl_xor_sync(kFull, n_knn, off);
+    n_visits += __shfl_xor_sync(kFull, n_visits, off);
+  }
+  if (lane == 0) {
+    if (n_knn) atomicAdd(A.counters + kCntKnn, (unsigned long long)n_knn);
+    if (n_visits) atomicAdd(A.counters + kCntKdVisits, n_visits);
+  }
+}
+template <int POLICY, bool GSC>
+static int knn_gather_occupancy(size_t sm) {
+  int occ = 0;
+  cudaFuncSetAttribute(k_knn_gather<POLICY, GSC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_knn_gather<POLICY, GSC>, kBlock, sm);
+  return occ < 1 ? 1 : occ;
+}
+int knn_gather_ctas_per_sm(int k, int kd_frames, int flavour) {
+  const size_t sm = knn_smem_bytes(k, kd_frames);
+  const bool g = k > kKnnSharedMaxK;
+  if (flavour == 0) return g ? knn_gather_occupancy<0, true>(sm) : knn_gather_occupancy<0, false>(sm);
+  return g ? knn_gather_occupancy<1, true>(sm) : knn_gather_occupancy<1, false>(sm);
+}
+void launch_knn_gather(const RenderArgs& a, int seg, cudaStream_t st) {
+  const size_t sm = knn_smem_bytes(a.k, a.kd_frames);
+  const int flavour = a.knn_exact < 0 ? 1 : 0;
+  const bool g = a.k > kKnnSharedMaxK;
+  int grid = (a.num_sms > 0 ? a.num_sms : 148) * knn_gather_ctas_per_sm(a.k, a.kd_frames, flavour);
+  if (g && (size_t)grid * kBlock > (size_t)a.knn_scratch_stride) grid = a.knn_scratch_stride / kBlock;
+  if (grid < 1) grid = 1;
+  if (flavour == 0) {
+    if (g) k_knn_gather<0, true><<<grid, kBlock, sm, st>>>(a, seg);
+    else k_knn_gather<0, false><<<grid, kBlock, sm, st>>>(a, seg);
+  } else {
+    if (g) k_knn_gather<1, true><<<grid, kBlock, sm, st>>>(a, seg);
+    else k_knn_gather<1, false><<<grid, kBlock, sm, st>>>(a, seg);
+  }
 }
 
 // NLT: 3 = the stock three-light loop unrolled (Main.cpp:101-124), 0 = any light count (Renderer.cpp:49).
@@ -786,7 +906,10 @@ __global__ void __launch_bounds__(kBlock, PHOTON ? 6 : RT_SHADE_MINB) k_shade(co
       hit_geometry(S, h, nrm, P, mesh, tp0, te1, te2);
       const DMaterial m = S.mats[mesh];
       A.hit_path[j] = (int)p;
-      if (PHOTON) {
+      if (PHOTON && A.knn_out != nullptr) {  // gathered by k_knn_gather, per ray slot of the segment
+        float3 c = shade_photon_from(A.knn_out[slot], d, nrm, m, A.k, A.num_photons);
+        A.contrib[j] = make_float4(c.x, c.y, c.z, 0.f);
+      } else if (PHOTON) {
         n_knn++;
         unsigned long long* sc;
         int ks;
@@ -861,10 +984,10 @@ int shade_photon_ctas_per_sm(int mode, int k, int kd_frames) {
 
 void launch_shade(const RenderArgs& a, int seg, int grid, cudaStream_t st) {
   if (a.photon) {
-    const size_t sm = knn_smem_bytes(a.k, a.kd_frames);
+    const size_t sm = a.knn_out ? 0 : knn_smem_bytes(a.k, a.kd_frames);
     // grid-stride kernel: launch exactly what is resident (the k-NN shared memory allows 6 CTAs/SM at k = 10, 2 at
     // k = 50; 8 per SM left a third of the CTAs for a second, mostly empty wave -- 26 % warps active in ncu)
-    const int occ = shade_photon_ctas_per_sm(a.mode, a.k, a.kd_frames);
+    const int occ = a.knn_out ? 8 : shade_photon_ctas_per_sm(a.mode, a.k, a.kd_frames);
     if (a.num_sms > 0) grid = grid < a.num_sms * occ ? grid : a.num_sms * occ;
     const bool g = a.k > kKnnSharedMaxK;
     if (g && (size_t)grid * kBlock > (size_t)a.knn_scratch_stride) grid = a.knn_scratch_stride / kBlock;

@@ -33,7 +33,7 @@ __host__ __device__ __forceinline__ unsigned shadow_slot_hit(unsigned s, unsigne
 // picks the dominant one by its measured share of the step.
 enum KernelClass {
   kKRaygen = 0, kKTraceNearest = 1, kKSort = 2, kKShade = 3, kKTraceAny = 4, kKCombine = 5, kKResolve = 6,
-  kKEmit = 7, kKOther = 8, kKNumClasses = 9
+  kKEmit = 7, kKOther = 8, kKGather = 9, kKNumClasses = 10
 };
 
 // One wavefront batch = `nsamp` consecutive samples of `npix` pixels; path p = s_local*npix + pixel_local.
@@ -79,6 +79,9 @@ struct RenderArgs {
   float3 sort_inv_cell;      // kSortGrid / extent per axis
   unsigned int* q_count;
   unsigned long long* counters;
+  // photon gather by the persistent k_knn_gather (reference-exact flavours): per ray slot of the segment
+  // (sum of the k incomeDirections in ascending distance, distance of the k-th); null: k_shade runs the query itself
+  float4* knn_out;
   // k > kKnnSharedMaxK: the k-NN candidates of every resident thread live in global memory, [slot][thread]
   unsigned long long* knn_scratch;
   int knn_scratch_stride;  // threads the scratch was sized for (grid of the k-NN kernel * kBlock)
@@ -116,6 +119,9 @@ void launch_trace_rays(const DScene& s, const float4* ro, const float4* rd, unsi
                        unsigned char* occluded, int any, int brute, int stack_depth, unsigned* fetch_counter,
                        int grid_ctas, cudaStream_t st);
 int shade_photon_ctas_per_sm(int mode, int k, int kd_frames);  // resident CTAs of the k-NN shade kernel
+// persistent k-nearest-photon gather of a segment's hit points (fills a.knn_out); grid = SMs x knn_gather_ctas_per_sm
+void launch_knn_gather(const RenderArgs& a, int seg, cudaStream_t st);
+int knn_gather_ctas_per_sm(int k, int kd_frames, int flavour);
 void launch_bsdf(DMaterial m, const float* n_wi_wo, long long n, float* rgb, cudaStream_t st);
 void launch_hsphere(uint64_t seed_mixed, uint64_t domain, uint64_t index0, const float* normals, long long n, float* out,
                     cudaStream_t st);

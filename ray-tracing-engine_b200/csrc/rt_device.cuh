@@ -531,6 +531,13 @@ RT_DI void hit_geometry(const DScene& S, const HitRec& h, float3& n, float3& P, 
   float3 p0, e1, e2;
   hit_geometry(S, h, n, P, mesh, p0, e1, e2);
 }
+// the hit point alone (same arithmetic): what the photon gather queries
+RT_DI float3 hit_point(const DScene& S, const HitRec& h) {
+  const int4 vi = __ldg(S.tri_vidx + h.gid);
+  const float w = __fsub_rn(__fsub_rn(1.f, h.u), h.v);
+  const float3 p0 = f3(__ldg(S.pos + vi.x)), p1 = f3(__ldg(S.pos + vi.y)), p2 = f3(__ldg(S.pos + vi.z));
+  return v_add(v_add(v_scl(p0, w), v_scl(p1, h.u)), v_scl(p2, h.v));
+}
 
 // ------------------------------------------------------------------------------------------------
 // kdtree::knearest (kdtree.h:87-107,180-195), quirks included.  The max-heap reproduces libstdc++'s
@@ -714,95 +721,6 @@ RT_DI unsigned long long kd_pack(float d, int idx) {  // distances are >= 0: the
 RT_DI float kd_dist_of(unsigned long long c) { return __uint_as_float((unsigned)(c >> 32)); }
 RT_DI int kd_index_of(unsigned long long c) { return (int)(unsigned)c; }
 
-// sc: k candidate slots (distance bits << 32 | node index, one 64-bit access per move), stride cs between a thread's
-// slots; kst: 3 ints per frame (far begin, far end | next axis << 28, threshold bits), stride ks.
-RT_DI bool kd_knearest_sorted(const DScene& S, float3 q, int k, unsigned long long* sc, int cs, int* kst, int ks,
-                              unsigned long long& visits) {
-  bool tie = false;
-  for (int j = 0; j < k; j++) {  // kdtree.h:186: the first k nodes of the array seed the candidates
-    const unsigned dj = __float_as_uint(v_dist(f3(__ldg(S.kd_pos + j)), q));
-    int m = j - 1;
-    unsigned long long w = 0;
-    while (m >= 0 && (unsigned)((w = sc[(unsigned)(m) * (unsigned)cs]) >> 32) > dj) {
-      sc[(unsigned)(m + 1) * (unsigned)cs] = w;
-      m--;
-    }
-    if (m >= 0 && (unsigned)(w >> 32) == dj) tie = true;
-    sc[(unsigned)(m + 1) * (unsigned)cs] = ((unsigned long long)dj << 32) | (unsigned)j;
-  }
-  float best = kd_dist_of(sc[(unsigned)(k - 1) * (unsigned)cs]);  // m_bestdist (a distance, not squared)
-  float reject2 = kd_reject_from(best);
-  int sp = 0, b = 0, e = S.kd_count, axis = 0;
-  unsigned nv = 0;
-  while (e > b) {
-    const int n = b + (e - b) / 2;
-    nv++;
-    const float4 p = __ldg(S.kd_pos + n);
-    const float d2 = kd_dist2(f3(p), q);
-    float dnode;
-    if (d2 < reject2 && (dnode = __fsqrt_rn(d2)) < best) {
-      // evict the largest; m_bestdist = the largest of the rest BEFORE the insertion (k == 1: libstdc++'s
-      // front() after pop_heap is the evicted candidate itself), kdtree.h:93-96
-      best = kd_dist_of(sc[(unsigned)(k > 1 ? k - 2 : 0) * (unsigned)cs]);
-      reject2 = kd_reject_from(best);
-      const unsigned dn = __float_as_uint(dnode);
-      int m = k - 2;
-      unsigned long long w = 0;
-      while (m >= 0 && (unsigned)((w = sc[(unsigned)(m) * (unsigned)cs]) >> 32) > dn) {
-        sc[(unsigned)(m + 1) * (unsigned)cs] = w;
-        m--;
-      }
-      // a tie with the evicted largest (old slot k-1) cannot matter: dnode < best <= it
-      if (m >= 0 && (unsigned)(w >> 32) == dn) tie = true;
-      sc[(unsigned)(m + 1) * (unsigned)cs] = ((unsigned long long)dn << 32) | (unsigned)n;
-    }
-    int nb = b, ne = b;  // empty
-    if (best != 0.f) {   // kdtree.h:101: best == 0 returns without visiting the children
-      float pa = p.x, qa = q.x;
-      if (axis == 1) pa = p.y, qa = q.y;
-      if (axis == 2) pa = p.z, qa = q.z;
-      const float dx = __fsub_rn(pa, qa);
-      const bool left_near = dx > 0.f;
-      nb = left_near ? b : n + 1;
-      ne = left_near ? n : e;
-      const int fb = left_near ? n + 1 : b, fe = left_near ? e : n;
-      axis = axis == 2 ? 0 : axis + 1;
-      if (fe > fb) {  // an empty far side has nothing to visit
-        // The far side is skipped when `dx*dx >= m_bestdist` (kdtree.h:105: a square against a distance, in
-        // binary64, where the square of a binary32 is exact) or when |dx| >= m_bestdist (every photon behind the
-        // plane is at least |dx| away, none can pass `d < m_bestdist`, so the visit would change nothing; the
-        // factor keeps a 2-ulp margin for sqrt(fl(a*a)) < |a|).  Both are "m_bestdist <= a number known now":
-        // the largest binary32 <= dx*dx, and fl(|dx| * 0.9999995) -- so one threshold is stored and the pop
-        // costs one comparison.
-        // For k >= 2 m_bestdist never grows (it is the second largest candidate and candidates only get
-        // closer), so a far side that is already skippable now is not pushed at all.  (k == 1: m_bestdist is
-        // the distance of the candidate evicted LAST, which can go up again.)
-        const float t_sq = __fmul_rd(dx, dx);  // the largest binary32 <= dx*dx (the binary64 square is exact)
-        const float t_pl = __fmul_rn(fabsf(dx), 0.9999995f);
-        const float thr = fmaxf(t_sq, t_pl);
-        if (best > thr || k == 1) {
-          kst[(3 * sp) * ks] = fb;
-          kst[(3 * sp + 1) * ks] = fe | (axis << 28);
-          kst[(3 * sp + 2) * ks] = __float_as_int(thr);
-          sp++;
-        }
-      }
-    }
-    b = nb;
-    e = ne;
-    while (e <= b && sp > 0) {  // near side empty: resume at the newest frame whose far side survives
-      sp--;
-      if (best <= __int_as_float(kst[(3 * sp + 2) * ks])) continue;
-      const int fe = kst[(3 * sp + 1) * ks];
-      b = kst[(3 * sp) * ks];
-      axis = (fe >> 28) & 3;
-      e = fe & 0x0fffffff;
-    }
-  }
-  visits += nv;
-  return tie;
-}
-
 // ------------------------------------------------------------------------------------------------
 // kd_knearest_heap: the same single-loop traversal with the candidates kept as libstdc++'s own max-heap (the element
 // moves of make_heap / pop_heap / push_heap / sort_heap restated literally, std::__adjust_heap and std::__push_heap)
@@ -869,29 +787,90 @@ struct KdHeapP {
     }
   }
 };
-RT_DI void kd_knearest_heap(const DScene& S, float3 q, int k, unsigned long long* sc, int cs, int* kst, int ks,
-                            unsigned long long& visits) {
-  KdHeapP H{sc, cs};
-  for (int j = 0; j < k; j++) H.set(j, kd_pack(v_dist(f3(__ldg(S.kd_pos + j)), q), j));  // kdtree.h:186
-  H.make(k);
-  float best = kd_dist_of(H.get(0));  // m_bestdist
-  float reject2 = kd_reject_from(best);
-  int sp = 0, b = 0, e = S.kd_count, axis = 0;
-  unsigned nv = 0;
-  while (e > b) {
+// ------------------------------------------------------------------------------------------------
+// KdQuery: ONE kdtree::knearest query as a resumable state machine -- init() seeds the candidates, every step()
+// visits exactly one node and unwinds the stack to the next one, finish() leaves the k candidates in ascending
+// distance.  The persistent gather kernel (k_knn_gather) interleaves the steps of 32 queries per warp and refills a
+// lane as soon as its query completes; kd_knearest_sorted / kd_knearest_heap below run one query to completion.
+//   POLICY 0: ascending candidate array (small k).  A new candidate is usually among the smallest (it lands ~2 slots
+//             from the front at k = 10), so the insertion point is found from the front and the tail is moved with
+//             a plain copy loop; ties are reported (see above) and the query is repeated with the literal heap.
+//   POLICY 1: libstdc++'s own max-heap moves restated (KdHeapP): log2(k) moves per eviction, ties for free.
+// sc: k candidate slots (distance bits << 32 | node index, one 64-bit access per move), stride cs between a thread's
+// slots; kst: 3 ints per frame (far begin, far end | next axis << 28, threshold bits), stride ks.
+// ------------------------------------------------------------------------------------------------
+template <int POLICY>
+struct KdQuery {
+  float3 q;
+  float best;     // m_bestdist (a distance, not squared)
+  float reject2;  // d2 >= reject2  =>  sqrt_rn(d2) >= best
+  int sp, b, e, axis;
+  unsigned nv;
+  bool tie;
+
+  RT_DI void init(const DScene& S, float3 query, int k, unsigned long long* sc, int cs) {
+    q = query;
+    tie = false;
+    if (POLICY == 0) {
+      for (int j = 0; j < k; j++) {  // kdtree.h:186: the first k nodes of the array seed the candidates
+        const unsigned dj = __float_as_uint(v_dist(f3(__ldg(S.kd_pos + j)), q));
+        int m = j - 1;
+        unsigned long long w = 0;
+        while (m >= 0 && (unsigned)((w = sc[(unsigned)(m) * (unsigned)cs]) >> 32) > dj) {
+          sc[(unsigned)(m + 1) * (unsigned)cs] = w;
+          m--;
+        }
+        if (m >= 0 && (unsigned)(w >> 32) == dj) tie = true;
+        sc[(unsigned)(m + 1) * (unsigned)cs] = ((unsigned long long)dj << 32) | (unsigned)j;
+      }
+      best = kd_dist_of(sc[(unsigned)(k - 1) * (unsigned)cs]);
+    } else {
+      KdHeapP H{sc, cs};
+      for (int j = 0; j < k; j++) H.set(j, kd_pack(v_dist(f3(__ldg(S.kd_pos + j)), q), j));
+      H.make(k);
+      best = kd_dist_of(H.get(0));
+    }
+    reject2 = kd_reject_from(best);
+    sp = 0;
+    b = 0;
+    e = S.kd_count;
+    axis = 0;
+    nv = 0;
+  }
+
+  // one node visit (precondition: e > b); returns false when the traversal is complete
+  RT_DI bool step(const DScene& S, int k, unsigned long long* sc, int cs, int* kst, int ks) {
     const int n = b + (e - b) / 2;
     nv++;
     const float4 p = __ldg(S.kd_pos + n);
     const float d2 = kd_dist2(f3(p), q);
     float dnode;
     if (d2 < reject2 && (dnode = __fsqrt_rn(d2)) < best) {  // kdtree.h:92-99
-      H.pop(k);
-      best = kd_dist_of(H.get(0));  // the new top BEFORE the insertion (for k == 1: the evicted candidate itself)
+      if (POLICY == 0) {
+        // evict the largest; m_bestdist = the largest of the rest BEFORE the insertion (k == 1: libstdc++'s
+        // front() after pop_heap is the evicted candidate itself), kdtree.h:93-96
+        best = kd_dist_of(sc[(unsigned)(k > 1 ? k - 2 : 0) * (unsigned)cs]);
+        const unsigned dn = __float_as_uint(dnode);
+        int pos = 0;  // first slot of [0, k-1) whose distance is above dn: the new candidate goes there
+        while (pos < k - 1) {
+          const unsigned dw = (unsigned)(sc[(unsigned)pos * (unsigned)cs] >> 32);
+          if (dw > dn) break;
+          // a tie with the evicted largest (old slot k-1) cannot matter: dnode < best <= it
+          if (dw == dn) tie = true;
+          pos++;
+        }
+        for (int j = k - 2; j >= pos; j--) sc[(unsigned)(j + 1) * (unsigned)cs] = sc[(unsigned)j * (unsigned)cs];
+        sc[(unsigned)pos * (unsigned)cs] = ((unsigned long long)dn << 32) | (unsigned)n;
+      } else {
+        KdHeapP H{sc, cs};
+        H.pop(k);
+        best = kd_dist_of(H.get(0));  // the new top BEFORE the insertion (for k == 1: the evicted candidate itself)
+        H.push_up(k - 1, 0, kd_pack(dnode, n));
+      }
       reject2 = kd_reject_from(best);
-      H.push_up(k - 1, 0, kd_pack(dnode, n));
     }
-    int nb = b, ne = b;
-    if (best != 0.f) {
+    int nb = b, ne = b;  // empty
+    if (best != 0.f) {   // kdtree.h:101: best == 0 returns without visiting the children
       float pa = p.x, qa = q.x;
       if (axis == 1) pa = p.y, qa = q.y;
       if (axis == 2) pa = p.z, qa = q.z;
@@ -901,7 +880,16 @@ RT_DI void kd_knearest_heap(const DScene& S, float3 q, int k, unsigned long long
       ne = left_near ? n : e;
       const int fb = left_near ? n + 1 : b, fe = left_near ? e : n;
       axis = axis == 2 ? 0 : axis + 1;
-      if (fe > fb) {
+      if (fe > fb) {  // an empty far side has nothing to visit
+        // The far side is skipped when `dx*dx >= m_bestdist` (kdtree.h:105: a square against a distance, in
+        // binary64, where the square of a binary32 is exact) or when |dx| >= m_bestdist (every photon behind the
+        // plane is at least |dx| away, none can pass `d < m_bestdist`, so the visit would change nothing; the
+        // factor keeps a 2-ulp margin for sqrt(fl(a*a)) < |a|).  Both are "m_bestdist <= a number known now":
+        // the largest binary32 <= dx*dx, and fl(|dx| * 0.9999995) -- so one threshold is stored and the pop
+        // costs one comparison.
+        // For k >= 2 m_bestdist never grows (it is the second largest candidate and candidates only get
+        // closer), so a far side that is already skippable now is not pushed at all.  (k == 1: m_bestdist is
+        // the distance of the candidate evicted LAST, which can go up again.)
         const float t_sq = __fmul_rd(dx, dx);  // the largest binary32 <= dx*dx (the binary64 square is exact)
         const float t_pl = __fmul_rn(fabsf(dx), 0.9999995f);
         const float thr = fmaxf(t_sq, t_pl);
@@ -915,7 +903,7 @@ RT_DI void kd_knearest_heap(const DScene& S, float3 q, int k, unsigned long long
     }
     b = nb;
     e = ne;
-    while (e <= b && sp > 0) {
+    while (e <= b && sp > 0) {  // near side empty: resume at the newest frame whose far side survives
       sp--;
       if (best <= __int_as_float(kst[(3 * sp + 2) * ks])) continue;
       const int fe = kst[(3 * sp + 1) * ks];
@@ -923,9 +911,36 @@ RT_DI void kd_knearest_heap(const DScene& S, float3 q, int k, unsigned long long
       axis = (fe >> 28) & 3;
       e = fe & 0x0fffffff;
     }
+    return e > b;
   }
-  H.sort(k);
-  visits += nv;
+
+  RT_DI void finish(int k, unsigned long long* sc, int cs) {
+    if (POLICY == 1) {
+      KdHeapP H{sc, cs};
+      H.sort(k);
+    }
+  }
+};
+
+// one query run to completion; the sorted flavour returns true when it saw a tie (the caller repeats the query with
+// kd_knearest, the literal heap restatement)
+RT_DI bool kd_knearest_sorted(const DScene& S, float3 q, int k, unsigned long long* sc, int cs, int* kst, int ks,
+                              unsigned long long& visits) {
+  KdQuery<0> Q;
+  Q.init(S, q, k, sc, cs);
+  while (Q.step(S, k, sc, cs, kst, ks)) {
+  }
+  visits += Q.nv;
+  return Q.tie;
+}
+RT_DI void kd_knearest_heap(const DScene& S, float3 q, int k, unsigned long long* sc, int cs, int* kst, int ks,
+                            unsigned long long& visits) {
+  KdQuery<1> Q;
+  Q.init(S, q, k, sc, cs);
+  while (Q.step(S, k, sc, cs, kst, ks)) {
+  }
+  Q.finish(k, sc, cs);
+  visits += Q.nv;
 }
 
 // ------------------------------------------------------------------------------------------------

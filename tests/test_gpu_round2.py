@@ -296,6 +296,26 @@ def test_own_triangle_pretest_does_not_change_the_frame(rt, monkeypatch):
     assert beq(a[0], b[0]) and (a[1] == b[1]).all()
 
 
+def test_persistent_gather_equals_the_inline_queries(rt, gold, monkeypatch):
+    """The photon gather as its own persistent kernel (k_knn_gather, default) and the queries run inside k_shade
+    (RT_KNN_GATHER=0) are the same arithmetic: bit-identical frames for both candidate structures (k = 10: ascending
+    array; k = 50: libstdc++'s heap restated) and for k beyond the shared-memory limit."""
+    scene = rt.Scene.load(scene_path("stock"))
+    ph = gold("photons.npz")["list"]
+    for k, mode in ((10, 1), (50, 0), (1, 0), (80, 0)):
+        frames = []
+        for gather in ("1", "0"):
+            monkeypatch.setenv("RT_KNN_GATHER", gather)
+            r = rt.Renderer(scene, 2, mode, None, 3000, k, seed=4, width=120, height=90)
+            r.set_photons(ph)
+            frames.append(r.render_accumulate() + (r.stats(),))
+            r.close()
+        (sa, ca, sta), (sb, cb, stb) = frames
+        assert beq(sa, sb) and (ca == cb).all(), k
+        assert sta["knn_queries"] == stb["knn_queries"] > 0 and sta["kd_visits"] == stb["kd_visits"]
+        assert sta["kernel_count"]["gather"] > 0 and stb["kernel_count"]["gather"] == 0
+
+
 def test_kernel_class_times_cover_the_device_time(rt):
     scene = rt.Scene.load(scene_path("example"))
     r = rt.Renderer(scene, 8, 1, seed=1, width=420, height=420)
