@@ -12,7 +12,8 @@ import os
 import numpy as np
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG_DIR, "lib", "librt_b200.so")
+# RT_B200_LIB selects another build of the same library (A/B runs of compile-time variants); default: the product build
+LIB_PATH = os.environ.get("RT_B200_LIB") or os.path.join(PKG_DIR, "lib", "librt_b200.so")
 
 RT_OK = 0
 RT_ERR_INVALID, RT_ERR_NO_DEVICE, RT_ERR_CUDA, RT_ERR_EMPTY_TREE, RT_ERR_K_TOO_LARGE, RT_ERR_OOM = -1, -2, -3, -4, -5, -6

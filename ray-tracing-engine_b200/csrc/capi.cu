@@ -105,7 +105,8 @@ struct rt_ctx {
   DevBuf<DLight> d_lights_ext;             // lights beyond the kMaxLights kept in kernel-parameter space
   DevBuf<unsigned long long> d_knn_scratch;  // k-NN candidates of every resident thread when k > kKnnSharedMaxK
   int knn_scratch_threads = 0;
-  int knn_gather = 1;  // RT_KNN_GATHER=0: the photon queries run inside k_shade instead of the persistent gather kernel
+  int knn_gather = 0;  // RT_KNN_GATHER=1: the photon queries run in the persistent gather kernel instead of inside k_shade
+  int sort_seg0 = 1;   // RT_SORT_SEG0=0: the photon gather of segment 0 keeps the pixel-tile order of the primary hits
   int own_tri = 0;  // RT_OWN_TRI=1: k_shade pre-tests a shadow ray against the triangle it starts on (measured: no gain)
   DevBuf<unsigned char> d_occ;
   DevBuf<int> d_hit_path;
@@ -324,6 +325,7 @@ void fill_args(rt_ctx* c, RenderArgs& a, const int* pix_map, int npix, bool use_
   a.hit = c->d_hit.p;
   a.nl = shadow_lights(c, use_photons);
   a.own_tri = c->own_tri;
+  a.sort_seg0 = c->sort_seg0;
   a.hit_p = c->d_hit_p.p;
   a.sh_d = c->d_sh_d.p;
   // the persistent gather handles the two reference-exact flavours; its result array reuses the (unused in photon
@@ -404,7 +406,7 @@ int run_batch(rt_ctx* c, RenderArgs& a, int s0, int nsamp) {
   const int nseg = a.mode == 1 ? 3 : 1;
   for (int seg = 0; seg < nseg; seg++) {
     SPAN(kKTraceNearest, 1, launch_trace_nearest(a, seg, grid, c->stream));
-    if ((seg > 0 || a.photon) && a.perm)  // spatial order: shadow-ray coherence / k-NN traversal coherence
+    if ((seg > 0 || (a.photon && a.sort_seg0)) && a.perm)  // spatial order: shadow-ray / k-NN traversal coherence
       SPAN(kKSort, 3, launch_sort_hits(a, seg, c->stream));
     if (a.photon && a.knn_out) SPAN(kKGather, 1, launch_knn_gather(a, seg, c->stream));
     SPAN(kKShade, 1, launch_shade(a, seg, std::max(grid_shade, 1), c->stream));
@@ -792,6 +794,7 @@ int rt_create(const rt_scene* s, const rt_params* p, int device, rt_ctx** out) {
   if (const char* e = getenv("RT_SORT_HITS")) c->sort_hits = atoi(e);
   if (const char* e = getenv("RT_OWN_TRI")) c->own_tri = atoi(e) != 0;
   if (const char* e = getenv("RT_KNN_GATHER")) c->knn_gather = atoi(e) != 0;
+  if (const char* e = getenv("RT_SORT_SEG0")) c->sort_seg0 = atoi(e) != 0;
   if (!(extent < 1e8f)) {  // keeps lo * safe_inv(d) finite in the slab test (rt_device.cuh)
     rt_destroy(c);
     return fail(RT_ERR_INVALID, "scene coordinates must be finite and smaller than 1e8");

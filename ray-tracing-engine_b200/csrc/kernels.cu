@@ -764,7 +764,7 @@ __global__ void __launch_bounds__(kBlock, 6) k_knn_gather(const RenderArgs A, co
       if (!live) {
         const unsigned my = base + __popc(need_mask & lt_mask);
         if (my < n) {
-          const float4 hr = A.perm != nullptr ? A.sorted[2 * (size_t)my] : A.hit[my];
+          const float4 hr = ((seg > 0 || A.sort_seg0) && A.perm != nullptr) ? A.sorted[2 * (size_t)my] : A.hit[my];
           HitRec h;
           h.t = hr.x, h.u = hr.y, h.v = hr.z, h.gid = __float_as_int(hr.w);
           if (h.gid >= 0) {
@@ -847,7 +847,7 @@ __global__ void __launch_bounds__(kBlock, PHOTON ? 6 : RT_SHADE_MINB) k_shade(co
   unsigned n_hit = 0, n_knn = 0;
   unsigned long long n_visits = 0;
 
-  const bool permuted = (seg > 0 || PHOTON) && A.perm != nullptr;
+  const bool permuted = (seg > 0 || (PHOTON && A.sort_seg0)) && A.perm != nullptr;
   for (unsigned base = blockIdx.x * kBlock; base < n; base += gridDim.x * kBlock) {
     const unsigned slot = base + threadIdx.x;
     bool found = false;

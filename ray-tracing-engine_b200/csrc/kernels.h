@@ -63,6 +63,8 @@ struct RenderArgs {
   float4* hit;       // per ray slot of the current segment: (t, u, v, triangle id | -1)
   int nl;            // shadow slots per hit (see shadow_slot): number of lights, or 1 for the photon gather
   int own_tri;       // 1: k_shade tests a shadow ray against the triangle it starts on before queueing it
+  int sort_seg0;     // photon gather: 1 = segment 0's hit points are binned by Morton cell too, 0 = they keep the
+                     // pixel-tile order of the primary rays (a warp = an 8x4 pixel tile of one sample)
   float4* hit_p;     // per compacted hit j: the hit point = origin of its nl shadow rays
   float4* sh_d;      // shadow ray directions, blocked layout (see shadow_slot); w != 0: already known occluded
   float4* contrib;   // radiance * bsdf of light l for hit j, same layout

@@ -792,13 +792,15 @@ struct KdHeapP {
 // visits exactly one node and unwinds the stack to the next one, finish() leaves the k candidates in ascending
 // distance.  The persistent gather kernel (k_knn_gather) interleaves the steps of 32 queries per warp and refills a
 // lane as soon as its query completes; kd_knearest_sorted / kd_knearest_heap below run one query to completion.
-//   POLICY 0: ascending candidate array (small k).  A new candidate is usually among the smallest (it lands ~2 slots
-//             from the front at k = 10), so the insertion point is found from the front and the tail is moved with
-//             a plain copy loop; ties are reported (see above) and the query is repeated with the literal heap.
+//   POLICY 0: ascending candidate array (small k): an insertion is one backward shift loop; ties are reported (see
+//             above) and the query is repeated with the literal heap.
 //   POLICY 1: libstdc++'s own max-heap moves restated (KdHeapP): log2(k) moves per eviction, ties for free.
 // sc: k candidate slots (distance bits << 32 | node index, one 64-bit access per move), stride cs between a thread's
 // slots; kst: 3 ints per frame (far begin, far end | next axis << 28, threshold bits), stride ks.
 // ------------------------------------------------------------------------------------------------
+#ifndef RT_KNN_FRONT_SCAN
+#define RT_KNN_FRONT_SCAN 0
+#endif
 template <int POLICY>
 struct KdQuery {
   float3 q;
@@ -851,16 +853,29 @@ struct KdQuery {
         // front() after pop_heap is the evicted candidate itself), kdtree.h:93-96
         best = kd_dist_of(sc[(unsigned)(k > 1 ? k - 2 : 0) * (unsigned)cs]);
         const unsigned dn = __float_as_uint(dnode);
+#if RT_KNN_FRONT_SCAN
+        // (measured on B200, cfg3 frame: 63.8 ms against 57.9 for the single backward loop below: the new candidate
+        // does land ~2 slots from the front, but two loops diverge twice)
         int pos = 0;  // first slot of [0, k-1) whose distance is above dn: the new candidate goes there
         while (pos < k - 1) {
           const unsigned dw = (unsigned)(sc[(unsigned)pos * (unsigned)cs] >> 32);
           if (dw > dn) break;
-          // a tie with the evicted largest (old slot k-1) cannot matter: dnode < best <= it
           if (dw == dn) tie = true;
           pos++;
         }
         for (int j = k - 2; j >= pos; j--) sc[(unsigned)(j + 1) * (unsigned)cs] = sc[(unsigned)j * (unsigned)cs];
         sc[(unsigned)pos * (unsigned)cs] = ((unsigned long long)dn << 32) | (unsigned)n;
+#else
+        int m = k - 2;
+        unsigned long long w = 0;
+        while (m >= 0 && (unsigned)((w = sc[(unsigned)(m) * (unsigned)cs]) >> 32) > dn) {
+          sc[(unsigned)(m + 1) * (unsigned)cs] = w;
+          m--;
+        }
+        // a tie with the evicted largest (old slot k-1) cannot matter: dnode < best <= it
+        if (m >= 0 && (unsigned)(w >> 32) == dn) tie = true;
+        sc[(unsigned)(m + 1) * (unsigned)cs] = ((unsigned long long)dn << 32) | (unsigned)n;
+#endif
       } else {
         KdHeapP H{sc, cs};
         H.pop(k);

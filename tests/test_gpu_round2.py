@@ -297,8 +297,8 @@ def test_own_triangle_pretest_does_not_change_the_frame(rt, monkeypatch):
 
 
 def test_persistent_gather_equals_the_inline_queries(rt, gold, monkeypatch):
-    """The photon gather as its own persistent kernel (k_knn_gather, default) and the queries run inside k_shade
-    (RT_KNN_GATHER=0) are the same arithmetic: bit-identical frames for both candidate structures (k = 10: ascending
+    """The photon gather as its own persistent kernel (k_knn_gather, RT_KNN_GATHER=1) and the queries run inside k_shade
+    (default) are the same arithmetic: bit-identical frames for both candidate structures (k = 10: ascending
     array; k = 50: libstdc++'s heap restated) and for k beyond the shared-memory limit."""
     scene = rt.Scene.load(scene_path("stock"))
     ph = gold("photons.npz")["list"]
@@ -306,6 +306,7 @@ def test_persistent_gather_equals_the_inline_queries(rt, gold, monkeypatch):
         frames = []
         for gather in ("1", "0"):
             monkeypatch.setenv("RT_KNN_GATHER", gather)
+            monkeypatch.setenv("RT_SORT_SEG0", gather)  # ... and the order segment 0's queries are processed in
             r = rt.Renderer(scene, 2, mode, None, 3000, k, seed=4, width=120, height=90)
             r.set_photons(ph)
             frames.append(r.render_accumulate() + (r.stats(),))
