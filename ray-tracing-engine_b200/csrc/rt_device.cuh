@@ -255,7 +255,14 @@ RT_DI bool box_hit(float3 lo, float3 hi, float3 o, float3 inv, float best_t, flo
 // rounding.  inv MUST come from safe_inv(): with inv = +-inf the form lo*inf - o*inf gives inf - inf = NaN
 // on ONE plane of a slab the origin is inside of, and fmin/fmax then resolve it as a miss (found by the
 // N=128 parity test: 3 of 22.6 M primary rays have an exactly-zero direction component).
-RT_DI float safe_inv(float d) { return fminf(fmaxf(1.0f / d, -1e30f), 1e30f); }
+// The reciprocal itself only steers the (conservative) slab test, so the 1-ulp hardware approximation is enough: it
+// adds 2^-23 relative to a t whose error budget is pad / |t d| ~ 2^-14 (host_build.h), and saves the ~10-instruction
+// IEEE division sequence three times per ray refill.  d = +-0 or denormal gives +-inf, clamped like before.
+RT_DI float safe_inv(float d) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d));
+  return fminf(fmaxf(r, -1e30f), 1e30f);
+}
 RT_DI bool box_hit_fma(float3 lo, float3 hi, float3 inv, float3 oinv, float best_t, float& tnear) {
   float t0x = __fmaf_rn(lo.x, inv.x, -oinv.x), t1x = __fmaf_rn(hi.x, inv.x, -oinv.x);
   float t0y = __fmaf_rn(lo.y, inv.y, -oinv.y), t1y = __fmaf_rn(hi.y, inv.y, -oinv.y);
@@ -373,17 +380,18 @@ RT_DI void camera_ray(const DCamera& c, int x, int y, float sx, float sy, int w,
 // restatement in C) and on the device by the hsphere golden (tests/test_gpu_round2.py).
 // Arguments here are in [0, 2 pi (1 + 3e-8)] or NaN (asin of a uniform that may exceed 1 by 3e-8, RayTracer.h:96).
 // ------------------------------------------------------------------------------------------------
-RT_DI float libm_sincosf_poly(double x, double x2, bool second_table, int n) {
+// the two polynomials of sinf_poly (s_sincosf.h): the sine one on (x, x^2), the cosine one on x^2 with the table's sign
+RT_DI float libm_sin_poly(double x, double x2) {
+  const double s1c = -0x1.555545995a603p-3, s2c = 0x1.1107605230bc4p-7, s3c = -0x1.994eb3774cf24p-13;
+  const double x3 = __dmul_rn(x, x2);
+  const double s1 = __fma_rn(x2, s3c, s2c);
+  const double x7 = __dmul_rn(x3, x2);
+  const double s = __fma_rn(x3, s1c, x);
+  return (float)__fma_rn(x7, s1, s);
+}
+RT_DI float libm_cos_poly(double x2, bool second_table) {
   // __sincosf_table[0] and [1]: the cosine coefficients change sign in the second table, the sine ones do not
   const double sg = second_table ? -1.0 : 1.0;
-  if ((n & 1) == 0) {
-    const double s1c = -0x1.555545995a603p-3, s2c = 0x1.1107605230bc4p-7, s3c = -0x1.994eb3774cf24p-13;
-    const double x3 = __dmul_rn(x, x2);
-    const double s1 = __fma_rn(x2, s3c, s2c);
-    const double x7 = __dmul_rn(x3, x2);
-    const double s = __fma_rn(x3, s1c, x);
-    return (float)__fma_rn(x7, s1, s);
-  }
   const double c0 = sg * 0x1p0, c1 = sg * -0x1.ffffffd0c621cp-2, c2 = sg * 0x1.55553e1068f19p-5,
                c3 = sg * -0x1.6c087e89a359dp-10, c4 = sg * 0x1.99343027bf8c3p-16;
   const double x4 = __dmul_rn(x2, x2);
@@ -393,8 +401,10 @@ RT_DI float libm_sincosf_poly(double x, double x2, bool second_table, int n) {
   const double c = __fma_rn(x4, c2, q1);
   return (float)__fma_rn(x6, q2, c);
 }
-// sinf(y) and cosf(y) of ONE argument: both calls reduce y the same way (same n, same remainder), so the reduction is
-// shared and only the two polynomials differ -- bit for bit what two separate libm calls return.
+// sinf(y) and cosf(y) of ONE argument: both calls reduce y the same way (same n, same remainder) and then evaluate
+// one the sine polynomial and the other the cosine polynomial -- which one depends on the quadrant's parity.  Both
+// polynomials are evaluated once, unconditionally (no divergence between lanes in different quadrants), and
+// assigned by parity: bit for bit what two separate libm calls return.
 RT_DI void libm_sincosf(float y, float& sin_y, float& cos_y) {
   const unsigned top = (__float_as_uint(y) >> 20) & 0x7ffu;  // abstop12
   const double x = (double)y;
@@ -405,8 +415,8 @@ RT_DI void libm_sincosf(float y, float& sin_y, float& cos_y) {
       return;
     }
     const double x2 = __dmul_rn(x, x);
-    sin_y = libm_sincosf_poly(x, x2, false, 0);
-    cos_y = libm_sincosf_poly(x, x2, false, 1);
+    sin_y = libm_sin_poly(x, x2);
+    cos_y = libm_cos_poly(x2, false);
     return;
   }
   if (top >= 0x42fu) {  // |y| >= 120, inf, NaN: never a finite argument on this path
@@ -420,8 +430,9 @@ RT_DI void libm_sincosf(float y, float& sin_y, float& cos_y) {
   const double xr = __fma_rn(-(double)n, 0x1.921FB54442D18p0, x);
   const double sign = ((n & 3) == 1 || (n & 3) == 2) ? -1.0 : 1.0;  // sign[] = {1, -1, -1, 1}
   const double xs = __dmul_rn(xr, sign), x2 = __dmul_rn(xr, xr);
-  sin_y = libm_sincosf_poly(xs, x2, (n & 2) != 0, n);
-  cos_y = libm_sincosf_poly(xs, x2, (n & 2) != 0, n ^ 1);
+  const float s = libm_sin_poly(xs, x2), c = libm_cos_poly(x2, (n & 2) != 0);
+  sin_y = (n & 1) ? c : s;  // sinf: sinf_poly(x*s, x*x, p, n);  cosf: sinf_poly(x*s, x*x, p, n ^ 1)
+  cos_y = (n & 1) ? s : c;
 }
 
 // RayTracer.h:95-107 with maxRayAngle = float(pi/2).  asin in binary64 like the reference (the result is rounded to
