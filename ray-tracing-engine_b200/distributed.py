@@ -13,6 +13,12 @@ The reference is a single process; the render path shards 
               composites over the background on its GPU (Renderer.cpp:262-265) and writes the PPM.
 
 Nothing here computes on the CPU: the functions move torch tensors and call the C ABI.
+
+Stream discipline: the library runs on its own CUDA stream and every entry point returns only when its work is
+complete, so data it produced is safe to hand to NCCL.  The other direction needs care: a torch tensor that a pending
+collective still reads must not be freed (and recycled by torch's allocator for a buffer this library then writes
+through a raw pointer) before the collective has finished -- the functions below synchronise the device on every rank
+before such a tensor goes out of scope.
 """
 from __future__ import annotations
 
@@ -156,9 +162,14 @@ def render_distributed(scene, num_rays, mode, num_photons=0, k=5, *, background,
         torch.cuda.synchronize(device)
         r.render_accumulate_packed_device(packed.data_ptr())
         reduce_packed(packed, 0, group)
+        # EVERY rank waits for the collective here.  Rank 0 because the reduce runs on NCCL's stream and the composite
+        # on the context's own.  The others because `packed` is freed when this function returns: torch's allocator may
+        # hand the block to the next tensor at once (it only orders reuse against torch's streams), and this library
+        # writes through raw pointers on its own stream -- a rank that raced ahead would overwrite its contribution
+        # while its NCCL kernel is still waiting for the slower ranks (seen on 8 GPUs: one 64 KiB chunk of the frame
+        # wrong in 2 of 6 runs of scripts/dist_check.py).
+        torch.cuda.synchronize(device)
         if rank == 0:
-            # the reduce runs on NCCL's stream and the composite on the context's own: wait for the collective first
-            torch.cuda.synchronize(device)
             out = r.composite_packed_device(num_rays, packed.data_ptr(), background)
     else:       # host tensors (gloo): separate sums and counters
         sum_np, cnt_np = r.render_accumulate()

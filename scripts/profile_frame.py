@@ -1,6 +1,6 @@
 """One frame of a bench workload bracketed by cudaProfilerStart/Stop, for ncu --profile-from-start off.
 
-usage: profile_frame.py cfg2|cfg3|cfg4|cfg5|stock [out.json]
+usage: profile_frame.py cfg2|cfg3|cfg4|cfg5|stock [out.json]      (RT_PROFILE_EMIT=1: the photon emission is captured too)
 Prints (and writes to out.json) the frame's logical work: rays by kind, queries, launches by kernel class, and the
 CUDA-event time of every class measured on an untouched warm-up frame before the capture.  scripts/ncu_roofline.py
 joins this with the ncu CSV into profiles/ncu_<workload>.json."""

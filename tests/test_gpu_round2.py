@@ -366,3 +366,38 @@ def test_device_kdtree_build_equals_the_canonical_host_build(rt, gold, monkeypat
     (sa, ca), (sb, cb) = a.render_accumulate(), b.render_accumulate()
     assert beq(sa, sb) and (ca == cb).all()
     assert a.stats()["kd_build_ms"] > 0 and a.stats()["photons_stored"] == b.stats()["photons_stored"]
+
+
+def test_device_photon_shards_splice_to_the_single_process_list(rt):
+    """The multi-GPU photon path on ONE GPU: `world` shards are emitted and compacted on the device one after the other
+    (rt_emit_photons_device), laid out like the NCCL all-gather lays them out (rank r's padded shard at r * stride),
+    spliced on the device (rt_splice_photons_device) and installed (rt_set_photons_device).  The result must be the
+    list -- and the kd-tree -- the single-process run builds, for shard counts that divide the paths and ones that do
+    not; repeated, to catch ordering hazards."""
+    import torch
+    from ray_tracing_engine_b200 import distributed as D
+    scene = rt.Scene.load(scene_path("stock"))
+    for photons, world in ((30000, 8), (3000, 3), (50000, 5), (10, 4)):
+        single = rt.Renderer(scene, 1, 0, None, photons, 5, seed=5)
+        want, want_counts, _ = single.emit_photons()
+        single.set_photons(want)
+        want_nodes = single.kdtree()[0]
+        for repeat in range(3):
+            r = rt.Renderer(scene, 1, 0, None, photons, 5, seed=5)
+            per, L = r.photons_per_light(), scene.L
+            cap = max(1, max(D.path_range(per, q, world)[1] for q in range(world)) * L)
+            gathered = torch.full((world * cap, 7), float("nan"), dtype=torch.float32, device="cuda")
+            counts = np.zeros((world, L), np.int64)
+            torch.cuda.synchronize()
+            for q in range(world):
+                first, count = D.path_range(per, q, world)
+                counts[q], _ = r.emit_photons_device(first, count, gathered[q * cap:].data_ptr(), cap)
+            assert (counts.sum(0) == want_counts).all()
+            total = int(counts.sum())
+            out = torch.full((max(total, 1), 7), float("nan"), dtype=torch.float32, device="cuda")
+            torch.cuda.synchronize()
+            assert r.splice_photons_device(gathered.data_ptr(), world, cap, counts, out.data_ptr(), max(total, 1)) == total
+            assert beq(out[:total].cpu().numpy(), want), (photons, world, repeat)
+            r.set_photons_device(out.data_ptr(), total)
+            assert beq(r.kdtree()[0], want_nodes)
+            r.close()
