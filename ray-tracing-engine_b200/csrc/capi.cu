@@ -1216,6 +1216,7 @@ static int emit_to_device(rt_ctx* c, int32_t first_path, int32_t num_paths, floa
   if (stored) *stored = 0;
   if (npaths == 0 || c->L == 0) return RT_OK;
   const size_t total = (size_t)c->L * npaths;
+  if (total >= ((size_t)1 << 32)) return fail(RT_ERR_INVALID, "too many photon paths in one emission");
   const int nb = photon_compact_blocks((long long)total);
   DevBuf<float4> d_a, d_b;
   DevBuf<unsigned> d_blk, d_hist;
@@ -1226,14 +1227,15 @@ static int emit_to_device(rt_ctx* c, int32_t first_path, int32_t num_paths, floa
   cudaError_t e = d_a.ensure(total);
   if (e == cudaSuccess) e = d_b.ensure(total);
   if (e == cudaSuccess) e = d_blk.ensure((size_t)nb + 1);
-  if (e == cudaSuccess) e = d_hist.ensure(20);
+  if (e == cudaSuccess) e = d_hist.ensure(21);  // 20 histogram bins + the emission kernel's work cursor
   if (e == cudaSuccess) e = d_lc.ensure((size_t)c->L);
   if (e == cudaSuccess) e = cudaMemsetAsync(d_hist.p, 0, 20 * sizeof(unsigned), c->stream);
   if (e == cudaSuccess) e = cudaMemsetAsync(d_lc.p, 0, (size_t)c->L * sizeof(unsigned long long), c->stream);
   if (e == cudaSuccess) {
     cudaEventRecord(c->ev0, c->stream);
     launch_emit(c->scene, mix64(c->params.seed + kGolden), per_light, light_pdf, first_path, npaths,
-                (c->params.flags & RT_FLAG_BRUTE_FORCE) ? 1 : 0, d_a.p, d_b.p, c->d_counters.p, c->stream);
+                (c->params.flags & RT_FLAG_BRUTE_FORCE) ? 1 : 0, d_a.p, d_b.p, c->d_counters.p, d_hist.p + 20, c->num_sms,
+                c->stream);
     cudaEventRecord(c->ev1, c->stream);
     launch_photon_compact(d_a.p, d_b.p, (long long)total, npaths, d_blk.p, d_lc.p, d_hist.p, out7_dev, capacity,
                           c->stream);

@@ -1239,79 +1239,117 @@ void launch_knn(const DScene& s, const float* q3, long long n, int k, int kd_fra
 }
 
 // ----------------------------------------------------------------------------------------------
-// k_emit: one thread per photon path (PhotonMap.h:19-44 emission, :92-155 random walk).
+// k_emit: photon paths (PhotonMap.h:19-44 emission, :92-155 random walk).
 // out_a = (position, weight), out_b = (incomeDirection, status bits): bit0 stored,
 // bits 8.. = 1 + depth of the Russian-roulette kill (0: not counted in the histogram).
+//
+// A path is 1-20 bounces and most end after one or two (PhotonMap.h:144-150: Russian roulette), so "one thread walks
+// one path" left 3.8 of 32 lanes busy (profiles/r2_cfg4_emit_full.csv, first capture): a warp ran as long as its
+// longest path.  Here the unit of a loop iteration is ONE BOUNCE: every lane advances its own path by one segment
+// (trace + shade + roulette), and a lane whose path has ended takes the next path from a global cursor (warp-
+// aggregated), so the warp stays full until the cursor runs out.  Results do not depend on which lane walks which
+// path: every path owns its random stream and its output slot q.
 // ----------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kBlock) k_emit(const DScene S, uint64_t seed_mixed, int per_light, float light_pdf,
                                                  int first_path, int npaths, int brute, float4* out_a, float4* out_b,
-                                                 unsigned long long* counters) {
+                                                 unsigned long long* counters, unsigned* cursor) {
   __shared__ int s_stack[kStackDepth * kBlock];
   int* stack = s_stack + threadIdx.x;
-  const long long total = (long long)S.num_lights * npaths;
+  const unsigned total = (unsigned)S.num_lights * (unsigned)npaths;
+  const unsigned lane = threadIdx.x & 31u, lt_mask = (1u << lane) - 1u;
   unsigned n_rays = 0;
-  for (long long q = (long long)blockIdx.x * kBlock + threadIdx.x; q < total; q += (long long)gridDim.x * kBlock) {
-    const int li = (int)(q / npaths);
-    const int path = first_path + (int)(q - (long long)li * npaths);
-    const DLight& L = light_at(S, li);
-    Rng g;
-    g.init(stream_key(seed_mixed, kDomainPhoton, (uint64_t)li * (uint64_t)per_light + (uint64_t)path), 0);
-    float3 o = light_rand_area_position(L, g);
-    float3 d = hsphere_uniform_sample(g, L.normal);
-    float pdf0 = v_dot(v_norm(d), v_norm(L.normal));
-    float weight = __fdiv_rn(light_radiance(L, o), __fmul_rn(pdf0, light_pdf));
-    float3 ppos = f3(0.f, 0.f, 0.f), pdir = f3(0.f, 0.f, 0.f);
-    bool exit = false, stored = false;
-    int hist = 0;
-    for (int depth = 0;; depth++) {
-      if (exit) {  // PhotonMap.h:94-97
-        stored = true;
-        hist = depth;  // 1 + (depth-1)
-        break;
+  // the path this lane is walking
+  bool alive = false, exhausted = false;
+  unsigned q = 0;
+  Rng g;
+  float3 o = f3(0, 0, 0), d = f3(0, 0, 0), ppos = f3(0, 0, 0), pdir = f3(0, 0, 0);
+  float weight = 0.f;
+  int depth = 0;
+  for (;;) {
+    const unsigned need = __ballot_sync(kFull, !alive);
+    if (!exhausted && need) {
+      unsigned base = 0;
+      if (lane == 0) base = atomicAdd(cursor, (unsigned)__popc(need));
+      base = __shfl_sync(kFull, base, 0);
+      if (base + __popc(need) >= total) exhausted = true;
+      if (!alive) {
+        q = base + __popc(need & lt_mask);
+        if (q < total) {  // PhotonMap.h:24-37: a new path leaves light li
+          const int li = (int)(q / (unsigned)npaths);
+          const int path = first_path + (int)(q - (unsigned)li * (unsigned)npaths);
+          const DLight& L = light_at(S, li);
+          g.init(stream_key(seed_mixed, kDomainPhoton, (uint64_t)li * (uint64_t)per_light + (uint64_t)path), 0);
+          o = light_rand_area_position(L, g);
+          d = hsphere_uniform_sample(g, L.normal);
+          const float pdf0 = v_dot(v_norm(d), v_norm(L.normal));
+          weight = __fdiv_rn(light_radiance(L, o), __fmul_rn(pdf0, light_pdf));
+          ppos = pdir = f3(0.f, 0.f, 0.f);
+          depth = 0;
+          alive = true;
+        }
       }
-      if (depth >= 20) break;  // PhotonMap.h:98: dropped
+    }
+    if (__ballot_sync(kFull, alive) == 0) {
+      if (exhausted) break;
+      continue;
+    }
+    if (alive) {  // one segment of calculatePhotonPath at `depth` (< 20)
       HitRec h;
       n_rays++;
       const bool f = brute ? brute_trace<false>(S, o, d, h) : bvh_traverse<false>(S, o, d, stack, kBlock, h);
-      if (!f) {  // PhotonMap.h:109-112
+      bool stored = false, done = false;
+      int hist = 0;
+      if (!f) {  // PhotonMap.h:109-112: the photon left the scene; it is stored where it last hit
         stored = depth != 0;
-        break;
+        done = true;
+      } else {
+        float3 nrm, P;
+        int mesh;
+        hit_geometry(S, h, nrm, P, mesh);
+        const DMaterial m = S.mats[mesh];
+        ppos = P;
+        pdir = v_neg(d);
+        const float3 rd = hsphere_uniform_sample(g, nrm);
+        const float3 refl = v_sub(d, v_scl(nrm, __fmul_rn(2.f, v_dot(d, nrm))));
+        const float bsdf = v_len(evaluate_color_response(m, nrm, d, rd));
+        const float pdf = __fdiv_rn(__fadd_rn(v_dot(v_norm(rd), v_norm(refl)), 1.f), 2.f);
+        weight = __fmul_rn(weight, __fdiv_rn(bsdf, pdf));
+        const float cont = fminf(weight, 1.f);
+        if (g.uniform_f(0.f, 1.f) > cont) {  // PhotonMap.h:144-150, then :94-97 on entry at depth + 1
+          stored = true;
+          hist = depth + 1;
+          done = true;
+        } else {
+          weight = __fdiv_rn(weight, cont);
+          o = P;
+          d = rd;
+          depth++;
+          done = depth >= 20;  // PhotonMap.h:98: dropped, not stored
+        }
       }
-      float3 nrm, P;
-      int mesh;
-      hit_geometry(S, h, nrm, P, mesh);
-      const DMaterial m = S.mats[mesh];
-      ppos = P;
-      pdir = v_neg(d);
-      float3 rd = hsphere_uniform_sample(g, nrm);
-      float3 refl = v_sub(d, v_scl(nrm, __fmul_rn(2.f, v_dot(d, nrm))));
-      float bsdf = v_len(evaluate_color_response(m, nrm, d, rd));
-      float pdf = __fdiv_rn(__fadd_rn(v_dot(v_norm(rd), v_norm(refl)), 1.f), 2.f);
-      weight = __fmul_rn(weight, __fdiv_rn(bsdf, pdf));
-      float cont = fminf(weight, 1.f);
-      if (g.uniform_f(0.f, 1.f) > cont)  // PhotonMap.h:144-150
-        exit = true;
-      else
-        weight = __fdiv_rn(weight, cont);
-      o = P;
-      d = rd;
+      if (done) {
+        out_a[q] = make_float4(ppos.x, ppos.y, ppos.z, weight);
+        out_b[q] = make_float4(pdir.x, pdir.y, pdir.z, __int_as_float((stored ? 1 : 0) | (hist << 8)));
+        alive = false;
+      }
     }
-    out_a[q] = make_float4(ppos.x, ppos.y, ppos.z, weight);
-    out_b[q] = make_float4(pdir.x, pdir.y, pdir.z, __int_as_float((stored ? 1 : 0) | (hist << 8)));
   }
   for (int off = 16; off > 0; off >>= 1) n_rays += __shfl_xor_sync(kFull, n_rays, off);
-  if ((threadIdx.x & 31) == 0 && n_rays) atomicAdd(counters + kCntPhotonRays, (unsigned long long)n_rays);
+  if (lane == 0 && n_rays) atomicAdd(counters + kCntPhotonRays, (unsigned long long)n_rays);
 }
 void launch_emit(const DScene& s, uint64_t seed_mixed, int per_light, float light_pdf, int first_path, int npaths,
-                 int brute, float4* out_a, float4* out_b, unsigned long long* counters, cudaStream_t st) {
+                 int brute, float4* out_a, float4* out_b, unsigned long long* counters, unsigned* cursor, int num_sms,
+                 cudaStream_t st) {
   long long total = (long long)s.num_lights * npaths;
   long long blocks = (total + kBlock - 1) / kBlock;
-  if (blocks > 148 * 16) blocks = 148 * 16;
+  // persistent: a few CTAs per SM share the cursor (20 KB of traversal stack each)
+  const long long resident = (long long)(num_sms > 0 ? num_sms : 148) * 8;
+  if (blocks > resident) blocks = resident;
   if (blocks < 1) blocks = 1;
+  cudaMemsetAsync(cursor, 0, sizeof(unsigned), st);
   k_emit<<<(int)blocks, kBlock, 0, st>>>(s, seed_mixed, per_light, light_pdf, first_path, npaths, brute, out_a, out_b,
-                                         counters);
+                                         counters, cursor);
 }
-
 
 // ----------------------------------------------------------------------------------------------
 // Device-resident photon list (multi-GPU path): the particles k_emit stored are compacted in

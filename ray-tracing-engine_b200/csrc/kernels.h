@@ -129,8 +129,10 @@ void launch_bsdf(DMaterial m, const float* n_wi_wo, long long n, float* rgb, cud
 void launch_hsphere(uint64_t seed_mixed, uint64_t domain, uint64_t index0, const float* normals, long long n, float* out,
                     cudaStream_t st);
 // photon emission: path q = light*npaths + j traces path (first_path + j) of `light`
+// cursor: one unsigned in device memory (zeroed by the launch), the work-fetch cursor of the persistent lanes
 void launch_emit(const DScene& s, uint64_t seed_mixed, int per_light, float light_pdf, int first_path, int npaths,
-                 int brute, float4* out_a, float4* out_b, unsigned long long* counters, cudaStream_t st);
+                 int brute, float4* out_a, float4* out_b, unsigned long long* counters, unsigned* cursor, int num_sms,
+                 cudaStream_t st);
 // device-resident photon list: ordered compaction of k_emit's output, splice of all-gathered shards, unpack for the gather
 int photon_compact_blocks(long long total);
 void launch_photon_compact(const float4* out_a, const float4* out_b, long long total, int npaths, unsigned* block_count,

@@ -286,19 +286,19 @@ def test_knn_errors(rt, gold):
 
 
 def test_photon_emission_against_oracle(rt, O, gold):
-    """Emission goes through asin/sin/cos at every bounce: statistical parity by contract.  We check
-    the stored count and the depth histogram against the reference (within 4 sigma per bin) and
-    that the large majority of paths are bit-identical."""
+    """Emission goes through asin/sin/cos at every bounce.  The stored count, the depth histogram and the particles
+    themselves are compared with the reference's list (same streams)."""
     g = gold("photons.npz")
     r = make_renderer(rt, "stock")
     r.set(num_photons=3000, k=10)
     plist, counts, hist = r.emit_photons()
     want = g["list"]
-    assert abs(len(plist) - len(want)) <= 4 * np.sqrt(len(want))
-    assert (np.abs(hist - g["hist"]) <= 4 * np.sqrt(np.maximum(g["hist"], 1)) + 2).all()
+    # round 2: with libm's sinf/cosf restated on the device the emitted list IS the reference's (observed: every
+    # particle bit-identical); the bar stays statistical for the rare asin last-bit difference
+    assert abs(len(plist) - len(want)) <= 2 and (np.abs(hist - g["hist"]) <= 2).all()
     same = {tuple(p) for p in want.view(np.uint32).reshape(len(want), 7).tolist()}
     got = sum(tuple(p) in same for p in plist.view(np.uint32).reshape(len(plist), 7).tolist())
-    assert got / len(want) > 0.85, got / len(want)
+    assert got / len(want) > 0.999, got / len(want)
     # sharded emission concatenates to the single-process list (the multi-GPU contract)
     per = r.photons_per_light()
     a, ca, _ = r.emit_photons(0, per // 2)
@@ -311,8 +311,8 @@ def test_photon_emission_against_oracle(rt, O, gold):
     assert beq(np.concatenate(parts), plist)
     r.set(num_photons=50000)
     plist50, _, hist50 = r.emit_photons()
-    assert abs(len(plist50) - int(g["count_50000"][0])) <= 4 * np.sqrt(len(plist50))
-    assert (np.abs(hist50 - g["hist_50000"]) <= 4 * np.sqrt(np.maximum(g["hist_50000"], 1)) + 2).all()
+    assert abs(len(plist50) - int(g["count_50000"][0])) <= 2
+    assert (np.abs(hist50 - g["hist_50000"]) <= 2).all()
 
 
 @pytest.mark.parametrize("case,N,mode,k", [("stock_m0_p3000_k10_win", 1, 0, 10), ("stock_m1_p3000_k5_N2_win", 2, 1, 5)])

@@ -92,17 +92,16 @@ def test_headline_cfg3_window_all_128_samples_shared_photons(rt, gold):
 
 
 def test_cfg3_emission_on_the_example_scene(rt, gold):
-    """Emission on the 11 666-triangle scene: count and depth histogram within 4 sigma of the reference's, and the
-    large majority of the particles bit-identical (emission goes through asin/sin/cos at every bounce)."""
+    """Emission on the 11 666-triangle scene: the stored count, the depth histogram and the particles are the
+    reference's (emission goes through asin and libm's sin/cos at every bounce; the latter are restated exactly)."""
     g = gold("render_example_m1_N128_p50000_k10_win.npz")
     r = rt.Renderer(rt.Scene.load(scene_path("example")), 1, 0, None, 50000, 10, seed=SEED)
     plist, counts, hist = r.emit_photons()
     want = g["photons"]
-    assert abs(len(plist) - len(want)) <= 4 * np.sqrt(len(want))
-    assert (np.abs(hist - g["depth_hist"]) <= 4 * np.sqrt(np.maximum(g["depth_hist"], 1)) + 2).all()
+    assert abs(len(plist) - len(want)) <= 2 and (np.abs(hist - g["depth_hist"]) <= 2).all()
     same = {tuple(p) for p in want.view(np.uint32).reshape(len(want), 7).tolist()}
     got = sum(tuple(p) in same for p in plist.view(np.uint32).reshape(len(plist), 7).tolist())
-    assert got / len(want) > 0.85, got / len(want)
+    assert got / len(want) > 0.999, got / len(want)  # observed: all 35 814 particles bit-identical
 
 
 def test_hsphere_sampling_is_bit_identical_to_the_reference(rt, gold):
@@ -203,10 +202,10 @@ def test_scenes_with_other_light_counts_match_the_reference(rt, gold, name):
     r0.set(num_photons=3000, k=5)
     plist, counts, hist = r0.emit_photons()
     want = g["photons"]
-    assert len(counts) == scene.L and abs(len(plist) - len(want)) <= 4 * np.sqrt(len(want))
+    assert len(counts) == scene.L and abs(len(plist) - len(want)) <= 2
     same = {tuple(p) for p in want.view(np.uint32).reshape(len(want), 7).tolist()}
     got = sum(tuple(p) in same for p in plist.view(np.uint32).reshape(len(plist), 7).tolist())
-    assert got / len(want) > 0.85
+    assert got / len(want) > 0.999
 
 
 def test_more_lights_than_fit_in_kernel_parameters(rt, O):
