@@ -332,8 +332,8 @@ def test_photon_render_on_shared_list(rt, gold, case, N, mode, k):
 
 
 def test_photon_render_full_pipeline_cfg4_like(rt, gold):
-    """-m 0 -p 50000 -k 10 on the stock scene, photons emitted on the GPU: per-pixel comparison with
-    the reference image is statistical here (different photons where a transcendental bit differs)."""
+    """-m 0 -p 50000 -k 10 on the stock scene, photons emitted on the GPU: the whole photon pipeline against the
+    reference's frame."""
     path = os.path.join(os.path.dirname(__file__), "golden", "render_stock_m0_p50000_k10_N1.npz")
     if not os.path.exists(path):
         pytest.skip("heavy golden not generated")
@@ -341,9 +341,12 @@ def test_photon_render_full_pipeline_cfg4_like(rt, gold):
     r = make_renderer(rt, "stock", N=1, mode=0)
     r.set(num_photons=50000, k=10)
     img = r.render(rt.Image(420, 420).fillBackground())
+    # round 2: the GPU emits the reference's photon list bit for bit (libm's sin/cos restated), so the whole pipeline
+    # -- emission, kd-tree, gather, shading -- reproduces the reference's 8-bit frame per pixel
+    d = np.abs(img.to8().astype(int) - g["image8"].astype(int)).max(axis=-1)
+    assert (d <= 1).mean() >= 0.999, f"only {(d <= 1).mean():.5f} of the pixels within 1/255"
     a, b = img.to8().astype(float) / 255, g["image8"].astype(float) / 255
-    assert abs(a.mean() - b.mean()) < 0.01
-    assert np.sqrt(np.mean((a - b) ** 2)) < 0.08
+    assert abs(a.mean() - b.mean()) < 1e-3
     assert r.stats()["knn_queries"] == int((g["counter"] > 0).sum())
 
 
