@@ -96,7 +96,7 @@ RT_DI void trace_start(const DScene& S, TraceLane& L, int* st_ref, int* st_tn) {
   for (int r = 0; r < S.num_roots; r++) {
     const float4 lo = S.root_lo[r], hi = S.root_hi[r];
     float tn;
-    if (box_hit_fma(f3(lo), f3(hi), L.inv, L.oinv, FLT_MAX, tn)) {
+    if (box_hit_fma<true>(f3(lo), f3(hi), L.inv, L.oinv, FLT_MAX, tn)) {
       const int ref = __float_as_int(hi.w);
       if (L.cur == kDone) {
         L.cur = ref;
@@ -121,8 +121,8 @@ RT_DI void trace_box_step(const DScene& S, TraceLane& L, int* st_ref, int* st_tn
   const float4 n0 = __ldg(S.nodes + 4 * L.cur), n1 = __ldg(S.nodes + 4 * L.cur + 1);
   const float4 n2 = __ldg(S.nodes + 4 * L.cur + 2), n3 = __ldg(S.nodes + 4 * L.cur + 3);
   float tn0, tn1;
-  const bool h0 = box_hit_fma(f3(n0.x, n0.y, n0.z), f3(n0.w, n1.x, n1.y), L.inv, L.oinv, L.h.t, tn0);
-  const bool h1 = box_hit_fma(f3(n1.z, n1.w, n2.x), f3(n2.y, n2.z, n2.w), L.inv, L.oinv, L.h.t, tn1);
+  const bool h0 = box_hit_fma<ANY>(f3(n0.x, n0.y, n0.z), f3(n0.w, n1.x, n1.y), L.inv, L.oinv, L.h.t, tn0);
+  const bool h1 = box_hit_fma<ANY>(f3(n1.z, n1.w, n2.x), f3(n2.y, n2.z, n2.w), L.inv, L.oinv, L.h.t, tn1);
   const int c0 = __float_as_int(n3.x), c1 = __float_as_int(n3.y);
   if (h0 && h1) {
     const bool first0 = tn0 <= tn1;
@@ -338,8 +338,8 @@ RT_DI void trace_body_spec(const DScene& S, const float4* __restrict__ ro, const
         const float4 n0 = __ldg(S.nodes + 4 * L.cur), n1 = __ldg(S.nodes + 4 * L.cur + 1);
         const float4 n2 = __ldg(S.nodes + 4 * L.cur + 2), n3 = __ldg(S.nodes + 4 * L.cur + 3);
         float tn0, tn1;
-        const bool h0 = box_hit_fma(f3(n0.x, n0.y, n0.z), f3(n0.w, n1.x, n1.y), L.inv, L.oinv, L.h.t, tn0);
-        const bool h1 = box_hit_fma(f3(n1.z, n1.w, n2.x), f3(n2.y, n2.z, n2.w), L.inv, L.oinv, L.h.t, tn1);
+        const bool h0 = box_hit_fma<ANY>(f3(n0.x, n0.y, n0.z), f3(n0.w, n1.x, n1.y), L.inv, L.oinv, L.h.t, tn0);
+        const bool h1 = box_hit_fma<ANY>(f3(n1.z, n1.w, n2.x), f3(n2.y, n2.z, n2.w), L.inv, L.oinv, L.h.t, tn1);
         const int c0 = __float_as_int(n3.x), c1 = __float_as_int(n3.y);
         const bool first0 = (ANY && kAnyFixedOrder) ? true : tn0 <= tn1;
         if (h0 && h1) {
