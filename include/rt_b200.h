@@ -148,10 +148,12 @@ typedef struct rt_stats {
   double kd_build_ms;      /* host wall time of the last kd-tree build (rt_set_photons)              */
   uint64_t kd_visits;      /* kd-tree nodes visited by the k-NN queries: kdtree::visited() summed, minus
                               the visits the exact plane-distance bound skips                        */
-  /* CUDA-event time (ms) and launch count of every kernel class in the LAST rt_render* / rt_emit_photons call
-   * (classes: RT_KERNEL_*); the events sit on the launching stream around each launch. */
+  /* CUDA-event time (ms) and launch count of every kernel class (RT_KERNEL_*), summed over the rt_render* calls since
+   * rt_create / rt_reset_stats; the events sit on the launching stream around each launch.  device_ms_total is
+   * device_ms summed the same way. */
   double kernel_ms[RT_NUM_KERNEL_CLASSES];
   uint64_t kernel_count[RT_NUM_KERNEL_CLASSES];
+  double device_ms_total;
 } rt_stats;
 
 typedef struct rt_ctx rt_ctx;

@@ -67,7 +67,8 @@ class rt_stats(C.Structure):
                 ("trace_ms", C.c_double), ("photon_ms", C.c_double), ("bvh_nodes", C.c_int32),
                 ("bvh_depth", C.c_int32), ("photons_stored", C.c_int64), ("create_ms", C.c_double),
                 ("bvh_build_ms", C.c_double), ("kd_build_ms", C.c_double), ("kd_visits", C.c_uint64),
-                ("kernel_ms", C.c_double * len(KERNEL_CLASSES)), ("kernel_count", C.c_uint64 * len(KERNEL_CLASSES))]
+                ("kernel_ms", C.c_double * len(KERNEL_CLASSES)), ("kernel_count", C.c_uint64 * len(KERNEL_CLASSES)),
+                ("device_ms_total", C.c_double)]
 
 
 PROGRESS_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_float))

@@ -121,6 +121,7 @@ struct rt_ctx {
   DevBuf<unsigned char> d_scratch;
   size_t auto_paths = 0;  // cached batch-size decision (paths per wavefront batch)
   bool oom_injected = false;  // RT_TEST_OOM_ONCE (tests only)
+  bool counters_dirty = false;  // the device ray / query counters moved since they were last read back
   // CUDA-event pairs around the kernel launches of the current render call, by kernel class
   struct TimedSpan {
     int cls;
@@ -366,24 +367,21 @@ int span_end(rt_ctx* c, int launches) {
   c->spans_used++;
   return RT_OK;
 }
-// after the stream has been synchronised: add the spans' times to the per-class totals of the call
+// after the stream has been synchronised: add the spans' times to the per-class totals (cumulative since
+// rt_reset_stats); trace_ms is the trace time of THIS call
 int collect_spans(rt_ctx* c) {
+  double trace = 0.0;
   for (size_t i = 0; i < c->spans_used; i++) {
     float t = 0.f;
     CU(cudaEventElapsedTime(&t, c->spans[i].e0, c->spans[i].e1));
     c->stats.kernel_ms[c->spans[i].cls] += t;
+    if (c->spans[i].cls == kKTraceNearest || c->spans[i].cls == kKTraceAny) trace += t;
   }
   c->spans_used = 0;
-  c->stats.trace_ms = c->stats.kernel_ms[kKTraceNearest] + c->stats.kernel_ms[kKTraceAny];
+  c->stats.trace_ms = trace;
   return RT_OK;
 }
-void reset_call_timing(rt_ctx* c) {
-  for (int i = 0; i < kKNumClasses; i++) {
-    c->stats.kernel_ms[i] = 0.0;
-    c->stats.kernel_count[i] = 0;
-  }
-  c->spans_used = 0;
-}
+void reset_call_timing(rt_ctx* c) { c->spans_used = 0; }
 
 // one wavefront batch: samples [s0, s0+nsamp) of the pixels in pix_map
 int run_batch(rt_ctx* c, RenderArgs& a, int s0, int nsamp) {
@@ -418,7 +416,15 @@ int run_batch(rt_ctx* c, RenderArgs& a, int s0, int nsamp) {
   return RT_OK;
 }
 
+// The device counters are read back only when somebody asks for the statistics (rt_get_stats): a render call does
+// not pay a device->host round trip for them.
 int pull_counters(rt_ctx* c) {
+  c->counters_dirty = true;
+  return RT_OK;
+}
+int read_counters(rt_ctx* c) {
+  if (!c->counters_dirty) return RT_OK;
+  c->counters_dirty = false;
   unsigned long long h[kCntNum];
   CU(cudaMemcpyAsync(h, c->d_counters.p, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
@@ -629,6 +635,7 @@ int render_to_device(rt_ctx* c, float* out_rgb_dev, int* out_cnt_dev, float* com
   float ms = 0.f;
   CU(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
   c->stats.device_ms = ms;
+  c->stats.device_ms_total += ms;
   if ((rc = collect_spans(c))) return rc;
   c->stats.samples += (uint64_t)c->npix * (uint64_t)std::max(samp_end - samp_first, 0);
   rc = pull_counters(c);
@@ -1255,7 +1262,7 @@ static int emit_to_device(rt_ctx* c, int32_t first_path, int32_t num_paths, floa
   d_lc.release();
   if (e != cudaSuccess) return fail(RT_ERR_CUDA, cudaGetErrorString(e));
   c->stats.photon_ms = ms;
-  c->stats.kernel_ms[kKEmit] = ms;
+  c->stats.kernel_ms[kKEmit] += ms;
   if (per_light_counts)
     for (int l = 0; l < c->L; l++) per_light_counts[l] = (int64_t)h_lc[l];
   if (depth_histogram20)
@@ -1544,6 +1551,11 @@ int rt_profiler_range(int on) {
 
 int rt_get_stats(rt_ctx* c, rt_stats* out) {
   if (!c || !out) return fail(RT_ERR_INVALID, "null argument");
+  if (c->counters_dirty) {
+    int rc = bind(c);
+    if (rc) return rc;
+    if ((rc = read_counters(c))) return rc;
+  }
   *out = c->stats;
   return RT_OK;
 }
@@ -1556,6 +1568,7 @@ int rt_reset_stats(rt_ctx* c) {
   if (rc) return rc;
   CU(cudaMemsetAsync(c->d_counters.p, 0, sizeof(unsigned long long) * kCntNum, c->stream));
   CU(cudaStreamSynchronize(c->stream));
+  c->counters_dirty = false;
   c->stats = rt_stats{};
   c->stats.bvh_nodes = nodes;
   c->stats.bvh_depth = depth;

@@ -42,7 +42,7 @@ def test_struct_layouts_match_the_header():
     assert C.sizeof(_capi.rt_material) == 32 and C.sizeof(_capi.rt_light) == 84 and C.sizeof(_capi.rt_camera) == 48
     assert C.sizeof(_capi.rt_params) == 64 and _capi.rt_params.seed.offset == 24
     assert C.sizeof(_capi.rt_scene) == 16 + 7 * 8 + 48
-    assert _capi.rt_stats.device_ms.offset == 64 and C.sizeof(_capi.rt_stats) == 136 + 2 * 8 * len(_capi.KERNEL_CLASSES)
+    assert _capi.rt_stats.device_ms.offset == 64 and C.sizeof(_capi.rt_stats) == 136 + 2 * 8 * len(_capi.KERNEL_CLASSES) + 8
     # ... and the library's own sizeof of every struct (rt_abi_sizes) agrees with the ctypes mirrors
     sizes = np.zeros(9, np.int32)
     assert _capi.load().rt_abi_sizes(_capi.ptr(sizes), 9) == 0
