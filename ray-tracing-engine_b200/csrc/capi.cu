@@ -100,13 +100,14 @@ struct rt_ctx {
   DevBuf<int> d_pix_map;
   int npix = 0;
   int pix_w = -1, pix_h = -1, pix_rank = -1, pix_count = -1, pix_tile = -1;
-  DevBuf<float4> d_col0, d_col1, d_qo0, d_qo1, d_qd0, d_qd1, d_acc;
+  DevBuf<float4> d_col0, d_col1, d_col2, d_qo0, d_qo1, d_qd0, d_qd1, d_acc;
   DevBuf<float4> d_hit, d_hit_p, d_sh_d, d_contrib;
   DevBuf<DLight> d_lights_ext;             // lights beyond the kMaxLights kept in kernel-parameter space
   DevBuf<unsigned long long> d_knn_scratch;  // k-NN candidates of every resident thread when k > kKnnSharedMaxK
   int knn_scratch_threads = 0;
   int knn_gather = 0;  // RT_KNN_GATHER=1: the photon queries run in the persistent gather kernel instead of inside k_shade
   int sort_seg0 = 1;   // RT_SORT_SEG0=0: the photon gather of segment 0 keeps the pixel-tile order of the primary hits
+  int sort_segs = -1;  // RT_SORT_SEGS=mask: which segments are Morton-binned (default: 1 and 2, plus 0 with a photon map)
   int own_tri = 0;  // RT_OWN_TRI=1: k_shade pre-tests a shadow ray against the triangle it starts on (measured: no gain)
   DevBuf<unsigned char> d_occ;
   DevBuf<int> d_hit_path;
@@ -221,14 +222,15 @@ int trace_stack_depth(const rt_ctx* c) {
   return std::max(std::max(c->bvh.depth, c->scene.num_roots > 0 ? c->bvh.mesh_depth + c->scene.num_roots : 0), 1);
 }
 
-// bytes of wavefront state per path slot (ensure_work below) with nl shadow slots per hit: colours 2 x 16, ray queues
+// bytes of wavefront state per path slot (ensure_work below) with nl shadow slots per hit: colours 3 x 16, ray queues
 // 2 x 32, hit record 16, hit point 16, per shadow slot direction 16 + contribution 16 + occlusion 1, path id 4,
 // sort key 4, sorted payload 32
-size_t bytes_per_path(int nl) { return 16 * 2 + 32 * 2 + 16 + 16 + (size_t)std::max(nl, 1) * (16 + 16 + 1) + 4 + 4 + 32; }
+size_t bytes_per_path(int nl) { return 16 * 3 + 32 * 2 + 16 + 16 + (size_t)std::max(nl, 1) * (16 + 16 + 1) + 4 + 4 + 32; }
 
 void release_work(rt_ctx* c) {
   c->d_col0.release();
   c->d_col1.release();
+  c->d_col2.release();
   c->d_qo0.release();
   c->d_qo1.release();
   c->d_qd0.release();
@@ -260,6 +262,7 @@ int ensure_work(rt_ctx* c, size_t paths, bool path_mode, int nl) {
   CU(c->d_occ.ensure(shadow));
   if (path_mode) {
     CU(c->d_col1.ensure(paths));
+    CU(c->d_col2.ensure(paths));
     CU(c->d_qo1.ensure(paths));
     CU(c->d_qd1.ensure(paths));
   }
@@ -319,6 +322,7 @@ void fill_args(rt_ctx* c, RenderArgs& a, const int* pix_map, int npix, bool use_
   a.stack_depth = trace_stack_depth(c);
   a.col0 = c->d_col0.p;
   a.col1 = c->d_col1.p;
+  a.col2 = c->d_col2.p;
   a.ray_o[0] = c->d_qo0.p;
   a.ray_o[1] = c->d_qo1.p;
   a.ray_d[0] = c->d_qd0.p;
@@ -326,7 +330,7 @@ void fill_args(rt_ctx* c, RenderArgs& a, const int* pix_map, int npix, bool use_
   a.hit = c->d_hit.p;
   a.nl = shadow_lights(c, use_photons);
   a.own_tri = c->own_tri;
-  a.sort_seg0 = c->sort_seg0;
+  a.sort_mask = c->sort_segs >= 0 ? c->sort_segs : (6 | ((use_photons && c->sort_seg0) ? 1 : 0));
   a.hit_p = c->d_hit_p.p;
   a.sh_d = c->d_sh_d.p;
   // the persistent gather handles the two reference-exact flavours; its result array reuses the (unused in photon
@@ -404,7 +408,7 @@ int run_batch(rt_ctx* c, RenderArgs& a, int s0, int nsamp) {
   const int nseg = a.mode == 1 ? 3 : 1;
   for (int seg = 0; seg < nseg; seg++) {
     SPAN(kKTraceNearest, 1, launch_trace_nearest(a, seg, grid, c->stream));
-    if ((seg > 0 || (a.photon && a.sort_seg0)) && a.perm)  // spatial order: shadow-ray / k-NN traversal coherence
+    if (((a.sort_mask >> seg) & 1) && a.perm)  // spatial order: shadow-ray / k-NN traversal coherence
       SPAN(kKSort, 3, launch_sort_hits(a, seg, c->stream));
     if (a.photon && a.knn_out) SPAN(kKGather, 1, launch_knn_gather(a, seg, c->stream));
     SPAN(kKShade, 1, launch_shade(a, seg, std::max(grid_shade, 1), c->stream));
@@ -589,7 +593,8 @@ int render_to_device(rt_ctx* c, float* out_rgb_dev, int* out_cnt_dev, float* com
       int ns = std::min(spb, samp_end - s0);
       if ((rc = run_batch(c, a, s0, ns))) return rc;
       if ((rc = span_begin(c, kKResolve))) return rc;
-      launch_resolve(c->d_col0.p, c->npix, ns, c->d_acc.p, c->d_acc_cnt.p, c->stream);
+      launch_resolve(c->d_col0.p, c->d_col1.p, c->d_col2.p, path_mode ? 1 : 0, c->npix, ns, c->d_acc.p, c->d_acc_cnt.p,
+                     c->stream);
       if ((rc = span_end(c, 1))) return rc;
       const int done = s0 + ns - samp_first;
       if (preview && s0 + ns < samp_end && done / progress->every != (done - ns) / progress->every) {
@@ -683,6 +688,7 @@ int rt_destroy(rt_ctx* c) {
   c->d_pix_map.release();
   c->d_col0.release();
   c->d_col1.release();
+  c->d_col2.release();
   c->d_qo0.release();
   c->d_qo1.release();
   c->d_hit.release();
@@ -802,6 +808,7 @@ int rt_create(const rt_scene* s, const rt_params* p, int device, rt_ctx** out) {
   if (const char* e = getenv("RT_OWN_TRI")) c->own_tri = atoi(e) != 0;
   if (const char* e = getenv("RT_KNN_GATHER")) c->knn_gather = atoi(e) != 0;
   if (const char* e = getenv("RT_SORT_SEG0")) c->sort_seg0 = atoi(e) != 0;
+  if (const char* e = getenv("RT_SORT_SEGS")) c->sort_segs = atoi(e) & 7;
   if (!(extent < 1e8f)) {  // keeps lo * safe_inv(d) finite in the slab test (rt_device.cuh)
     rt_destroy(c);
     return fail(RT_ERR_INVALID, "scene coordinates must be finite and smaller than 1e8");
@@ -1079,7 +1086,10 @@ int rt_render_samples(rt_ctx* c, int32_t x0, int32_t y0, int32_t x1, int32_t y1,
   rc = run_batch(c, a, s0, ns);
   std::vector<float4> h(paths);
   cudaError_t e = cudaSuccess;
-  if (rc == RT_OK) e = cudaMemcpyAsync(h.data(), c->d_col0.p, paths * sizeof(float4), cudaMemcpyDeviceToHost, c->stream);
+  if (rc == RT_OK) {
+    launch_finalize_paths(c->d_col0.p, c->d_col1.p, c->d_col2.p, (long long)paths, p.mode == 1 ? 1 : 0, c->stream);
+    e = cudaMemcpyAsync(h.data(), c->d_col0.p, paths * sizeof(float4), cudaMemcpyDeviceToHost, c->stream);
+  }
   cudaError_t e2 = cudaStreamSynchronize(c->stream);
   if (e == cudaSuccess) e = e2;
   d_map.release();

@@ -764,7 +764,7 @@ __global__ void __launch_bounds__(kBlock, 6) k_knn_gather(const RenderArgs A, co
       if (!live) {
         const unsigned my = base + __popc(need_mask & lt_mask);
         if (my < n) {
-          const float4 hr = ((seg > 0 || A.sort_seg0) && A.perm != nullptr) ? A.sorted[2 * (size_t)my] : A.hit[my];
+          const float4 hr = (((A.sort_mask >> seg) & 1) && A.perm != nullptr) ? A.sorted[2 * (size_t)my] : A.hit[my];
           HitRec h;
           h.t = hr.x, h.u = hr.y, h.v = hr.z, h.gid = __float_as_int(hr.w);
           if (h.gid >= 0) {
@@ -847,7 +847,7 @@ __global__ void __launch_bounds__(kBlock, PHOTON ? 6 : RT_SHADE_MINB) k_shade(co
   unsigned n_hit = 0, n_knn = 0;
   unsigned long long n_visits = 0;
 
-  const bool permuted = (seg > 0 || (PHOTON && A.sort_seg0)) && A.perm != nullptr;
+  const bool permuted = ((A.sort_mask >> seg) & 1) && A.perm != nullptr;
   for (unsigned base = blockIdx.x * kBlock; base < n; base += gridDim.x * kBlock) {
     const unsigned slot = base + threadIdx.x;
     bool found = false;
@@ -882,15 +882,14 @@ __global__ void __launch_bounds__(kBlock, PHOTON ? 6 : RT_SHADE_MINB) k_shade(co
       j = j0 + __popc(mask & ((1u << lane) - 1u));
     }
     if (slot < n && !found) {
-      // Renderer.cpp:154-160: a miss ends the path; the colour so far is clamped and final
-      if (seg == 0) {
-        A.col0[p] = make_float4(0.f, 0.f, 0.f, 0.f);  // posIntersectionFound = false
-      } else {
-        float4 c0 = A.col0[p];
-        float3 sum = f3(c0);
-        if (seg == 2) sum = v_add(sum, v_add(f3(A.col1[p]), f3(0.f, 0.f, 0.f)));
-        float3 out = normalize_color(sum);
-        A.col0[p] = make_float4(out.x, out.y, out.z, c0.w);
+      // Renderer.cpp:154-160: a miss ends the path and contributes Vec3f(0) from this segment on.  The segments' colours
+      // live in their own arrays and are added -- c0 + (c1 + c2), Renderer.cpp:168 -- and clamped by k_resolve, so a
+      // path that ends here only zeroes the terms it will never write (no read-modify-write of earlier ones).
+      const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (seg == 0) A.col0[p] = zero;  // w = 0: posIntersectionFound = false
+      if (MODE == 1) {
+        if (seg <= 1) A.col1[p] = zero;
+        A.col2[p] = zero;
       }
     }
     if (found) {
@@ -1030,15 +1029,17 @@ __global__ void __launch_bounds__(256) k_combine(const RenderArgs A, const int s
       }
     }
     const unsigned p = (unsigned)A.hit_path[j];
+    // one write per hit and no read: hits of the bounce segments arrive in Morton order, so p is scattered; the path
+    // sum and the per-sample clamp (Renderer.cpp:168,254) happen in k_resolve, which reads the three arrays coalesced
+    // (with the read-modify-write of col0 here k_combine took 2.26 ms per cfg2 frame, 0.80 ms when the hits were
+    // left unsorted)
     if (seg == 0) {
       float3 out = A.mode == 0 ? normalize_color(c) : c;
       A.col0[p] = make_float4(out.x, out.y, out.z, 1.f);
     } else if (seg == 1) {
       A.col1[p] = make_float4(c.x, c.y, c.z, 0.f);
     } else {
-      float4 c0 = A.col0[p];
-      float3 out = normalize_color(v_add(f3(c0), v_add(f3(A.col1[p]), c)));
-      A.col0[p] = make_float4(out.x, out.y, out.z, c0.w);
+      A.col2[p] = make_float4(c.x, c.y, c.z, 0.f);
     }
   }
 }
@@ -1052,13 +1053,34 @@ void launch_combine(const RenderArgs& a, int seg, int grid, cudaStream_t st) {
 // ----------------------------------------------------------------------------------------------
 // ordered accumulation: updateImage(x,y) += colorResponse for samples in index order
 // ----------------------------------------------------------------------------------------------
-__global__ void k_resolve(const float4* __restrict__ col0, int npix, int nsamp, float4* acc_rgb, int* acc_cnt) {
+// path colour of one sample: -m 0: col0 holds the clamped colour already; -m 1: colorResponse = clamp(c0 + (c1 + c2))
+// (Renderer.cpp:168: color + calculateColorPath(...), recursion depth 3; :254 normalizeColor)
+RT_DI float4 path_colour(const float4* __restrict__ col0, const float4* __restrict__ col1, const float4* __restrict__ col2,
+                         size_t p, int mode) {
+  float4 c = col0[p];
+  if (mode == 1) {
+    const float3 out = normalize_color(v_add(f3(c), v_add(f3(col1[p]), f3(col2[p]))));
+    c = make_float4(out.x, out.y, out.z, c.w);
+  }
+  return c;
+}
+// the same written back into col0 (rt_render_samples hands the per-sample colours to the caller)
+__global__ void k_finalize_paths(float4* col0, const float4* __restrict__ col1, const float4* __restrict__ col2,
+                                 long long n, int mode) {
+  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < n) col0[p] = path_colour(col0, col1, col2, (size_t)p, mode);
+}
+void launch_finalize_paths(float4* col0, const float4* col1, const float4* col2, long long n, int mode, cudaStream_t st) {
+  if (n > 0 && mode == 1) k_finalize_paths<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(col0, col1, col2, n, mode);
+}
+__global__ void k_resolve(const float4* __restrict__ col0, const float4* __restrict__ col1,
+                          const float4* __restrict__ col2, int mode, int npix, int nsamp, float4* acc_rgb, int* acc_cnt) {
   int pl = blockIdx.x * blockDim.x + threadIdx.x;
   if (pl >= npix) return;
   float4 acc = acc_rgb[pl];
   int cnt = acc_cnt[pl];
   for (int s = 0; s < nsamp; s++) {
-    float4 c = col0[(size_t)s * npix + pl];
+    float4 c = path_colour(col0, col1, col2, (size_t)s * npix + pl, mode);
     acc.x = __fadd_rn(acc.x, c.x);
     acc.y = __fadd_rn(acc.y, c.y);
     acc.z = __fadd_rn(acc.z, c.z);
@@ -1067,8 +1089,9 @@ __global__ void k_resolve(const float4* __restrict__ col0, int npix, int nsamp, 
   acc_rgb[pl] = acc;
   acc_cnt[pl] = cnt;
 }
-void launch_resolve(const float4* col0, int npix, int nsamp, float4* acc_rgb, int* acc_cnt, cudaStream_t st) {
-  k_resolve<<<(npix + 255) / 256, 256, 0, st>>>(col0, npix, nsamp, acc_rgb, acc_cnt);
+void launch_resolve(const float4* col0, const float4* col1, const float4* col2, int mode, int npix, int nsamp,
+                    float4* acc_rgb, int* acc_cnt, cudaStream_t st) {
+  k_resolve<<<(npix + 255) / 256, 256, 0, st>>>(col0, col1, col2, mode, npix, nsamp, acc_rgb, acc_cnt);
 }
 
 __global__ void k_scatter(const float4* __restrict__ acc_rgb, const int* __restrict__ acc_cnt,

@@ -57,15 +57,17 @@ struct RenderArgs {
   const int* pix_map;  // local pixel -> y*W + x
   int npix;
   int s0, nsamp;
-  float4* col0;  // per path: seg-0 colour, then the final clamped colour; w = posIntersectionFound
-  float4* col1;  // per path: seg-1 colour
+  float4* col0;  // per path: seg-0 colour (-m 0: clamped, final); w = posIntersectionFound
+  float4* col1;  // per path: seg-1 colour (zero when the path ended before)
+  float4* col2;  // per path: seg-2 colour (zero when the path ended before)
   float4* ray_o[2];  // ray queues, ping-pong by segment: (origin, path id) / (direction, -)
   float4* ray_d[2];
   float4* hit;       // per ray slot of the current segment: (t, u, v, triangle id | -1)
   int nl;            // shadow slots per hit (see shadow_slot): number of lights, or 1 for the photon gather
   int own_tri;       // 1: k_shade tests a shadow ray against the triangle it starts on before queueing it
-  int sort_seg0;     // photon gather: 1 = segment 0's hit points are binned by Morton cell too, 0 = they keep the
-                     // pixel-tile order of the primary rays (a warp = an 8x4 pixel tile of one sample)
+  int sort_mask;     // bit s: segment s's hit points are binned by Morton cell before k_shade (default: the bounce
+                     // segments 1 and 2; with a photon map also segment 0, whose queries otherwise keep the pixel-tile
+                     // order of the primary rays)
   float4* hit_p;     // per compacted hit j: the hit point = origin of its nl shadow rays
   float4* sh_d;      // shadow ray directions, blocked layout (see shadow_slot); w != 0: already known occluded
   float4* contrib;   // radiance * bsdf of light l for hit j, same layout
@@ -105,7 +107,10 @@ void launch_combine(const RenderArgs& a, int seg, int grid_ctas, cudaStream_t st
 int trace_ctas_per_sm(int stack_depth);
 size_t trace_smem_bytes(int stack_depth);
 
-void launch_resolve(const float4* col0, int npix, int nsamp, float4* acc_rgb, int* acc_cnt, cudaStream_t st);
+void launch_resolve(const float4* col0, const float4* col1, const float4* col2, int mode, int npix, int nsamp,
+                    float4* acc_rgb, int* acc_cnt, cudaStream_t st);
+// col0 <- the final clamped path colours (what k_resolve accumulates), for rt_render_samples
+void launch_finalize_paths(float4* col0, const float4* col1, const float4* col2, long long n, int mode, cudaStream_t st);
 void launch_scatter(const float4* acc_rgb, const int* acc_cnt, const int* pix_map, int npix, float* out_rgb,
                     int* out_cnt, cudaStream_t st);
 // sums + counter as one float4 per pixel (one reduce across GPUs instead of two)
