@@ -512,8 +512,12 @@ struct Progress {
   rt_progress_fn fn = nullptr;
   void* user = nullptr;
 };
+// background_host != null: the host frame composite_dev is to be filled from.  It is uploaded AFTER the sample batches have
+// been enqueued (the staging of a pageable source then runs on the host while the GPU traces), or up front when a
+// preview needs it between batches.
 int render_to_device(rt_ctx* c, float* out_rgb_dev, int* out_cnt_dev, float* composite_dev = nullptr,
-                     const Progress* progress = nullptr, float4* packed_dev = nullptr) {
+                     const Progress* progress = nullptr, float4* packed_dev = nullptr,
+                     const float* background_host = nullptr) {
   static const bool timing = getenv("RT_TIMING") != nullptr;
   double t_prev = now_ms();
   auto tick = [&](const char* what) {
@@ -554,6 +558,11 @@ int render_to_device(rt_ctx* c, float* out_rgb_dev, int* out_cnt_dev, float* com
   if (preview) {
     snapshot.resize(3 * npx);
     CU(c->d_scratch.ensure(sizeof(float) * 3 * npx));
+  }
+  bool background_up = !(background_host && composite_dev);
+  if (!background_up && preview) {
+    CU(cudaMemcpyAsync(composite_dev, background_host, sizeof(float) * 3 * npx, cudaMemcpyHostToDevice, c->stream));
+    background_up = true;
   }
   tick("batch sizing");
   rc = ensure_work(c, (size_t)c->npix * spb, path_mode, nl);
@@ -609,6 +618,8 @@ int render_to_device(rt_ctx* c, float* out_rgb_dev, int* out_cnt_dev, float* com
       }
     }
   }
+  if (!background_up)
+    CU(cudaMemcpyAsync(composite_dev, background_host, sizeof(float) * 3 * npx, cudaMemcpyHostToDevice, c->stream));
   if ((rc = span_begin(c, kKOther))) return rc;
   int tail_launches = 0;
   if (composite_dev) {
@@ -1046,9 +1057,8 @@ int rt_render_progressive(rt_ctx* c, float* rgb_inout, int32_t every, rt_progres
   if (rc) return rc;
   // background up, the whole Renderer::render on the device (composite included), frame down
   CU(c->d_out_rgb.ensure(3 * npx));
-  CU(cudaMemcpyAsync(c->d_out_rgb.p, rgb_inout, sizeof(float) * 3 * npx, cudaMemcpyHostToDevice, c->stream));
   Progress progress{every, fn, user};
-  if ((rc = render_to_device(c, nullptr, nullptr, c->d_out_rgb.p, &progress))) return rc;
+  if ((rc = render_to_device(c, nullptr, nullptr, c->d_out_rgb.p, &progress, nullptr, rgb_inout))) return rc;
   CU(cudaMemcpyAsync(rgb_inout, c->d_out_rgb.p, sizeof(float) * 3 * npx, cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
   if (fn && every > 0) fn(user, p.num_rays, p.num_rays, rgb_inout);  // the last pass: update.ppm == the result

@@ -18,7 +18,8 @@ W = H = 200
 bg = rt.Image(W, H).fillBackground().pixels
 scene.w = scene.h = W
 ok = True
-for (N, mode, photons, k) in ((8, 1, 0, 5), (2, 0, 30000, 10), (4, 1, 30000, 7)):
+REPEAT = int(os.environ.get("DIST_CHECK_REPEAT", "1"))  # buffer-lifetime races are intermittent: repeat the cases
+for (N, mode, photons, k) in ((8, 1, 0, 5), (2, 0, 30000, 10), (4, 1, 30000, 7)) * REPEAT:
     for shard in ("tile", "sample"):
         img = D.render_distributed(scene, N, mode, photons, k, background=bg, seed=5, shard=shard, device=dev,
                                    local_device=local)

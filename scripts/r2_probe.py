@@ -82,3 +82,21 @@ if "cfg4" in what:
                               photon_rays=st["photon_rays"], knn_queries=st["knn_queries"], kd_visits=st["kd_visits"],
                               kernel_ms={k: round(x, 3) for k, x in st["kernel_ms"].items()}, mean=float(img.pixels.mean()))), flush=True)
         r.close()
+if "e2e" in what:  # where the host side of one user-facing cfg2 call goes (bench.py's e2e step, phase by phase)
+    bg = rt.Image(420, 420).fillBackground().pixels
+    acc = {}
+    n_it = 12
+    for it in range(n_it + 2):
+        t = [time.perf_counter()]
+        r = rt.Renderer(ex, 128, 1, seed=1); t.append(time.perf_counter())
+        img = rt.Image(420, 420); img.pixels = bg.copy(); t.append(time.perf_counter())
+        r.render(img); t.append(time.perf_counter())
+        st = r.stats(); t.append(time.perf_counter())
+        r.close(); t.append(time.perf_counter())
+        if it < 2:
+            continue
+        for name, a, b in (("Renderer()", 0, 1), ("image", 1, 2), ("render", 2, 3), ("stats", 3, 4), ("close", 4, 5), ("total", 0, 5)):
+            acc[name] = acc.get(name, 0.0) + 1e3 * (t[b] - t[a]) / n_it
+        for key in ("create_ms", "bvh_build_ms", "device_ms"):
+            acc[key] = acc.get(key, 0.0) + st[key] / n_it
+    print(json.dumps(dict(probe="e2e_phases", **{k: round(v, 3) for k, v in acc.items()})), flush=True)
