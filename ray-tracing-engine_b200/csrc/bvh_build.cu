@@ -22,6 +22,7 @@
 // subtree, so no per-triangle bookkeeping other than `side` is needed.  Among equal keys the reference's order is
 // whatever libstdc++'s unstable std::sort leaves; ours is by triangle index.  The tree shape, the node numbering and
 // the layout are those of csrc/host_build.cpp, which stays the builder for small scenes and the checker in the tests.
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -302,6 +303,257 @@ __global__ void k_leaf_tris(const float4* __restrict__ pos, const int4* __restri
   tris[3 * (size_t)slot + 2] = make_float4(__fsub_rn(c.x, a.x), __fsub_rn(c.y, a.y), __fsub_rn(c.z, a.z), 0.f);
 }
 
+// ---- small meshes: one thread-block cluster builds one mesh's whole subtree ---------------------------------------
+// The level loop above costs 7 launches per level (120 launches, 0.64 ms at 11 666 triangles: launch latency, the
+// kernels are empty).  When no mesh has more than kSmallMeshMax triangles, a cluster of kMeshCluster CTAs x 1024 threads
+// runs the same phases for its mesh with the hardware cluster barrier between them; the scratch arrays stay in global
+// memory and are read with ld.cg (L2: the CTAs of a cluster sit on different SMs, whose L1s are not coherent).
+// A position's segment at a level -- its range [b, e), node index, parent and side -- follows from halving the mesh's
+// range `level` times (node numbering is analytic, see above), so no segment table is kept: descend() recomputes it.
+// (Measured, B200, 11 666 triangles in 5 meshes: a single CTA per mesh took 1.69 ms -- 32 warps walking 12 rounds of
+// dependent L2 round trips per phase; see profiles/r2_tuning.md for the cluster's number.)
+constexpr int kMeshThreads = 1024;
+constexpr int kMeshCluster = 8;
+constexpr int kSmallMeshMax = 16384;
+struct MeshJob {
+  int t0, n;      // the mesh's triangle range == its position range in the three orders == its leaf slots
+  int node_base;  // first node of its subtree
+  int root;       // slot in the root tables
+};
+struct SegAt {
+  int b, e, node, parent, side;
+  bool active;  // false: the position's segment became a leaf on an earlier level
+};
+__device__ inline SegAt descend(const MeshJob& J, int i, int level) {
+  SegAt g{J.t0, J.t0 + J.n, J.node_base, -1, J.root, true};
+  for (int l = 0; l < level; l++) {
+    const int n = g.e - g.b;
+    if (n < 2) {
+      g.active = false;
+      break;
+    }
+    const int nl = n / 2;  // BVH.h:151-158
+    g.parent = g.node;
+    if (i < g.b + nl) {
+      g.side = 0;
+      g.node = g.node + 1;
+      g.e = g.b + nl;
+    } else {
+      g.side = 1;
+      g.node = g.node + nl;
+      g.b = g.b + nl;
+    }
+  }
+  return g;
+}
+struct MeshScratch {
+  const float4 *box_lo, *box_hi;     // per triangle
+  const unsigned long long* key[3];  // sorted (mesh | key | index) words
+  int *ord_a, *ord_b;                // 3 x T each: the three orders, ping-pong
+  unsigned* seg_box;                 // 6 per position, used at a segment's first position
+  int* seg_axis;                     // per position, used at a segment's first position
+  unsigned char* side;               // per triangle
+  int* scan;                         // 3 x T
+  int* slot_tri;
+  float* root_box;
+  int* root_ref;
+};
+__global__ void __launch_bounds__(kMeshThreads) k_build_mesh(const MeshJob* __restrict__ jobs, MeshScratch W, int T, int levels_max,
+                                                             const float4* __restrict__ pos, const int4* __restrict__ vidx,
+                                                             float pad, float* nodes, float4* tris) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  __shared__ unsigned long long warp_total[kMeshThreads / 32];
+  __shared__ unsigned long long cta_total;
+  const MeshJob J = jobs[blockIdx.x / kMeshCluster];
+  const int rank = (int)cluster.block_rank();
+  const int tid = threadIdx.x, gt = rank * kMeshThreads + tid, GT = kMeshCluster * kMeshThreads;
+  const int t0 = J.t0, t1 = J.t0 + J.n;
+  int levels = 1;
+  for (int n = J.n; n > 1; n -= n / 2) levels++;  // tree_depth(n)
+  levels = min(levels, levels_max);
+  int* ord_in = W.ord_a;
+  int* ord_out = W.ord_b;
+  for (int a = 0; a < 3; a++)
+    for (int i = t0 + gt; i < t1; i += GT) ord_in[(size_t)a * T + i] = (int)(W.key[a][i] & 0xffffffull);
+  if (gt < 6) W.seg_box[6 * (size_t)t0 + gt] = gt < 3 ? 0xffffffffu : 0u;
+  cluster.sync();
+  const int rounds = (J.n + GT - 1) / GT;  // positions per thread, strided (a warp = 32 neighbours)
+  const int chunk = rounds;                // positions per thread, contiguous (the scans)
+  for (int level = 0; level < levels; level++) {
+    // A. segment boxes: ordered-int atomic min/max at the segment's first position, warp-aggregated
+    for (int r = 0; r < rounds; r++) {
+      const int i = t0 + r * GT + gt;
+      int s = -1;
+      unsigned v[6] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u};
+      if (i < t1) {
+        const SegAt g = descend(J, i, level);
+        if (g.active) {
+          s = g.b;
+          const int t = __ldcg(ord_in + i);
+          const float4 lo = W.box_lo[t], hi = W.box_hi[t];
+          v[0] = f2ord(lo.x), v[1] = f2ord(lo.y), v[2] = f2ord(lo.z);
+          v[3] = f2ord(hi.x), v[4] = f2ord(hi.y), v[5] = f2ord(hi.z);
+        }
+      }
+      const unsigned full = 0xffffffffu;
+      const int s0 = __shfl_sync(full, s, 0);
+      if (__all_sync(full, s == s0)) {
+        if (s0 >= 0) {
+#pragma unroll
+          for (int c = 0; c < 6; c++)
+            for (int off = 16; off > 0; off >>= 1) {
+              const unsigned o = __shfl_xor_sync(full, v[c], off);
+              v[c] = c < 3 ? min(v[c], o) : max(v[c], o);
+            }
+          if ((tid & 31) == 0) {
+            for (int c = 0; c < 3; c++) atomicMin(W.seg_box + 6 * (size_t)s0 + c, v[c]);
+            for (int c = 3; c < 6; c++) atomicMax(W.seg_box + 6 * (size_t)s0 + c, v[c]);
+          }
+        }
+      } else if (s >= 0) {
+        for (int c = 0; c < 3; c++) atomicMin(W.seg_box + 6 * (size_t)s + c, v[c]);
+        for (int c = 3; c < 6; c++) atomicMax(W.seg_box + 6 * (size_t)s + c, v[c]);
+      }
+    }
+    cluster.sync();
+    // B. one thread per segment (the one at its first position): the box goes into the parent node, a leaf into the
+    //    slot table; an inner node picks its axis and clears its children's accumulators
+    for (int r = 0; r < rounds; r++) {
+      const int i = t0 + r * GT + gt;
+      if (i >= t1) break;
+      const SegAt g = descend(J, i, level);
+      if (!g.active || i != g.b) continue;
+      const int n = g.e - g.b;
+      float lo[3], hi[3];
+      for (int c = 0; c < 3; c++) {
+        lo[c] = ord2f(__ldcg(W.seg_box + 6 * (size_t)g.b + c));
+        hi[c] = ord2f(__ldcg(W.seg_box + 6 * (size_t)g.b + 3 + c));
+      }
+      const int ref = n == 1 ? ~g.b : g.node;
+      if (g.parent >= 0) {
+        float* nd = nodes + 16 * (size_t)g.parent + 6 * g.side;
+        for (int c = 0; c < 3; c++) {
+          nd[c] = lo[c] - pad;
+          nd[3 + c] = hi[c] + pad;
+        }
+        nodes[16 * (size_t)g.parent + 12 + g.side] = __int_as_float(ref);
+      } else {
+        for (int c = 0; c < 3; c++) {
+          W.root_box[6 * g.side + c] = lo[c];
+          W.root_box[6 * g.side + 3 + c] = hi[c];
+        }
+        W.root_ref[g.side] = ref;
+      }
+      if (n == 1) {
+        W.slot_tri[g.b] = __ldcg(ord_in + g.b);
+      } else {
+        float longest = 0.f;  // BVH.h:131-140: the first axis whose extent is strictly larger than everything before it
+        int axis = 0;
+        for (int c = 0; c < 3; c++) {
+          const float len = hi[c] - lo[c];
+          if (len > longest) {
+            longest = len;
+            axis = c;
+          }
+        }
+        W.seg_axis[g.b] = axis;
+        nodes[16 * (size_t)g.node + 14] = nodes[16 * (size_t)g.node + 15] = 0.f;
+        const int nl = n / 2;
+        for (int c = 0; c < 6; c++)
+          W.seg_box[6 * (size_t)g.b + c] = W.seg_box[6 * (size_t)(g.b + nl) + c] = c < 3 ? 0xffffffffu : 0u;
+      }
+    }
+    if (level + 1 >= levels) break;  // every segment of the last level is a leaf
+    cluster.sync();
+    // C. side of every triangle = its rank in the cut axis' order >= floor(n/2)
+    for (int r = 0; r < rounds; r++) {
+      const int i = t0 + r * GT + gt;
+      if (i >= t1) break;
+      const SegAt g = descend(J, i, level);
+      if (!g.active || g.e - g.b < 2) continue;
+      const int axis = __ldcg(W.seg_axis + g.b);
+      W.side[__ldcg(ord_in + (size_t)axis * T + i)] = i >= g.b + (g.e - g.b) / 2 ? 1 : 0;
+    }
+    cluster.sync();
+    // D1. per order: exclusive scan over the mesh's positions of "this triangle moves right" (0 inside segments cut on
+    //     this very axis, inside leaves and finished segments).  A thread owns `chunk` consecutive positions; the three
+    //     running sums travel as 21-bit fields of one word (n <= 16 384).
+    {
+      const int c0 = t0 + gt * chunk, c1 = min(c0 + chunk, t1);
+      unsigned long long local = 0;
+      for (int i = c0; i < c1; i++) {
+        const SegAt g = descend(J, i, level);
+        if (!g.active || g.e - g.b < 2) continue;
+        const int axis = __ldcg(W.seg_axis + g.b);
+        for (int a = 0; a < 3; a++)
+          if (a != axis) local += (unsigned long long)__ldcg(W.side + __ldcg(ord_in + (size_t)a * T + i)) << (21 * a);
+      }
+      unsigned long long incl = local;
+      for (int off = 1; off < 32; off <<= 1) {
+        const unsigned long long o = __shfl_up_sync(0xffffffffu, incl, off);
+        if ((tid & 31) >= off) incl += o;
+      }
+      if ((tid & 31) == 31) warp_total[tid >> 5] = incl;
+      __syncthreads();
+      if (tid < 32) {
+        unsigned long long w = warp_total[tid], wi = w;
+        for (int off = 1; off < 32; off <<= 1) {
+          const unsigned long long o = __shfl_up_sync(0xffffffffu, wi, off);
+          if (tid >= off) wi += o;
+        }
+        warp_total[tid] = wi - w;  // exclusive
+        if (tid == 31) cta_total = wi;
+      }
+      cluster.sync();  // every CTA's total is in its shared memory (a __syncthreads as well)
+      unsigned long long run = warp_total[tid >> 5] + incl - local;
+      for (int q = 0; q < rank; q++) run += *cluster.map_shared_rank(&cta_total, q);  // distributed shared memory
+      for (int i = c0; i < c1; i++) {
+        for (int a = 0; a < 3; a++) W.scan[(size_t)a * T + i] = (int)((run >> (21 * a)) & 0x1fffffull);
+        const SegAt g = descend(J, i, level);
+        if (!g.active || g.e - g.b < 2) continue;
+        const int axis = __ldcg(W.seg_axis + g.b);
+        for (int a = 0; a < 3; a++)
+          if (a != axis) run += (unsigned long long)__ldcg(W.side + __ldcg(ord_in + (size_t)a * T + i)) << (21 * a);
+      }
+    }
+    cluster.sync();
+    // D2. stable partition of the two other orders inside every segment
+    for (int r = 0; r < rounds; r++) {
+      const int i = t0 + r * GT + gt;
+      if (i >= t1) break;
+      const SegAt g = descend(J, i, level);
+      const bool split = g.active && g.e - g.b >= 2;
+      const int axis = split ? __ldcg(W.seg_axis + g.b) : -1;
+      for (int a = 0; a < 3; a++) {
+        const int t = __ldcg(ord_in + (size_t)a * T + i);
+        int dst = i;
+        if (split && a != axis) {
+          const int nl = (g.e - g.b) / 2;
+          // of this segment, before i, going right
+          const int rr = __ldcg(W.scan + (size_t)a * T + i) - __ldcg(W.scan + (size_t)a * T + g.b);
+          dst = __ldcg(W.side + t) ? g.b + nl + rr : g.b + (i - g.b) - rr;
+        }
+        ord_out[(size_t)a * T + dst] = t;
+      }
+    }
+    cluster.sync();
+    int* sw = ord_in;
+    ord_in = ord_out;
+    ord_out = sw;
+  }
+  cluster.sync();
+  // leaf-order triangles: (p0, global id) (e1) (e2) with the reference's own binary32 subtractions (Ray.cpp:11)
+  for (int slot = t0 + gt; slot < t1; slot += GT) {
+    const int gid = __ldcg(W.slot_tri + slot);
+    const int4 v = vidx[gid];
+    const float4 a = pos[v.x], b = pos[v.y], c = pos[v.z];
+    tris[3 * (size_t)slot] = make_float4(a.x, a.y, a.z, __int_as_float(gid));
+    tris[3 * (size_t)slot + 1] = make_float4(__fsub_rn(b.x, a.x), __fsub_rn(b.y, a.y), __fsub_rn(b.z, a.z), 0.f);
+    tris[3 * (size_t)slot + 2] = make_float4(__fsub_rn(c.x, a.x), __fsub_rn(c.y, a.y), __fsub_rn(c.z, a.z), 0.f);
+  }
+}
+
 // one stream-ordered scratch allocation carved into 256-byte aligned pieces (25 separate cudaMallocAsync calls
 // cost 9.5 ms of a 17 ms build)
 struct Arena {
@@ -332,6 +584,96 @@ int tree_depth(int n) {  // nodes on the longest root-to-leaf path of the median
     d++;
   }
   return d;
+}
+
+// the join of the per-mesh roots on the host, shared by both device paths (st is synchronised on return)
+bool finish_build(int T, int nonempty, int max_n, float pad, float* d_root_box, int* d_root_ref, int* d_slot_tri,
+                  float4* d_nodes, cudaStream_t st, Bvh& out, std::string& err) {
+  std::vector<float> h_root_box(6 * (size_t)nonempty);
+  std::vector<int32_t> h_root_ref(nonempty);
+  out.slot_tri.resize(T);
+  BV(cudaMemcpyAsync(h_root_box.data(), d_root_box, sizeof(float) * h_root_box.size(), cudaMemcpyDeviceToHost, st));
+  BV(cudaMemcpyAsync(h_root_ref.data(), d_root_ref, sizeof(int32_t) * nonempty, cudaMemcpyDeviceToHost, st));
+  BV(cudaMemcpyAsync(out.slot_tri.data(), d_slot_tri, sizeof(int32_t) * (size_t)T, cudaMemcpyDeviceToHost, st));
+  BV(cudaStreamSynchronize(st));
+  BV(cudaGetLastError());
+  const size_t num_nodes = (size_t)(T - nonempty) + (size_t)std::max(nonempty - 1, 0);
+  out.nodes.assign(16 * std::max<size_t>((size_t)std::max(nonempty - 1, 1), 1), 0.f);  // host copy of the join only
+  build_top_level(nonempty, h_root_box.data(), h_root_ref.data(), pad, tree_depth(max_n), out);
+  if (nonempty > 1)
+    BV(cudaMemcpyAsync(d_nodes, out.nodes.data(), sizeof(float) * 16 * (size_t)(nonempty - 1), cudaMemcpyHostToDevice, st));
+  BV(cudaStreamSynchronize(st));
+  out.num_nodes = num_nodes;  // the caller fetches the nodes from the device on demand (rt_get_bvh)
+  return true;
+}
+
+// keys + one batched sort + one cluster per mesh (k_build_mesh): 15 launches at 11 666 triangles instead of 120
+bool build_small_meshes(const float4* d_pos, const int4* d_vidx, int T, const std::vector<Seg>& roots, int max_n,
+                        long long n2, float pad, float4* d_nodes, float4* d_tris, cudaStream_t st, Bvh& out,
+                        long long* launches_out, std::string& err) {
+  long long launches = 0;
+  const int nonempty = (int)roots.size();
+  const int threads = 256, blocksT = (T + threads - 1) / threads;
+  Arena arena(st);
+  auto P = Arena::padded;
+  const size_t t = (size_t)T;
+  BV(arena.reserve(2 * P(t * 16) + 3 * P((size_t)n2 * 8) + 2 * P(3 * t * 4) + P(6 * t * 4) + P(t * 4) + P(t) + P(3 * t * 4) +
+                   P(t * 4) + P(6 * (size_t)nonempty * 4) + P((size_t)nonempty * 4) + P((size_t)nonempty * sizeof(MeshJob)) +
+                   4096));
+  float4* box_lo = arena.take<float4>(T);
+  float4* box_hi = arena.take<float4>(T);
+  unsigned long long* key[3] = {arena.take<unsigned long long>(n2), arena.take<unsigned long long>(n2),
+                                arena.take<unsigned long long>(n2)};
+  MeshScratch W;
+  W.box_lo = box_lo;
+  W.box_hi = box_hi;
+  for (int a = 0; a < 3; a++) W.key[a] = key[a];
+  W.ord_a = arena.take<int>(3 * t);
+  W.ord_b = arena.take<int>(3 * t);
+  W.seg_box = arena.take<unsigned>(6 * t);
+  W.seg_axis = arena.take<int>(T);
+  W.side = arena.take<unsigned char>(T);
+  W.scan = arena.take<int>(3 * t);
+  W.slot_tri = arena.take<int>(T);
+  W.root_box = arena.take<float>(6 * (size_t)nonempty);
+  W.root_ref = arena.take<int>(nonempty);
+  MeshJob* d_jobs = arena.take<MeshJob>(nonempty);
+  if (arena.used > arena.cap || key[1] != key[0] + n2 || key[2] != key[1] + n2) {
+    err = "internal: scratch arena too small";
+    return false;
+  }
+  std::vector<MeshJob> jobs;  // stays alive until the synchronisation in finish_build
+  for (const Seg& r : roots) jobs.push_back(MeshJob{r.b, r.e - r.b, r.node, r.side});
+  BV(cudaMemcpyAsync(d_jobs, jobs.data(), sizeof(MeshJob) * jobs.size(), cudaMemcpyHostToDevice, st));
+  k_tri_prepare<<<blocksT, threads, 0, st>>>(d_pos, d_vidx, T, box_lo, box_hi, key[0], key[1], key[2]);
+  launches++;
+  for (int a = 0; a < 3 && n2 > T; a++) {
+    k_fill_u64<<<(unsigned)((n2 - T + 255) / 256), 256, 0, st>>>(key[a], T, n2, ~0ull);
+    launches++;
+  }
+  if (!sort_keys(key[0], n2, st, &launches, 3, n2)) {
+    err = "bitonic sort launch failed";
+    return false;
+  }
+  {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)nonempty * kMeshCluster);
+    cfg.blockDim = dim3(kMeshThreads);
+    cfg.stream = st;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = kMeshCluster;
+    attr.val.clusterDim.y = attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    const MeshJob* jobs_arg = d_jobs;
+    BV(cudaLaunchKernelEx(&cfg, k_build_mesh, jobs_arg, W, T, tree_depth(max_n), d_pos, d_vidx, pad, (float*)d_nodes, d_tris));
+    launches++;
+  }
+  BV(cudaGetLastError());
+  if (!finish_build(T, nonempty, max_n, pad, W.root_box, W.root_ref, W.slot_tri, d_nodes, st, out, err)) return false;
+  if (launches_out) *launches_out = launches;
+  return true;
 }
 
 }  // namespace
@@ -369,6 +711,12 @@ bool build_bvh_device(const float4* d_pos, const int4* d_vidx, int T, int M, con
   const int threads = 256, blocksT = (T + threads - 1) / threads;
   long long n2 = kSortTile;
   while (n2 < T) n2 <<= 1;
+
+  {
+    const char* e = getenv("RT_BVH_SMALL");  // "0": always the level-synchronous launches (tests cover both)
+    if (max_n <= kSmallMeshMax && !(e && atoi(e) == 0))
+      return build_small_meshes(d_pos, d_vidx, T, roots, max_n, n2, pad, d_nodes, d_tris, st, out, launches_out, err);
+  }
 
   const int nb = (T + kScanBlock - 1) / kScanBlock;
   const size_t max_seg = (size_t)T + 2;
@@ -415,15 +763,15 @@ bool build_bvh_device(const float4* d_pos, const int4* d_vidx, int T, int M, con
   // 1. keys and the three orders
   k_tri_prepare<<<blocksT, threads, 0, st>>>(d_pos, d_vidx, T, box_lo.p, box_hi.p, key[0].p, key[1].p, key[2].p);
   launches++;
+  for (int a = 0; a < 3 && n2 > T; a++) {
+    k_fill_u64<<<(unsigned)((n2 - T + 255) / 256), 256, 0, st>>>(key[a].p, T, n2, ~0ull);
+    launches++;
+  }
+  if (key[1].p != key[0].p + n2 || key[2].p != key[1].p + n2 || !sort_keys(key[0].p, n2, st, &launches, 3, n2)) {
+    err = "bitonic sort launch failed";  // (the three arrays are consecutive arena pieces: one batched sort)
+    return false;
+  }
   for (int a = 0; a < 3; a++) {
-    if (n2 > T) {
-      k_fill_u64<<<(unsigned)((n2 - T + 255) / 256), 256, 0, st>>>(key[a].p, T, n2, ~0ull);
-      launches++;
-    }
-    if (!sort_keys(key[a].p, n2, st, &launches)) {
-      err = "bitonic sort launch failed";
-      return false;
-    }
     k_extract_index<<<blocksT, threads, 0, st>>>(key[a].p, T, ord[a].p);
     launches++;
   }
@@ -506,21 +854,7 @@ bool build_bvh_device(const float4* d_pos, const int4* d_vidx, int T, int M, con
   // 3. leaves, and the top-level join on the host
   k_leaf_tris<<<blocksT, threads, 0, st>>>(d_pos, d_vidx, slot_tri.p, T, d_tris);
   launches++;
-  std::vector<float> h_root_box(6 * (size_t)nonempty);
-  std::vector<int32_t> h_root_ref(nonempty);
-  out.slot_tri.resize(T);
-  BV(cudaMemcpyAsync(h_root_box.data(), root_box.p, sizeof(float) * h_root_box.size(), cudaMemcpyDeviceToHost, st));
-  BV(cudaMemcpyAsync(h_root_ref.data(), root_ref.p, sizeof(int32_t) * nonempty, cudaMemcpyDeviceToHost, st));
-  BV(cudaMemcpyAsync(out.slot_tri.data(), slot_tri.p, sizeof(int32_t) * (size_t)T, cudaMemcpyDeviceToHost, st));
-  BV(cudaStreamSynchronize(st));
-  BV(cudaGetLastError());
-  const size_t num_nodes = (size_t)(T - nonempty) + (size_t)std::max(nonempty - 1, 0);
-  out.nodes.assign(16 * std::max<size_t>((size_t)std::max(nonempty - 1, 1), 1), 0.f);  // host copy of the join only
-  build_top_level(nonempty, h_root_box.data(), h_root_ref.data(), pad, tree_depth(max_n), out);
-  if (nonempty > 1)
-    BV(cudaMemcpyAsync(d_nodes, out.nodes.data(), sizeof(float) * 16 * (size_t)(nonempty - 1), cudaMemcpyHostToDevice, st));
-  BV(cudaStreamSynchronize(st));
-  out.num_nodes = num_nodes;  // the caller fetches the nodes from the device on demand (rt_get_bvh)
+  if (!finish_build(T, nonempty, max_n, pad, root_box.p, root_ref.p, slot_tri.p, d_nodes, st, out, err)) return false;
   if (launches_out) *launches_out = launches;
   if (timing) {
     tick("leaves + top-level join");

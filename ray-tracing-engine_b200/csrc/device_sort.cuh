@@ -29,9 +29,11 @@ __device__ inline void cmp_swap(unsigned long long& x, unsigned long long& y, bo
     y = t;
   }
 }
+// Every kernel sorts gridDim.y independent arrays of the same length in one launch: array y starts at a + y * stride.
 // all steps (k, j) with k <= kSortTile: sorts every tile, alternating direction so that the merge can continue
-__global__ void __launch_bounds__(1024) k_bitonic_tile_sort(unsigned long long* a) {
+__global__ void __launch_bounds__(1024) k_bitonic_tile_sort(unsigned long long* a, long long stride) {
   __shared__ unsigned long long s[kSortTile];
+  a += (long long)blockIdx.y * stride;
   const long long base = (long long)blockIdx.x * kSortTile;
   s[threadIdx.x] = a[base + threadIdx.x];
   s[threadIdx.x + 1024] = a[base + threadIdx.x + 1024];
@@ -48,7 +50,8 @@ __global__ void __launch_bounds__(1024) k_bitonic_tile_sort(unsigned long long* 
   a[base + threadIdx.x + 1024] = s[threadIdx.x + 1024];
 }
 // one global step (k, j) with j >= kSortTile
-__global__ void k_bitonic_global(unsigned long long* a, long long n, long long k, long long j) {
+__global__ void k_bitonic_global(unsigned long long* a, long long stride, long long n, long long k, long long j) {
+  a += (long long)blockIdx.y * stride;
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n / 2) return;
   const long long i = 2 * t - (t & (j - 1));
@@ -60,8 +63,9 @@ __global__ void k_bitonic_global(unsigned long long* a, long long n, long long k
   }
 }
 // the steps j = kSortTile/2 .. 1 of merge size k > kSortTile, inside shared memory
-__global__ void __launch_bounds__(1024) k_bitonic_tile_merge(unsigned long long* a, long long k) {
+__global__ void __launch_bounds__(1024) k_bitonic_tile_merge(unsigned long long* a, long long stride, long long k) {
   __shared__ unsigned long long s[kSortTile];
+  a += (long long)blockIdx.y * stride;
   const long long base = (long long)blockIdx.x * kSortTile;
   s[threadIdx.x] = a[base + threadIdx.x];
   s[threadIdx.x + 1024] = a[base + threadIdx.x + 1024];
@@ -75,15 +79,17 @@ __global__ void __launch_bounds__(1024) k_bitonic_tile_merge(unsigned long long*
   a[base + threadIdx.x] = s[threadIdx.x];
   a[base + threadIdx.x + 1024] = s[threadIdx.x + 1024];
 }
-bool sort_keys(unsigned long long* keys, long long n2, cudaStream_t st, long long* launches) {
-  k_bitonic_tile_sort<<<(unsigned)(n2 / kSortTile), 1024, 0, st>>>(keys);
+// `batch` arrays of n2 words each, `stride` words apart, sorted by the same launches
+bool sort_keys(unsigned long long* keys, long long n2, cudaStream_t st, long long* launches, int batch = 1,
+               long long stride = 0) {
+  k_bitonic_tile_sort<<<dim3((unsigned)(n2 / kSortTile), batch), 1024, 0, st>>>(keys, stride);
   ++*launches;
   for (long long k = 2 * kSortTile; k <= n2; k <<= 1) {
     for (long long j = k >> 1; j >= kSortTile; j >>= 1) {
-      k_bitonic_global<<<(unsigned)((n2 / 2 + 255) / 256), 256, 0, st>>>(keys, n2, k, j);
+      k_bitonic_global<<<dim3((unsigned)((n2 / 2 + 255) / 256), batch), 256, 0, st>>>(keys, stride, n2, k, j);
       ++*launches;
     }
-    k_bitonic_tile_merge<<<(unsigned)(n2 / kSortTile), 1024, 0, st>>>(keys, k);
+    k_bitonic_tile_merge<<<dim3((unsigned)(n2 / kSortTile), batch), 1024, 0, st>>>(keys, stride, k);
     ++*launches;
   }
   return cudaGetLastError() == cudaSuccess;

@@ -235,15 +235,17 @@ bool build_kdtree_device(const float* d_photons7, int n, float4* d_kd_pos, float
   }
   k_kd_keys<<<blocks, threads, 0, st>>>(d_photons7, n, key[0], key[1], key[2], seg);
   launches++;
+  for (int a = 0; a < 3 && n2 > n; a++) {
+    k_kd_fill<<<(unsigned)((n2 - n + 255) / 256), 256, 0, st>>>(key[a], n, n2);
+    launches++;
+  }
+  // the three key arrays are consecutive pieces of the arena (n2 * 8 bytes is a multiple of its 256-byte granule): one
+  // batched sort, a third of the launches
+  if (key[1] != key[0] + n2 || key[2] != key[1] + n2 || !sort_keys(key[0], n2, st, &launches, 3, n2)) {
+    err = "bitonic sort launch failed";
+    return false;
+  }
   for (int a = 0; a < 3; a++) {
-    if (n2 > n) {
-      k_kd_fill<<<(unsigned)((n2 - n + 255) / 256), 256, 0, st>>>(key[a], n, n2);
-      launches++;
-    }
-    if (!sort_keys(key[a], n2, st, &launches)) {
-      err = "bitonic sort launch failed";
-      return false;
-    }
     k_kd_extract<<<blocks, threads, 0, st>>>(key[a], n, ord[a]);
     launches++;
   }

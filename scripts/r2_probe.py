@@ -100,3 +100,18 @@ if "e2e" in what:  # where the host side of one user-facing cfg2 call goes (benc
         for key in ("create_ms", "bvh_build_ms", "device_ms"):
             acc[key] = acc.get(key, 0.0) + st[key] / n_it
     print(json.dumps(dict(probe="e2e_phases", **{k: round(v, 3) for k, v in acc.items()})), flush=True)
+if "bvh" in what:  # BVH build at 11 666 triangles: host / device per-level launches / device one CTA per mesh
+    for label, env in (("host", {"RT_BVH_BUILD": "host"}), ("device, per-level launches", {"RT_BVH_BUILD": "gpu", "RT_BVH_SMALL": "0"}),
+                       ("device, one CTA per mesh", {"RT_BVH_BUILD": "gpu", "RT_BVH_SMALL": "1"})):
+        os.environ.update(env)
+        best_b, best_c = 1e9, 1e9
+        for _ in range(8):
+            r = rt.Renderer(ex, 1, 1, seed=1)
+            st = r.stats()
+            best_b, best_c = min(best_b, st["bvh_build_ms"]), min(best_c, st["create_ms"])
+            launches = st["kernel_launches"]
+            r.close()
+        print(json.dumps(dict(probe="bvh_build", builder=label, triangles=ex.T, bvh_build_ms=round(best_b, 3),
+                              create_ms=round(best_c, 3), launches=launches)), flush=True)
+        for k in env:
+            os.environ.pop(k)

@@ -404,12 +404,15 @@ def test_progressive_updates_match_the_per_pass_composite(rt):
 
 
 # ----------------------------------------------------------------------------- device BVH build
+@pytest.mark.parametrize("small", ["1", "0"])
 @pytest.mark.parametrize("name", ["stock", "lowres", "example"])
-def test_device_bvh_build_follows_the_policy_and_traces_identically(rt, gold, name, monkeypatch):
+def test_device_bvh_build_follows_the_policy_and_traces_identically(rt, gold, name, small, monkeypatch):
     """csrc/bvh_build.cu: the level-synchronous GPU build obeys the same split-policy checker as the host builder
     (tests/test_host.py), has the same shape (node count, depth), and tracing through it returns the reference's
-    golden hits bit for bit."""
+    golden hits bit for bit.  Both device paths: one CTA per mesh (meshes up to 16 384 triangles, the default for these
+    scenes) and the per-level launches (RT_BVH_SMALL=0, what million-triangle meshes use)."""
     from test_host import _check_bvh_policy
+    monkeypatch.setenv("RT_BVH_SMALL", small)
     scene = rt.Scene.load(scene_path(name))
     monkeypatch.setenv("RT_BVH_BUILD", "host")
     rh = rt.Renderer(scene, 1, 0, seed=SEED)
