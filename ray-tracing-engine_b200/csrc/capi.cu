@@ -107,6 +107,9 @@ struct rt_ctx {
   int knn_scratch_threads = 0;
   int knn_gather = 0;  // RT_KNN_GATHER=1: the photon queries run in the persistent gather kernel instead of inside k_shade
   int sort_seg0 = 1;   // RT_SORT_SEG0=0: the photon gather of segment 0 keeps the pixel-tile order of the primary hits
+  int tile_rounds = 8;  // RT_SHADE_TILE_ROUNDS=r (power of two): the photon k_shade orders each tile of r * 128 slots by fine Morton code
+  int sort_bits = -1;  // RT_SORT_BITS=0|5|6|7: Morton cells per axis = 2^bits (0: the 32^3 shared-memory counting sort);
+                       // default: 6 with a photon map (k-NN queries gain more from neighbours than the finer sort costs), else 0
   int sort_segs = -1;  // RT_SORT_SEGS=mask: which segments are Morton-binned (default: 1 and 2, plus 0 with a photon map)
   int own_tri = 0;  // RT_OWN_TRI=1: k_shade pre-tests a shadow ray against the triangle it starts on (measured: no gain)
   DevBuf<unsigned char> d_occ;
@@ -269,7 +272,8 @@ int ensure_work(rt_ctx* c, size_t paths, bool path_mode, int nl) {
   if (path_mode || c->params.num_photons > 0) {
     CU(c->d_perm.ensure(paths));
     CU(c->d_sorted.ensure(2 * paths));
-    CU(c->d_sort_hist.ensure(kSortBuckets + 2));
+    const bool fine = c->sort_bits > 0 || (c->sort_bits < 0 && c->params.num_photons > 0);
+    CU(c->d_sort_hist.ensure(fine ? (size_t)kSortFineMax + 2 + kSortFineTiles : (size_t)kSortBuckets + 2));
   }
   CU(c->d_qcount.ensure(kQNum));
   CU(c->d_counters.ensure(kCntNum));
@@ -345,9 +349,20 @@ void fill_args(rt_ctx* c, RenderArgs& a, const int* pix_map, int npix, bool use_
   a.sort_hist = c->d_sort_hist.p;
   a.sorted = c->d_sorted.p;
   a.sort_lo = c->bounds_lo;
-  a.sort_inv_cell = make_float3(kSortGrid / std::max(c->bounds_hi.x - c->bounds_lo.x, 1e-20f),
-                                kSortGrid / std::max(c->bounds_hi.y - c->bounds_lo.y, 1e-20f),
-                                kSortGrid / std::max(c->bounds_hi.z - c->bounds_lo.z, 1e-20f));
+  a.sort_bits = c->sort_bits >= 0 ? c->sort_bits : (use_photons ? 6 : 0);
+  // the tile sort borrows the shared memory of the queries it precedes (8 bytes per slot of a tile; tiles are powers
+  // of two for the bitonic network) and parks its order in the perm array
+  a.tile_rounds = 0;
+  if (use_photons && c->tile_rounds > 1 && a.knn_out == nullptr && a.perm != nullptr) {
+    int rounds = 1;
+    while (2 * rounds <= c->tile_rounds && knn_smem_bytes(p.k, c->kd_height + 1) >= (size_t)2 * rounds * kBlock * 8) rounds *= 2;
+    a.tile_rounds = rounds > 1 ? rounds : 0;
+  }
+  const float cells = a.sort_bits > 0 ? (float)(1 << a.sort_bits) : (float)kSortGrid;
+  a.sort_inv_cell = make_float3(cells / std::max(c->bounds_hi.x - c->bounds_lo.x, 1e-20f),
+                                cells / std::max(c->bounds_hi.y - c->bounds_lo.y, 1e-20f),
+                                cells / std::max(c->bounds_hi.z - c->bounds_lo.z, 1e-20f));
+  a.sort_key_scale = 1024.f / cells;
   a.q_count = c->d_qcount.p;
   a.counters = c->d_counters.p;
 }
@@ -820,6 +835,8 @@ int rt_create(const rt_scene* s, const rt_params* p, int device, rt_ctx** out) {
   if (const char* e = getenv("RT_KNN_GATHER")) c->knn_gather = atoi(e) != 0;
   if (const char* e = getenv("RT_SORT_SEG0")) c->sort_seg0 = atoi(e) != 0;
   if (const char* e = getenv("RT_SORT_SEGS")) c->sort_segs = atoi(e) & 7;
+  if (const char* e = getenv("RT_SHADE_TILE_ROUNDS")) c->tile_rounds = std::min(std::max(atoi(e), 0), 64);
+  if (const char* e = getenv("RT_SORT_BITS")) c->sort_bits = std::min(std::max(atoi(e), 0), 7);
   if (!(extent < 1e8f)) {  // keeps lo * safe_inv(d) finite in the slab test (rt_device.cuh)
     rt_destroy(c);
     return fail(RT_ERR_INVALID, "scene coordinates must be finite and smaller than 1e8");

@@ -649,7 +649,143 @@ __global__ void __launch_bounds__(kSortThreads) k_sort_scatter(const RenderArgs 
     A.sorted[2 * (size_t)dst + 1] = make_float4(d.x, d.y, d.z, o.w);
   }
 }
+// ---- the same binning with 2^bits cells per axis (bits = 6, 7: 262 144 / 2 097 152 Morton cells) ----------------------
+// Finer cells put rays that start almost at the same point into the same warp (their traversals -- and their k-NN
+// queries -- then run in lock-step), but the counters no longer fit in shared memory: the histogram lives in global
+// memory (L2-resident, <= 8 MB), both passes are plain grid-stride kernels, and only the miss bucket -- the one address
+// every lane of a warp can want -- is warp-aggregated.  The scan is two kernels (per-block exclusive scan + block
+// sums, scan of the block sums); the scatter adds the block offset itself.
+RT_DI unsigned morton3_10bit(unsigned x, unsigned y, unsigned z) {
+  auto spread = [](unsigned v) {  // 10 bits -> every third bit
+    v = (v | (v << 16)) & 0x030000FFu;
+    v = (v | (v << 8)) & 0x0300F00Fu;
+    v = (v | (v << 4)) & 0x030C30C3u;
+    v = (v | (v << 2)) & 0x09249249u;
+    return v;
+  };
+  return spread(x) | (spread(y) << 1) | (spread(z) << 2);
+}
+RT_DI unsigned sort_key_fine(const RenderArgs& A, int seg, unsigned i) {
+  const float4 hr = A.hit[i];
+  if (__float_as_int(hr.w) < 0) return 1u << (3 * A.sort_bits);  // misses last
+  const float4 o = A.ray_o[seg & 1][i], d = A.ray_d[seg & 1][i];
+  const float px = fmaf(hr.x, d.x, o.x), py = fmaf(hr.x, d.y, o.y), pz = fmaf(hr.x, d.z, o.z);  // ~hit point
+  const int g1 = (1 << A.sort_bits) - 1;
+  const int cx = min(max((int)((px - A.sort_lo.x) * A.sort_inv_cell.x), 0), g1);
+  const int cy = min(max((int)((py - A.sort_lo.y) * A.sort_inv_cell.y), 0), g1);
+  const int cz = min(max((int)((pz - A.sort_lo.z) * A.sort_inv_cell.z), 0), g1);
+  return morton3_10bit((unsigned)cx, (unsigned)cy, (unsigned)cz);
+}
+constexpr int kScanThreads = 1024, kScanPer = 8, kScanTile = kScanThreads * kScanPer;
+__global__ void k_sort_count_fine(const RenderArgs A, const int seg) {
+  const unsigned n = seg == 0 ? (unsigned)A.npix * (unsigned)A.nsamp : A.q_count[kQHits0 + seg - 1];
+  const unsigned miss = 1u << (3 * A.sort_bits);
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const unsigned key = sort_key_fine(A, seg, i);
+    A.perm[i] = key;  // the scatter pass reads 4 bytes per ray instead of recomputing the key from 48
+    if (key == miss) {
+      const unsigned m = __activemask();
+      if ((threadIdx.x & 31) == __ffs(m) - 1) atomicAdd(A.sort_hist + miss, (unsigned)__popc(m));
+    } else {
+      atomicAdd(A.sort_hist + key, 1u);
+    }
+  }
+}
+// in place: hist[i] <- exclusive prefix inside its tile of kScanTile counters; tile_sum[tile] <- the tile's total
+__global__ void __launch_bounds__(kScanThreads) k_sort_scan_tiles(unsigned* hist, unsigned n, unsigned* tile_sum) {
+  __shared__ unsigned s_warp[kScanThreads / 32];
+  const unsigned first = blockIdx.x * kScanTile + threadIdx.x * kScanPer;
+  unsigned v[kScanPer], sum = 0;
+#pragma unroll
+  for (int k = 0; k < kScanPer; k++) {
+    v[k] = first + k < n ? hist[first + k] : 0u;
+    sum += v[k];
+  }
+  unsigned incl = sum;
+  for (int off = 1; off < 32; off <<= 1) {
+    const unsigned o = __shfl_up_sync(0xffffffffu, incl, off);
+    if ((threadIdx.x & 31) >= off) incl += o;
+  }
+  if ((threadIdx.x & 31) == 31) s_warp[threadIdx.x >> 5] = incl;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    const unsigned w = s_warp[threadIdx.x];
+    unsigned wi = w;
+    for (int off = 1; off < 32; off <<= 1) {
+      const unsigned o = __shfl_up_sync(0xffffffffu, wi, off);
+      if (threadIdx.x >= off) wi += o;
+    }
+    s_warp[threadIdx.x] = wi - w;
+    if (threadIdx.x == 31) tile_sum[blockIdx.x] = wi;
+  }
+  __syncthreads();
+  unsigned run = s_warp[threadIdx.x >> 5] + incl - sum;
+#pragma unroll
+  for (int k = 0; k < kScanPer; k++) {
+    if (first + k < n) hist[first + k] = run;
+    run += v[k];
+  }
+}
+__global__ void __launch_bounds__(kScanThreads) k_sort_scan_sums(unsigned* tile_sum, int tiles) {  // tiles <= 1024
+  __shared__ unsigned s_warp[kScanThreads / 32];
+  const unsigned v = (int)threadIdx.x < tiles ? tile_sum[threadIdx.x] : 0u;
+  unsigned incl = v;
+  for (int off = 1; off < 32; off <<= 1) {
+    const unsigned o = __shfl_up_sync(0xffffffffu, incl, off);
+    if ((threadIdx.x & 31) >= off) incl += o;
+  }
+  if ((threadIdx.x & 31) == 31) s_warp[threadIdx.x >> 5] = incl;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    const unsigned w = s_warp[threadIdx.x];
+    unsigned wi = w;
+    for (int off = 1; off < 32; off <<= 1) {
+      const unsigned o = __shfl_up_sync(0xffffffffu, wi, off);
+      if (threadIdx.x >= off) wi += o;
+    }
+    s_warp[threadIdx.x] = wi - w;
+  }
+  __syncthreads();
+  if ((int)threadIdx.x < tiles) tile_sum[threadIdx.x] = s_warp[threadIdx.x >> 5] + incl - v;
+}
+__global__ void k_sort_scatter_fine(const RenderArgs A, const int seg, const unsigned* __restrict__ tile_sum) {
+  const unsigned n = seg == 0 ? (unsigned)A.npix * (unsigned)A.nsamp : A.q_count[kQHits0 + seg - 1];
+  const unsigned miss = 1u << (3 * A.sort_bits);
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const unsigned key = A.perm[i];
+    unsigned dst;
+    if (key == miss) {
+      const unsigned m = __activemask();
+      const int leader = __ffs(m) - 1, lane = threadIdx.x & 31;
+      unsigned base = 0;
+      if (lane == leader) base = atomicAdd(A.sort_hist + miss, (unsigned)__popc(m));
+      base = __shfl_sync(m, base, leader);
+      dst = base + __popc(m & ((1u << lane) - 1u));
+    } else {
+      dst = atomicAdd(A.sort_hist + key, 1u);
+    }
+    dst += tile_sum[key / kScanTile];
+    const float4 o = A.ray_o[seg & 1][i], d = A.ray_d[seg & 1][i];
+    A.sorted[2 * (size_t)dst] = A.hit[i];  // one full 32-byte sector per ray
+    A.sorted[2 * (size_t)dst + 1] = make_float4(d.x, d.y, d.z, o.w);
+  }
+}
+static void launch_sort_hits_fine(const RenderArgs& a, int seg, cudaStream_t st) {
+  const unsigned n = (1u << (3 * a.sort_bits)) + 1;  // cells + the miss bucket
+  const int tiles = (int)((n + kScanTile - 1) / kScanTile);
+  unsigned* tile_sum = a.sort_hist + kSortFineMax + 2;
+  cudaMemsetAsync(a.sort_hist, 0, (size_t)n * sizeof(unsigned), st);
+  const int ctas = (a.num_sms > 0 ? a.num_sms : 148) * 8;
+  k_sort_count_fine<<<ctas, 256, 0, st>>>(a, seg);
+  k_sort_scan_tiles<<<tiles, kScanThreads, 0, st>>>(a.sort_hist, n, tile_sum);
+  k_sort_scan_sums<<<1, kScanThreads, 0, st>>>(tile_sum, tiles);
+  k_sort_scatter_fine<<<ctas, 256, 0, st>>>(a, seg, tile_sum);
+}
 void launch_sort_hits(const RenderArgs& a, int seg, cudaStream_t st) {
+  if (a.sort_bits > 0) {
+    launch_sort_hits_fine(a, seg, st);
+    return;
+  }
   static bool configured = false;
   if (!configured) {
     cudaFuncSetAttribute(k_sort_count, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSortSmem);
@@ -848,8 +984,71 @@ __global__ void __launch_bounds__(kBlock, PHOTON ? 6 : RT_SHADE_MINB) k_shade(co
   unsigned long long n_visits = 0;
 
   const bool permuted = ((A.sort_mask >> seg) & 1) && A.perm != nullptr;
-  for (unsigned base = blockIdx.x * kBlock; base < n; base += gridDim.x * kBlock) {
-    const unsigned slot = base + threadIdx.x;
+  // PHOTON: a CTA takes tile_rounds * kBlock consecutive slots at a time and first orders them by the 30-bit Morton
+  // code of their hit points (bitonic sort in the shared memory the queries use afterwards; the order is parked in
+  // this tile's own piece of the perm array, idle at this point), so that the 32 queries of a warp start a few
+  // millimetres apart and walk the photon tree in lock-step.  The global binning (k_sort_*) makes consecutive slots
+  // neighbours at the scale of its cells; this refines it for ~400 instructions per query.  The order only decides
+  // which lane runs which query: results do not depend on it.
+  const int R = PHOTON ? max(A.tile_rounds, 1) : 1;
+  const unsigned TILE = (unsigned)kBlock * (unsigned)R;
+  const bool tile_sort = PHOTON && A.tile_rounds > 1;
+  // tiles are handed out by a cursor (the any-hit fetch counter, idle in photon mode): a tile of 1024 queries is ~4 % of a
+  // CTA's share of a segment, and static round-robin left the SMs waiting for the CTAs with the expensive tiles
+  __shared__ unsigned s_tile;
+  unsigned* tile_cursor = A.q_count + kQFetchAny0 + seg;
+  for (unsigned tile = blockIdx.x * TILE;; tile += gridDim.x * TILE) {
+   if (PHOTON && tile_sort) {
+     if (threadIdx.x == 0) s_tile = atomicAdd(tile_cursor, 1u);
+     __syncthreads();
+     tile = s_tile * TILE;  // (the previous tile's closing barrier keeps s_tile stable until everyone has read it)
+   }
+   if (tile >= n) break;
+   if (PHOTON && tile_sort) {
+     unsigned long long* sb = s_knn;
+     for (int r = 0; r < R; r++) {
+       const unsigned li = (unsigned)r * kBlock + threadIdx.x, slot = tile + li;
+       unsigned key = 0xffffffffu;
+       if (slot < n) {
+         const float4 hr = permuted ? A.sorted[2 * (size_t)slot] : A.hit[slot];
+         HitRec h;
+         h.t = hr.x, h.u = hr.y, h.v = hr.z, h.gid = __float_as_int(hr.w);
+         key = 0xfffffffeu;
+         if (h.gid >= 0) {
+           const float3 P = hit_point(S, h);
+           const float sc10 = A.sort_key_scale;
+           const int cx = min(max((int)((P.x - A.sort_lo.x) * A.sort_inv_cell.x * sc10), 0), 1023);
+           const int cy = min(max((int)((P.y - A.sort_lo.y) * A.sort_inv_cell.y * sc10), 0), 1023);
+           const int cz = min(max((int)((P.z - A.sort_lo.z) * A.sort_inv_cell.z * sc10), 0), 1023);
+           key = morton3_10bit((unsigned)cx, (unsigned)cy, (unsigned)cz);
+         }
+       }
+       sb[li] = ((unsigned long long)key << 32) | li;
+     }
+     __syncthreads();
+     for (unsigned k2 = 2; k2 <= TILE; k2 <<= 1)
+       for (unsigned j2 = k2 >> 1; j2 > 0; j2 >>= 1) {
+         for (unsigned q = threadIdx.x; q < TILE / 2; q += kBlock) {
+           const unsigned i = 2 * q - (q & (j2 - 1));
+           const unsigned long long x = sb[i], y = sb[i + j2];
+           if ((x > y) == ((i & k2) == 0)) {
+             sb[i] = y;
+             sb[i + j2] = x;
+           }
+         }
+         __syncthreads();
+       }
+     for (int r = 0; r < R; r++) {
+       const unsigned li = (unsigned)r * kBlock + threadIdx.x;
+       if (tile + li < n) A.perm[tile + li] = (unsigned)sb[li];  // low word: the tile-local index
+     }
+     __syncthreads();
+   }
+   for (int r = 0; r < R; r++) {
+    unsigned li = (unsigned)r * kBlock + threadIdx.x;
+    // (written above by this very thread; slots past n sort last, so the first n - tile entries are the valid ones)
+    if (PHOTON && tile_sort && tile + li < n) li = A.perm[tile + li];
+    const unsigned slot = tile + li;
     bool found = false;
     unsigned p = 0;
     float3 d = f3(0, 0, 0);
@@ -953,6 +1152,8 @@ __global__ void __launch_bounds__(kBlock, PHOTON ? 6 : RT_SHADE_MINB) k_shade(co
         qd_out[j] = make_float4(nd.x, nd.y, nd.z, 0.f);
       }
     }
+   }
+   if (PHOTON && tile_sort) __syncthreads();  // the next tile's sort reuses the queries' shared memory
   }
   for (int off = 16; off > 0; off >>= 1) {
     n_hit += __shfl_xor_sync(kFull, n_hit, off);
@@ -990,12 +1191,17 @@ void launch_shade(const RenderArgs& a, int seg, int grid, cudaStream_t st) {
     if (a.num_sms > 0) grid = grid < a.num_sms * occ ? grid : a.num_sms * occ;
     const bool g = a.k > kKnnSharedMaxK;
     if (g && (size_t)grid * kBlock > (size_t)a.knn_scratch_stride) grid = a.knn_scratch_stride / kBlock;
+    // a tile is a CTA's unit of work: keep at least four of them per resident CTA, or the tail (and, for a single
+    // sample per pixel, half of the SMs) idles -- -m 0 -N 1 -p 500000 -k 50 went from 3.7 to 9.0 ms with 1024-slot tiles
+    RenderArgs b = a;
+    const long long slots = (long long)a.npix * a.nsamp;
+    while (b.tile_rounds > 1 && slots < 4LL * grid * kBlock * b.tile_rounds) b.tile_rounds /= 2;
     if (a.mode == 0) {
-      if (g) k_shade<0, true, 0, true><<<grid, kBlock, sm, st>>>(a, seg);
-      else k_shade<0, true, 0, false><<<grid, kBlock, sm, st>>>(a, seg);
+      if (g) k_shade<0, true, 0, true><<<grid, kBlock, sm, st>>>(b, seg);
+      else k_shade<0, true, 0, false><<<grid, kBlock, sm, st>>>(b, seg);
     } else {
-      if (g) k_shade<1, true, 0, true><<<grid, kBlock, sm, st>>>(a, seg);
-      else k_shade<1, true, 0, false><<<grid, kBlock, sm, st>>>(a, seg);
+      if (g) k_shade<1, true, 0, true><<<grid, kBlock, sm, st>>>(b, seg);
+      else k_shade<1, true, 0, false><<<grid, kBlock, sm, st>>>(b, seg);
     }
     return;
   }

@@ -79,9 +79,13 @@ struct RenderArgs {
                              // holds the Morton cell of every ray between k_sort_count and k_sort_scatter
   float4* sorted;            // sorted payload, 32 B per ray: [2k] hit record, [2k+1] direction (xyz) + path id (w)
                              // of the ray processed k-th by k_shade
-  unsigned int* sort_hist;   // kSortBuckets + 2 counters (bucket kSortBuckets = misses)
+  unsigned int* sort_hist;   // kSortBuckets + 2 counters (bucket kSortBuckets = misses); with sort_bits > 0:
+                             // kSortFineMax + 2 counters followed by kSortFineTiles tile sums of the scan
+  int sort_bits;             // 0: 32^3 cells counted in shared memory; 6 / 7: (2^bits)^3 cells, histogram in global memory
+  int tile_rounds;           // photon k_shade: > 1: order every tile of tile_rounds * kBlock slots by fine Morton code
+  float sort_key_scale;      // 1024 / cells per axis: sort_inv_cell * this maps a coordinate to the 10-bit fine grid
   float3 sort_lo;            // scene bounds
-  float3 sort_inv_cell;      // kSortGrid / extent per axis
+  float3 sort_inv_cell;      // cells per axis / extent per axis
   unsigned int* q_count;
   unsigned long long* counters;
   // photon gather by the persistent k_knn_gather (reference-exact flavours): per ray slot of the segment
@@ -98,6 +102,8 @@ constexpr int kKnnSharedMaxK = 64;  // up to here the candidate rows fit in shar
 #endif
 constexpr int kSortGrid = RT_SORT_GRID;                          // cells per axis (16: trace +0.3 ms, binning -0.3 ms: same frame time)
 constexpr int kSortBuckets = kSortGrid * kSortGrid * kSortGrid;  // 32768 Morton cells (+1 bucket for misses)
+constexpr int kSortFineMax = 1 << 21;                            // cells of the finest grid (128 per axis)
+constexpr int kSortFineTiles = 1024;                             // >= tiles of 8 192 counters the fine scan can need
 void launch_sort_hits(const RenderArgs& a, int seg, cudaStream_t st);  // fills a.perm for segment seg
 void launch_raygen(const RenderArgs& a, cudaStream_t st);
 void launch_trace_nearest(const RenderArgs& a, int seg, int grid_ctas, cudaStream_t st);
@@ -126,6 +132,7 @@ void launch_composite(const float4* acc_rgb, const int* acc_cnt, const int* pix_
 void launch_trace_rays(const DScene& s, const float4* ro, const float4* rd, unsigned n, float4* hits,
                        unsigned char* occluded, int any, int brute, int stack_depth, unsigned* fetch_counter,
                        int grid_ctas, cudaStream_t st);
+size_t knn_smem_bytes(int k, int kd_frames);                   // dynamic shared memory of the kernels that run the k-NN
 int shade_photon_ctas_per_sm(int mode, int k, int kd_frames);  // resident CTAs of the k-NN shade kernel
 // persistent k-nearest-photon gather of a segment's hit points (fills a.knn_out); grid = SMs x knn_gather_ctas_per_sm
 void launch_knn_gather(const RenderArgs& a, int seg, cudaStream_t st);

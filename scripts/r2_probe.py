@@ -115,3 +115,28 @@ if "bvh" in what:  # BVH build at 11 666 triangles: host / device per-level laun
                               create_ms=round(best_c, 3), launches=launches)), flush=True)
         for k in env:
             os.environ.pop(k)
+if "sortbits" in what:  # Morton cells per axis for the binning of hit points: 32 (shared-memory counters) vs 2^bits (global)
+    for photons in (0, 50000):
+        for bits in ("0", "5", "6", "7"):
+            os.environ["RT_SORT_BITS"] = bits
+            r = rt.Renderer(ex, 128, 1, None, photons, 10, seed=1)
+            if photons:
+                r.build_photon_map()
+            ms, st, chk, hits = frames(r, 2)
+            print(json.dumps(dict(probe="sort_bits", photons=photons, RT_SORT_BITS=bits, frame_ms=round(ms, 3),
+                                  kernel_ms={k: round(x, 3) for k, x in st["kernel_ms"].items()}, checksum=chk, hits=hits)), flush=True)
+            r.close()
+    os.environ.pop("RT_SORT_BITS")
+if "tilesort" in what:  # photon k_shade: tile-local Morton ordering of the queries x global binning granularity
+    for bits in os.environ.get("PROBE_BITS", "0,6").split(","):
+        for ts in os.environ.get("PROBE_ROUNDS", "0,4,8,16,32").split(","):
+            os.environ["RT_SORT_BITS"] = bits
+            os.environ["RT_SHADE_TILE_ROUNDS"] = ts
+            r = rt.Renderer(ex, 128, 1, None, 50000, 10, seed=1)
+            r.build_photon_map()
+            ms, st, chk, hits = frames(r, 2)
+            print(json.dumps(dict(probe="tile_sort", RT_SORT_BITS=bits, RT_SHADE_TILE_ROUNDS=ts, frame_ms=round(ms, 3),
+                                  kernel_ms={k: round(x, 3) for k, x in st["kernel_ms"].items() if x}, checksum=chk, hits=hits,
+                                  kd_visits=st["kd_visits"])), flush=True)
+            r.close()
+    os.environ.pop("RT_SORT_BITS"); os.environ.pop("RT_SHADE_TILE_ROUNDS")

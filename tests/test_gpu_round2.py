@@ -316,6 +316,30 @@ def test_persistent_gather_equals_the_inline_queries(rt, gold, monkeypatch):
         assert sta["kernel_count"]["gather"] > 0 and stb["kernel_count"]["gather"] == 0
 
 
+def test_query_order_switches_do_not_change_the_frame(rt, gold, monkeypatch):
+    """The order the k-NN queries are processed in -- Morton cells of the global binning (32^3 in shared memory, 64^3 or
+    128^3 with the histogram in global memory) and the per-tile fine ordering inside the photon k_shade -- only decides
+    which lane runs which query: sums, counters and the work counters are identical for every combination, for both
+    candidate structures, and in a plain path-traced frame as well."""
+    scene = rt.Scene.load(scene_path("stock"))
+    ph = gold("photons.npz")["list"]
+    for k, mode, photons in ((10, 1, 3000), (50, 0, 3000), (0, 1, 0)):
+        ref = None
+        for bits, rounds in (("0", "0"), ("0", "8"), ("6", "0"), ("6", "8"), ("7", "4"), ("5", "16")):
+            monkeypatch.setenv("RT_SORT_BITS", bits)
+            monkeypatch.setenv("RT_SHADE_TILE_ROUNDS", rounds)
+            r = rt.Renderer(scene, 6, mode, None, photons, k or 5, seed=4, width=420, height=300)
+            if photons:
+                r.set_photons(ph)
+            s, c = r.render_accumulate()
+            st = r.stats()
+            r.close()
+            cur = (s, c, st["knn_queries"], st["kd_visits"], st["rays"])
+            if ref is None:
+                ref = cur
+            assert beq(ref[0], cur[0]) and (ref[1] == cur[1]).all() and ref[2:] == cur[2:], (k, bits, rounds)
+
+
 def test_kernel_class_times_cover_the_device_time(rt):
     scene = rt.Scene.load(scene_path("example"))
     r = rt.Renderer(scene, 8, 1, seed=1, width=420, height=420)
