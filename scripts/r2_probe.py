@@ -140,3 +140,14 @@ if "tilesort" in what:  # photon k_shade: tile-local Morton ordering of the quer
                                   kd_visits=st["kd_visits"])), flush=True)
             r.close()
     os.environ.pop("RT_SORT_BITS"); os.environ.pop("RT_SHADE_TILE_ROUNDS")
+if "cfg5bits" in what:  # the 1.23 M-triangle scene (L2-latency-bound traversal): does finer binning of the bounce hits pay there?
+    import bench
+    sc5, W5, H5, N5, mode5, _, _, _ = bench.load_workload(rt, "cfg5", 0)
+    for bits in ("0", "6", "7"):
+        os.environ["RT_SORT_BITS"] = bits
+        r = rt.Renderer(sc5, 16, mode5, seed=1)
+        ms, st, chk, hits = frames(r, 2)
+        print(json.dumps(dict(probe="cfg5_sort_bits", RT_SORT_BITS=bits, N=16, frame_ms=round(ms, 3), grays=round(st["rays"] / ms / 1e6, 3),
+                              kernel_ms={k: round(x, 3) for k, x in st["kernel_ms"].items() if x}, checksum=chk, hits=hits)), flush=True)
+        r.close()
+    os.environ.pop("RT_SORT_BITS")
