@@ -854,7 +854,7 @@ size_t knn_smem_bytes(int k, int frames) {
 
 // ----------------------------------------------------------------------------------------------
 // k_knn_gather: the k-nearest-photon queries of a segment's hit points as their own persistent kernel.
-// ncu on the query inside k_shade (profiles/r2_knn_sass.txt): the traversal loop ran with 24 of 32 lanes (a warp's 32
+// ncu on the query inside k_shade (start of round 2; profiles/r2_cfg3_knn_seg0_sass_regions.txt is the shipped build): the traversal loop ran with 24 of 32 lanes (a warp's 32
 // queries take 60-140 node visits each and the warp waits for the longest), the candidate insertion with 13 and the
 // stack unwind with 7.  Here a query is a resumable state machine (KdQuery): every lane advances its own query by
 // one node per round, a lane whose query is complete writes its result -- the sum of the k incomeDirections in

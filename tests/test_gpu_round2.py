@@ -340,6 +340,45 @@ def test_query_order_switches_do_not_change_the_frame(rt, gold, monkeypatch):
             assert beq(ref[0], cur[0]) and (ref[1] == cur[1]).all() and ref[2:] == cur[2:], (k, bits, rounds)
 
 
+@pytest.mark.parametrize("sizes", [(1, 2, 3, 5, 127, 1000, 4097, 16384), (16385, 7, 1, 2500)])
+def test_device_bvh_builders_agree_on_random_meshes(rt, sizes, monkeypatch):
+    """Triangle soups with mesh sizes around every boundary of the device builders (single-triangle meshes, odd sizes, the
+    16 384-triangle limit of the cluster-per-mesh kernel and one triangle beyond it): the host builder, the per-level
+    launches and the cluster kernel produce the same nodes and the same leaf order, bit for bit; nearest hits through the
+    tree equal the O(T) scan."""
+    stock = rt.Scene.load(scene_path("stock"))
+    g = np.random.default_rng(11)
+    T = int(sum(sizes))
+    centre = g.uniform(-1, 1, size=(T, 1, 3))
+    pos = (centre + g.normal(size=(T, 3, 3)) * 0.02).astype(np.float32).reshape(-1, 3)
+    nrm = np.tile(np.float32([0, 0, 1]), (3 * T, 1))
+    tri = np.arange(3 * T, dtype=np.int32).reshape(T, 3)
+    off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
+    mats = np.tile(stock.mats.reshape(-1, 8)[:1], (len(sizes), 1))
+    scene = rt.Scene(pos, nrm, tri, off, (3 * off).astype(np.int32), mats, stock.lights, stock.cam, 32, 32, None)
+    built = {}
+    for name, env in (("host", {"RT_BVH_BUILD": "host"}), ("levels", {"RT_BVH_BUILD": "gpu", "RT_BVH_SMALL": "0"}),
+                      ("cluster", {"RT_BVH_BUILD": "gpu", "RT_BVH_SMALL": "1"})):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        r = rt.Renderer(scene, 1, 0, seed=1)
+        nodes, depth = r.bvh()
+        built[name] = (nodes.copy(), depth, r.bvh_slots().copy(), r.stats()["kernel_launches"])
+        if name == "cluster":
+            rays = np.concatenate([g.uniform(-1, 1, size=(4000, 3)), g.normal(size=(4000, 3))], 1).astype(np.float32)
+            a, b = r.rayTrace(rays), r.rayTrace(rays, brute_force=True)
+            assert (a["tri_index"] == b["tri_index"]).all() and beq(a["uvd"], b["uvd"]) and (a["tri_index"] >= 0).sum() > 100
+        r.close()
+    for name in ("levels", "cluster"):
+        assert built[name][1] == built["host"][1], name
+        assert (built[name][2] == built["host"][2]).all(), name
+        assert beq(built[name][0], built["host"][0]), name
+    if max(sizes) <= 16384:  # the cluster kernel ran: a dozen launches instead of seven per level
+        assert built["cluster"][3] < built["levels"][3] / 4
+    else:
+        assert built["cluster"][3] == built["levels"][3]
+
+
 def test_kernel_class_times_cover_the_device_time(rt):
     scene = rt.Scene.load(scene_path("example"))
     r = rt.Renderer(scene, 8, 1, seed=1, width=420, height=420)
