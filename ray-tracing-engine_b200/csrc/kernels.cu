@@ -967,6 +967,52 @@ void launch_knn_gather(const RenderArgs& a, int seg, cudaStream_t st) {
   }
 }
 
+// Photon k_shade: order the slots [tile, tile + R * kBlock) of a segment by the 30-bit Morton code of their hit points --
+// bitonic sort of (code << 32 | tile-local index) in `sb` (the shared memory the queries use afterwards) -- and park
+// the order in this tile's own piece of the perm array (idle between k_sort_scatter and the next k_sort_count).
+// Slots past n sort last, misses just before them.
+RT_DI void shade_tile_order(const RenderArgs& A, unsigned tile, unsigned n, int R, bool permuted, unsigned long long* sb) {
+  const DScene& S = A.scene;
+  const unsigned TILE = (unsigned)kBlock * (unsigned)R;
+  for (int r = 0; r < R; r++) {
+    const unsigned li = (unsigned)r * kBlock + threadIdx.x, slot = tile + li;
+    unsigned key = 0xffffffffu;
+    if (slot < n) {
+      const float4 hr = permuted ? A.sorted[2 * (size_t)slot] : A.hit[slot];
+      HitRec h;
+      h.t = hr.x, h.u = hr.y, h.v = hr.z, h.gid = __float_as_int(hr.w);
+      key = 0xfffffffeu;
+      if (h.gid >= 0) {
+        const float3 P = hit_point(S, h);
+        const float sc10 = A.sort_key_scale;
+        const int cx = min(max((int)((P.x - A.sort_lo.x) * A.sort_inv_cell.x * sc10), 0), 1023);
+        const int cy = min(max((int)((P.y - A.sort_lo.y) * A.sort_inv_cell.y * sc10), 0), 1023);
+        const int cz = min(max((int)((P.z - A.sort_lo.z) * A.sort_inv_cell.z * sc10), 0), 1023);
+        key = morton3_10bit((unsigned)cx, (unsigned)cy, (unsigned)cz);
+      }
+    }
+    sb[li] = ((unsigned long long)key << 32) | li;
+  }
+  __syncthreads();
+  for (unsigned k2 = 2; k2 <= TILE; k2 <<= 1)
+    for (unsigned j2 = k2 >> 1; j2 > 0; j2 >>= 1) {
+      for (unsigned q = threadIdx.x; q < TILE / 2; q += kBlock) {
+        const unsigned i = 2 * q - (q & (j2 - 1));
+        const unsigned long long x = sb[i], y = sb[i + j2];
+        if ((x > y) == ((i & k2) == 0)) {
+          sb[i] = y;
+          sb[i + j2] = x;
+        }
+      }
+      __syncthreads();
+    }
+  for (int r = 0; r < R; r++) {
+    const unsigned li = (unsigned)r * kBlock + threadIdx.x;
+    if (tile + li < n) A.perm[tile + li] = (unsigned)sb[li];  // low word: the tile-local index
+  }
+  __syncthreads();
+}
+
 // NLT: 3 = the stock three-light loop unrolled (Main.cpp:101-124), 0 = any light count (Renderer.cpp:49).
 // GSC (PHOTON only): k-NN candidates in global memory (k > kKnnSharedMaxK).
 template <int MODE, bool PHOTON, int NLT, bool GSC>
@@ -998,162 +1044,123 @@ __global__ void __launch_bounds__(kBlock, PHOTON ? 6 : RT_SHADE_MINB) k_shade(co
   __shared__ unsigned s_tile;
   unsigned* tile_cursor = A.q_count + kQFetchAny0 + seg;
   for (unsigned tile = blockIdx.x * TILE;; tile += gridDim.x * TILE) {
-   if (PHOTON && tile_sort) {
-     if (threadIdx.x == 0) s_tile = atomicAdd(tile_cursor, 1u);
-     __syncthreads();
-     tile = s_tile * TILE;  // (the previous tile's closing barrier keeps s_tile stable until everyone has read it)
-   }
-   if (tile >= n) break;
-   if (PHOTON && tile_sort) {
-     unsigned long long* sb = s_knn;
-     for (int r = 0; r < R; r++) {
-       const unsigned li = (unsigned)r * kBlock + threadIdx.x, slot = tile + li;
-       unsigned key = 0xffffffffu;
-       if (slot < n) {
-         const float4 hr = permuted ? A.sorted[2 * (size_t)slot] : A.hit[slot];
-         HitRec h;
-         h.t = hr.x, h.u = hr.y, h.v = hr.z, h.gid = __float_as_int(hr.w);
-         key = 0xfffffffeu;
-         if (h.gid >= 0) {
-           const float3 P = hit_point(S, h);
-           const float sc10 = A.sort_key_scale;
-           const int cx = min(max((int)((P.x - A.sort_lo.x) * A.sort_inv_cell.x * sc10), 0), 1023);
-           const int cy = min(max((int)((P.y - A.sort_lo.y) * A.sort_inv_cell.y * sc10), 0), 1023);
-           const int cz = min(max((int)((P.z - A.sort_lo.z) * A.sort_inv_cell.z * sc10), 0), 1023);
-           key = morton3_10bit((unsigned)cx, (unsigned)cy, (unsigned)cz);
-         }
-       }
-       sb[li] = ((unsigned long long)key << 32) | li;
-     }
-     __syncthreads();
-     for (unsigned k2 = 2; k2 <= TILE; k2 <<= 1)
-       for (unsigned j2 = k2 >> 1; j2 > 0; j2 >>= 1) {
-         for (unsigned q = threadIdx.x; q < TILE / 2; q += kBlock) {
-           const unsigned i = 2 * q - (q & (j2 - 1));
-           const unsigned long long x = sb[i], y = sb[i + j2];
-           if ((x > y) == ((i & k2) == 0)) {
-             sb[i] = y;
-             sb[i + j2] = x;
-           }
-         }
-         __syncthreads();
-       }
-     for (int r = 0; r < R; r++) {
-       const unsigned li = (unsigned)r * kBlock + threadIdx.x;
-       if (tile + li < n) A.perm[tile + li] = (unsigned)sb[li];  // low word: the tile-local index
-     }
-     __syncthreads();
-   }
-   for (int r = 0; r < R; r++) {
-    unsigned li = (unsigned)r * kBlock + threadIdx.x;
-    // (written above by this very thread; slots past n sort last, so the first n - tile entries are the valid ones)
-    if (PHOTON && tile_sort && tile + li < n) li = A.perm[tile + li];
-    const unsigned slot = tile + li;
-    bool found = false;
-    unsigned p = 0;
-    float3 d = f3(0, 0, 0);
-    HitRec h;
-    if (slot < n) {
-      float4 b, hr;
-      if (permuted) {  // sorted payload written by k_sort_scatter: direction + path id, hit record
-        hr = A.sorted[2 * (size_t)slot];
-        b = A.sorted[2 * (size_t)slot + 1];
-        p = (unsigned)__float_as_int(b.w);
-      } else {
-        b = qd_in[slot];
-        hr = A.hit[slot];
-        p = (unsigned)__float_as_int(qo_in[slot].w);
-      }
-      d = f3(b);
-      h.t = hr.x;
-      h.u = hr.y;
-      h.v = hr.z;
-      h.gid = __float_as_int(hr.w);
-      found = h.gid >= 0;
+    if (PHOTON && tile_sort) {
+      if (threadIdx.x == 0) s_tile = atomicAdd(tile_cursor, 1u);
+      __syncthreads();
+      tile = s_tile * TILE;  // (the previous tile's closing barrier keeps s_tile stable until everyone has read it)
     }
-    // compacted index j of this hit (warp-aggregated)
-    const unsigned mask = __ballot_sync(kFull, found);
-    unsigned j = 0;
-    if (mask) {
-      unsigned j0 = 0;
-      if (lane == (unsigned)(__ffs(mask) - 1)) j0 = atomicAdd(A.q_count + kQHits0 + seg, (unsigned)__popc(mask));
-      j0 = __shfl_sync(kFull, j0, __ffs(mask) - 1);
-      j = j0 + __popc(mask & ((1u << lane) - 1u));
-    }
-    if (slot < n && !found) {
-      // Renderer.cpp:154-160: a miss ends the path and contributes Vec3f(0) from this segment on.  The segments' colours
-      // live in their own arrays and are added -- c0 + (c1 + c2), Renderer.cpp:168 -- and clamped by k_resolve, so a
-      // path that ends here only zeroes the terms it will never write (no read-modify-write of earlier ones).
-      const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (seg == 0) A.col0[p] = zero;  // w = 0: posIntersectionFound = false
-      if (MODE == 1) {
-        if (seg <= 1) A.col1[p] = zero;
-        A.col2[p] = zero;
-      }
-    }
-    if (found) {
-      n_hit++;
-      int pixel, sample;
-      Rng g;
-      // words consumed before this segment: 4 (jitter), then per earlier segment 2 per light + 4 (hemisphere);
-      // the photon gather draws nothing (Renderer.cpp:63-104)
-      g.init(path_stream_key(A, p, pixel, sample),
-             4u + (PHOTON ? 4u : 2u * (unsigned)S.num_lights + 4u) * (unsigned)seg);
-      float3 nrm, P, tp0, te1, te2;
-      int mesh;
-      hit_geometry(S, h, nrm, P, mesh, tp0, te1, te2);
-      const DMaterial m = S.mats[mesh];
-      A.hit_path[j] = (int)p;
-      if (PHOTON && A.knn_out != nullptr) {  // gathered by k_knn_gather, per ray slot of the segment
-        float3 c = shade_photon_from(A.knn_out[slot], d, nrm, m, A.k, A.num_photons);
-        A.contrib[j] = make_float4(c.x, c.y, c.z, 0.f);
-      } else if (PHOTON) {
-        n_knn++;
-        unsigned long long* sc;
-        int ks;
-        int* kst;
-        if (GSC) {
-          sc = A.knn_scratch + (size_t)blockIdx.x * kBlock + threadIdx.x;
-          ks = A.knn_scratch_stride;
-          kst = (int*)s_knn + threadIdx.x;
+    if (tile >= n) break;
+    if (PHOTON && tile_sort) shade_tile_order(A, tile, n, R, permuted, s_knn);
+    for (int r = 0; r < R; r++) {
+      unsigned li = (unsigned)r * kBlock + threadIdx.x;
+      // (written above by this very thread; slots past n sort last, so the first n - tile entries are the valid ones)
+      if (PHOTON && tile_sort && tile + li < n) li = A.perm[tile + li];
+      const unsigned slot = tile + li;
+      bool found = false;
+      unsigned p = 0;
+      float3 d = f3(0, 0, 0);
+      HitRec h;
+      if (slot < n) {
+        float4 b, hr;
+        if (permuted) {  // sorted payload written by k_sort_scatter: direction + path id, hit record
+          hr = A.sorted[2 * (size_t)slot];
+          b = A.sorted[2 * (size_t)slot + 1];
+          p = (unsigned)__float_as_int(b.w);
         } else {
-          sc = s_knn + threadIdx.x;
-          ks = kBlock;
-          kst = (int*)(s_knn + A.k * kBlock) + threadIdx.x;
+          b = qd_in[slot];
+          hr = A.hit[slot];
+          p = (unsigned)__float_as_int(qo_in[slot].w);
         }
-        float3 c = shade_photon(S, d, nrm, P, m, A.k, A.num_photons, A.knn_exact, sc, ks, kst, n_visits);
-        A.contrib[j] = make_float4(c.x, c.y, c.z, 0.f);  // nl == 1: slot(j, 0) = j; no shadow ray, no occlusion byte
-      } else {
-        // Renderer.cpp:49-60: per light 2 uniforms, the shadow ray, and (eagerly) radiance * bsdf
-        const BsdfFrame bf = bsdf_frame(m, nrm, v_neg(d));
-        A.hit_p[j] = make_float4(P.x, P.y, P.z, 0.f);
-#pragma unroll
-        for (int l = 0; l < (NLT > 0 ? NLT : (int)nl); l++) {
-          const unsigned s = shadow_slot(j, (unsigned)l, nl);
-          const DLight& L = light_at(S, l);
-          float3 to_light = v_sub(light_rand_area_position(L, g), P);
-          float3 c = v_mul(light_evaluate(L, P), evaluate_color_response(m, bf, to_light));
-          // Any-hit is an OR over all triangles (Renderer.cpp:52-55, RayTracer.h:40), so testing the triangle the ray
-          // starts on first cannot change the answer: 12-15 % of the shadow rays end here (shadow acne is part of
-          // the reference image), at this kernel's ~97 % lane use instead of the traversal's ~65 %.
-          bool self = false;
-          if (A.own_tri) {
-            float tu, tv, tt;
-            self = mt_intersect(P, to_light, tp0, te1, te2, tu, tv, tt) && tt > 0.f && tt < FLT_MAX;
-          }
-          A.sh_d[s] = make_float4(to_light.x, to_light.y, to_light.z, self ? 1.f : 0.f);
-          A.contrib[s] = make_float4(c.x, c.y, c.z, 0.f);
-          if (self) A.occ[s] = 1;
+        d = f3(b);
+        h.t = hr.x;
+        h.u = hr.y;
+        h.v = hr.z;
+        h.gid = __float_as_int(hr.w);
+        found = h.gid >= 0;
+      }
+      // compacted index j of this hit (warp-aggregated)
+      const unsigned mask = __ballot_sync(kFull, found);
+      unsigned j = 0;
+      if (mask) {
+        unsigned j0 = 0;
+        if (lane == (unsigned)(__ffs(mask) - 1)) j0 = atomicAdd(A.q_count + kQHits0 + seg, (unsigned)__popc(mask));
+        j0 = __shfl_sync(kFull, j0, __ffs(mask) - 1);
+        j = j0 + __popc(mask & ((1u << lane) - 1u));
+      }
+      if (slot < n && !found) {
+        // Renderer.cpp:154-160: a miss ends the path and contributes Vec3f(0) from this segment on.  The segments' colours
+        // live in their own arrays and are added -- c0 + (c1 + c2), Renderer.cpp:168 -- and clamped by k_resolve, so a
+        // path that ends here only zeroes the terms it will never write (no read-modify-write of earlier ones).
+        const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (seg == 0) A.col0[p] = zero;  // w = 0: posIntersectionFound = false
+        if (MODE == 1) {
+          if (seg <= 1) A.col1[p] = zero;
+          A.col2[p] = zero;
         }
       }
-      if (MODE == 1 && seg < 2) {  // Renderer.cpp:164-166: bounce
-        float3 nd = hsphere_uniform_sample(g, nrm);
-        qo_out[j] = make_float4(P.x, P.y, P.z, __int_as_float((int)p));
-        qd_out[j] = make_float4(nd.x, nd.y, nd.z, 0.f);
+      if (found) {
+        n_hit++;
+        int pixel, sample;
+        Rng g;
+        // words consumed before this segment: 4 (jitter), then per earlier segment 2 per light + 4 (hemisphere);
+        // the photon gather draws nothing (Renderer.cpp:63-104)
+        g.init(path_stream_key(A, p, pixel, sample),
+               4u + (PHOTON ? 4u : 2u * (unsigned)S.num_lights + 4u) * (unsigned)seg);
+        float3 nrm, P, tp0, te1, te2;
+        int mesh;
+        hit_geometry(S, h, nrm, P, mesh, tp0, te1, te2);
+        const DMaterial m = S.mats[mesh];
+        A.hit_path[j] = (int)p;
+        if (PHOTON && A.knn_out != nullptr) {  // gathered by k_knn_gather, per ray slot of the segment
+          float3 c = shade_photon_from(A.knn_out[slot], d, nrm, m, A.k, A.num_photons);
+          A.contrib[j] = make_float4(c.x, c.y, c.z, 0.f);
+        } else if (PHOTON) {
+          n_knn++;
+          unsigned long long* sc;
+          int ks;
+          int* kst;
+          if (GSC) {
+            sc = A.knn_scratch + (size_t)blockIdx.x * kBlock + threadIdx.x;
+            ks = A.knn_scratch_stride;
+            kst = (int*)s_knn + threadIdx.x;
+          } else {
+            sc = s_knn + threadIdx.x;
+            ks = kBlock;
+            kst = (int*)(s_knn + A.k * kBlock) + threadIdx.x;
+          }
+          float3 c = shade_photon(S, d, nrm, P, m, A.k, A.num_photons, A.knn_exact, sc, ks, kst, n_visits);
+          A.contrib[j] = make_float4(c.x, c.y, c.z, 0.f);  // nl == 1: slot(j, 0) = j; no shadow ray, no occlusion byte
+        } else {
+          // Renderer.cpp:49-60: per light 2 uniforms, the shadow ray, and (eagerly) radiance * bsdf
+          const BsdfFrame bf = bsdf_frame(m, nrm, v_neg(d));
+          A.hit_p[j] = make_float4(P.x, P.y, P.z, 0.f);
+  #pragma unroll
+          for (int l = 0; l < (NLT > 0 ? NLT : (int)nl); l++) {
+            const unsigned s = shadow_slot(j, (unsigned)l, nl);
+            const DLight& L = light_at(S, l);
+            float3 to_light = v_sub(light_rand_area_position(L, g), P);
+            float3 c = v_mul(light_evaluate(L, P), evaluate_color_response(m, bf, to_light));
+            // Any-hit is an OR over all triangles (Renderer.cpp:52-55, RayTracer.h:40), so testing the triangle the ray
+            // starts on first cannot change the answer: 12-15 % of the shadow rays end here (shadow acne is part of
+            // the reference image), at this kernel's ~97 % lane use instead of the traversal's ~65 %.
+            bool self = false;
+            if (A.own_tri) {
+              float tu, tv, tt;
+              self = mt_intersect(P, to_light, tp0, te1, te2, tu, tv, tt) && tt > 0.f && tt < FLT_MAX;
+            }
+            A.sh_d[s] = make_float4(to_light.x, to_light.y, to_light.z, self ? 1.f : 0.f);
+            A.contrib[s] = make_float4(c.x, c.y, c.z, 0.f);
+            if (self) A.occ[s] = 1;
+          }
+        }
+        if (MODE == 1 && seg < 2) {  // Renderer.cpp:164-166: bounce
+          float3 nd = hsphere_uniform_sample(g, nrm);
+          qo_out[j] = make_float4(P.x, P.y, P.z, __int_as_float((int)p));
+          qd_out[j] = make_float4(nd.x, nd.y, nd.z, 0.f);
+        }
       }
     }
-   }
-   if (PHOTON && tile_sort) __syncthreads();  // the next tile's sort reuses the queries' shared memory
+    if (PHOTON && tile_sort) __syncthreads();  // the next tile's sort reuses the queries' shared memory
   }
   for (int off = 16; off > 0; off >>= 1) {
     n_hit += __shfl_xor_sync(kFull, n_hit, off);
