@@ -107,6 +107,7 @@ struct rt_ctx {
   int knn_scratch_threads = 0;
   int knn_gather = 0;  // RT_KNN_GATHER=1: the photon queries run in the persistent gather kernel instead of inside k_shade
   int sort_seg0 = 1;   // RT_SORT_SEG0=0: the photon gather of segment 0 keeps the pixel-tile order of the primary hits
+  bool tile_force = false;  // RT_SHADE_TILE_FORCE=1: keep the tile size even when the frame has few queries (tests)
   int tile_rounds = 8;  // RT_SHADE_TILE_ROUNDS=r (power of two): the photon k_shade orders each tile of r * 128 slots by fine Morton code
   int sort_bits = -1;  // RT_SORT_BITS=0|5|6|7: Morton cells per axis = 2^bits (0: the 32^3 shared-memory counting sort);
                        // default: 6 with a photon map (k-NN queries gain more from neighbours than the finer sort costs), else 0
@@ -356,7 +357,7 @@ void fill_args(rt_ctx* c, RenderArgs& a, const int* pix_map, int npix, bool use_
   if (use_photons && c->tile_rounds > 1 && a.knn_out == nullptr && a.perm != nullptr) {
     int rounds = 1;
     while (2 * rounds <= c->tile_rounds && knn_smem_bytes(p.k, c->kd_height + 1) >= (size_t)2 * rounds * kBlock * 8) rounds *= 2;
-    a.tile_rounds = rounds > 1 ? rounds : 0;
+    a.tile_rounds = rounds > 1 ? (c->tile_force ? -rounds : rounds) : 0;
   }
   const float cells = a.sort_bits > 0 ? (float)(1 << a.sort_bits) : (float)kSortGrid;
   a.sort_inv_cell = make_float3(cells / std::max(c->bounds_hi.x - c->bounds_lo.x, 1e-20f),
@@ -835,6 +836,7 @@ int rt_create(const rt_scene* s, const rt_params* p, int device, rt_ctx** out) {
   if (const char* e = getenv("RT_KNN_GATHER")) c->knn_gather = atoi(e) != 0;
   if (const char* e = getenv("RT_SORT_SEG0")) c->sort_seg0 = atoi(e) != 0;
   if (const char* e = getenv("RT_SORT_SEGS")) c->sort_segs = atoi(e) & 7;
+  if (const char* e = getenv("RT_SHADE_TILE_FORCE")) c->tile_force = atoi(e) != 0;
   if (const char* e = getenv("RT_SHADE_TILE_ROUNDS")) c->tile_rounds = std::min(std::max(atoi(e), 0), 64);
   if (const char* e = getenv("RT_SORT_BITS")) c->sort_bits = std::min(std::max(atoi(e), 0), 7);
   if (!(extent < 1e8f)) {  // keeps lo * safe_inv(d) finite in the slab test (rt_device.cuh)

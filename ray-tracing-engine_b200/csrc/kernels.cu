@@ -1202,7 +1202,9 @@ void launch_shade(const RenderArgs& a, int seg, int grid, cudaStream_t st) {
     // sample per pixel, half of the SMs) idles -- -m 0 -N 1 -p 500000 -k 50 went from 3.7 to 9.0 ms with 1024-slot tiles
     RenderArgs b = a;
     const long long slots = (long long)a.npix * a.nsamp;
-    while (b.tile_rounds > 1 && slots < 4LL * grid * kBlock * b.tile_rounds) b.tile_rounds /= 2;
+    if (b.tile_rounds < 0) b.tile_rounds = -b.tile_rounds;  // forced (tests: small frames must take the tiled path too)
+    else
+      while (b.tile_rounds > 1 && slots < 4LL * grid * kBlock * b.tile_rounds) b.tile_rounds /= 2;
     if (a.mode == 0) {
       if (g) k_shade<0, true, 0, true><<<grid, kBlock, sm, st>>>(b, seg);
       else k_shade<0, true, 0, false><<<grid, kBlock, sm, st>>>(b, seg);

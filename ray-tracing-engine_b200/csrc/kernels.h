@@ -83,6 +83,7 @@ struct RenderArgs {
                              // kSortFineMax + 2 counters followed by kSortFineTiles tile sums of the scan
   int sort_bits;             // 0: 32^3 cells counted in shared memory; 6 / 7: (2^bits)^3 cells, histogram in global memory
   int tile_rounds;           // photon k_shade: > 1: order every tile of tile_rounds * kBlock slots by fine Morton code
+                             // (host side only: negative = that many rounds whatever the amount of work, see launch_shade)
   float sort_key_scale;      // 1024 / cells per axis: sort_inv_cell * this maps a coordinate to the 10-bit fine grid
   float3 sort_lo;            // scene bounds
   float3 sort_inv_cell;      // cells per axis / extent per axis

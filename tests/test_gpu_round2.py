@@ -323,9 +323,10 @@ def test_query_order_switches_do_not_change_the_frame(rt, gold, monkeypatch):
     candidate structures, and in a plain path-traced frame as well."""
     scene = rt.Scene.load(scene_path("stock"))
     ph = gold("photons.npz")["list"]
-    for k, mode, photons in ((10, 1, 3000), (50, 0, 3000), (0, 1, 0)):
+    monkeypatch.setenv("RT_SHADE_TILE_FORCE", "1")  # a frame this small would otherwise shrink its tiles to nothing
+    for k, mode, photons in ((10, 1, 3000), (50, 0, 3000), (80, 0, 3000), (1, 1, 3000), (0, 1, 0)):
         ref = None
-        for bits, rounds in (("0", "0"), ("0", "8"), ("6", "0"), ("6", "8"), ("7", "4"), ("5", "16")):
+        for bits, rounds in (("0", "0"), ("0", "8"), ("6", "0"), ("6", "8"), ("7", "4"), ("5", "16"), ("6", "2")):
             monkeypatch.setenv("RT_SORT_BITS", bits)
             monkeypatch.setenv("RT_SHADE_TILE_ROUNDS", rounds)
             r = rt.Renderer(scene, 6, mode, None, photons, k or 5, seed=4, width=420, height=300)
