@@ -313,9 +313,13 @@ class Renderer:
         """The sums and the counter as one [H,W,4] float32 device buffer (a single reduce across GPUs)."""
         _capi.check(self.lib.rt_render_accumulate_packed_device(self._ctx, C.c_void_p(sum_rgbn_ptr)))
 
-    def composite_packed_device(self, num_rays, sum_rgbn_ptr: int, background):
-        """Renderer.cpp:262-265 on the packed DEVICE frame (after the multi-GPU reduce); returns [H,W,3]."""
-        out = np.ascontiguousarray(background, np.float32).copy()
+    def composite_packed_device(self, num_rays, sum_rgbn_ptr: int, background, out=None):
+        """Renderer.cpp:262-265 on the packed DEVICE frame (after the multi-GPU reduce); returns [H,W,3].
+        out: an optional caller-owned float32 [H,W,3] host frame (e.g. pinned memory) that receives the result."""
+        if out is None:
+            out = np.ascontiguousarray(background, np.float32).copy()
+        else:
+            np.copyto(out, background)
         _capi.check(self.lib.rt_composite_packed_device(self._ctx, int(num_rays), C.c_void_p(sum_rgbn_ptr),
                                                         _capi.ptr(out)))
         return out
