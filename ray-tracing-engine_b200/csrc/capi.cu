@@ -429,7 +429,7 @@ int run_batch(rt_ctx* c, RenderArgs& a, int s0, int nsamp) {
     if (a.photon && a.knn_out) SPAN(kKGather, 1, launch_knn_gather(a, seg, c->stream));
     SPAN(kKShade, 1, launch_shade(a, seg, std::max(grid_shade, 1), c->stream));
     if (!a.photon && a.nl > 0) SPAN(kKTraceAny, 1, launch_trace_any(a, seg, grid, c->stream));
-    SPAN(kKCombine, 1, launch_combine(a, seg, std::max(grid_shade, 1), c->stream));
+    if (!a.photon) SPAN(kKCombine, 1, launch_combine(a, seg, std::max(grid_shade, 1), c->stream));
   }
 #undef SPAN
   CU(cudaGetLastError());

@@ -1110,10 +1110,23 @@ __global__ void __launch_bounds__(kBlock, PHOTON ? 6 : RT_SHADE_MINB) k_shade(co
         int mesh;
         hit_geometry(S, h, nrm, P, mesh, tp0, te1, te2);
         const DMaterial m = S.mats[mesh];
-        A.hit_path[j] = (int)p;
+        if (!PHOTON) A.hit_path[j] = (int)p;
+        // PHOTON: no shadow rays, so nothing waits for an any-hit answer: the segment's colour goes straight to the
+        // path's slot -- what k_combine would do with it one launch later (`0 + contribution`, Renderer.cpp:44,59;
+        // seg 0 of -m 0 clamped, Renderer.cpp:254), without the trip through contrib[] and hit_path[]
+        auto write_photon_colour = [&](float3 c) {
+          c = v_add(f3(0.f, 0.f, 0.f), c);
+          if (seg == 0) {
+            const float3 out = MODE == 0 ? normalize_color(c) : c;
+            A.col0[p] = make_float4(out.x, out.y, out.z, 1.f);
+          } else if (seg == 1) {
+            A.col1[p] = make_float4(c.x, c.y, c.z, 0.f);
+          } else {
+            A.col2[p] = make_float4(c.x, c.y, c.z, 0.f);
+          }
+        };
         if (PHOTON && A.knn_out != nullptr) {  // gathered by k_knn_gather, per ray slot of the segment
-          float3 c = shade_photon_from(A.knn_out[slot], d, nrm, m, A.k, A.num_photons);
-          A.contrib[j] = make_float4(c.x, c.y, c.z, 0.f);
+          write_photon_colour(shade_photon_from(A.knn_out[slot], d, nrm, m, A.k, A.num_photons));
         } else if (PHOTON) {
           n_knn++;
           unsigned long long* sc;
@@ -1128,8 +1141,7 @@ __global__ void __launch_bounds__(kBlock, PHOTON ? 6 : RT_SHADE_MINB) k_shade(co
             ks = kBlock;
             kst = (int*)(s_knn + A.k * kBlock) + threadIdx.x;
           }
-          float3 c = shade_photon(S, d, nrm, P, m, A.k, A.num_photons, A.knn_exact, sc, ks, kst, n_visits);
-          A.contrib[j] = make_float4(c.x, c.y, c.z, 0.f);  // nl == 1: slot(j, 0) = j; no shadow ray, no occlusion byte
+          write_photon_colour(shade_photon(S, d, nrm, P, m, A.k, A.num_photons, A.knn_exact, sc, ks, kst, n_visits));
         } else {
           // Renderer.cpp:49-60: per light 2 uniforms, the shadow ray, and (eagerly) radiance * bsdf
           const BsdfFrame bf = bsdf_frame(m, nrm, v_neg(d));
@@ -1233,15 +1245,11 @@ __global__ void __launch_bounds__(256) k_combine(const RenderArgs A, const int s
   const unsigned n = A.q_count[kQHits0 + seg];
   const unsigned nl = NLT > 0 ? (unsigned)NLT : (unsigned)A.nl;
   for (unsigned j = blockIdx.x * 256 + threadIdx.x; j < n; j += gridDim.x * 256) {
-    float3 c = f3(0.f, 0.f, 0.f);
-    if (A.photon) {
-      c = v_add(c, f3(A.contrib[j]));
-    } else {
+    float3 c = f3(0.f, 0.f, 0.f);  // (the photon gather writes its colour in k_shade: this kernel does not run for it)
 #pragma unroll
-      for (int l = 0; l < (NLT > 0 ? NLT : (int)nl); l++) {
-        const unsigned s = shadow_slot(j, (unsigned)l, nl);
-        if (A.occ[s] == 0) c = v_add(c, f3(A.contrib[s]));
-      }
+    for (int l = 0; l < (NLT > 0 ? NLT : (int)nl); l++) {
+      const unsigned s = shadow_slot(j, (unsigned)l, nl);
+      if (A.occ[s] == 0) c = v_add(c, f3(A.contrib[s]));
     }
     const unsigned p = (unsigned)A.hit_path[j];
     // one write per hit and no read: hits of the bounce segments arrive in Morton order, so p is scattered; the path
@@ -1259,7 +1267,7 @@ __global__ void __launch_bounds__(256) k_combine(const RenderArgs A, const int s
   }
 }
 void launch_combine(const RenderArgs& a, int seg, int grid, cudaStream_t st) {
-  if (!a.photon && a.nl == 3)
+  if (a.nl == 3)
     k_combine<3><<<grid, 256, 0, st>>>(a, seg);
   else
     k_combine<0><<<grid, 256, 0, st>>>(a, seg);
