@@ -151,3 +151,13 @@ if "cfg5bits" in what:  # the 1.23 M-triangle scene (L2-latency-bound traversal)
                               kernel_ms={k: round(x, 3) for k, x in st["kernel_ms"].items() if x}, checksum=chk, hits=hits)), flush=True)
         r.close()
     os.environ.pop("RT_SORT_BITS")
+if "envab" in what:  # generic A/B of an environment switch on the cfg2 frame: PROBE_ENV="RT_X=0,1"
+    var, vals = os.environ["PROBE_ENV"].split("=")
+    for v in vals.split(","):
+        os.environ[var] = v
+        r = rt.Renderer(ex, 128, 1, seed=1)
+        ms, st, chk, hits = frames(r)
+        print(json.dumps(dict(probe="env_ab", env=f"{var}={v}", frame_ms=round(ms, 3), grays=round(st["rays"] / ms / 1e6, 3),
+                              kernel_ms={k: round(x, 3) for k, x in st["kernel_ms"].items() if x}, checksum=chk, hits=hits)), flush=True)
+        r.close()
+    os.environ.pop(var)
