@@ -41,8 +41,9 @@ constexpr int kDone = INT_MIN;    // traversal cursor value: no work (never a va
 #endif
 constexpr bool kAnyFixedOrder = RT_ANY_FIXED_ORDER != 0;  // any-hit: visit child 0 first instead of the nearer child
 constexpr int kRefillBelowDefault = 14;  // refill a warp's idle lanes when fewer lanes than this are live
-__constant__ int c_refill_below = kRefillBelowDefault;
-#define kRefillBelow c_refill_below
+__constant__ int c_refill_below = kRefillBelowDefault;          // any-hit launches
+__constant__ int c_refill_below_nearest = kRefillBelowDefault;  // nearest-hit launches (RT_REFILL_BELOW_NEAREST)
+#define kRefillBelow (ANY ? c_refill_below : c_refill_below_nearest)
 
 // ----------------------------------------------------------------------------------------------
 // k_trace: persistent warps, one ray per lane, lanes refilled from the queue as their rays finish.
@@ -475,8 +476,11 @@ static void launch_trace_t(const DScene& S, const float4* ro, const float4* rd, 
     cudaMemsetAsync(fetch, 0, sizeof(unsigned), st);
     static const int refill = getenv("RT_REFILL_BELOW") ? atoi(getenv("RT_REFILL_BELOW")) : -1;
     static bool refill_set = false;
-    if (refill >= 0 && !refill_set) {
-      cudaMemcpyToSymbol(c_refill_below, &refill, sizeof(int));
+    static const int refill_nearest =
+        getenv("RT_REFILL_BELOW_NEAREST") ? atoi(getenv("RT_REFILL_BELOW_NEAREST")) : refill;
+    if ((refill >= 0 || refill_nearest >= 0) && !refill_set) {
+      if (refill >= 0) cudaMemcpyToSymbol(c_refill_below, &refill, sizeof(int));
+      if (refill_nearest >= 0) cudaMemcpyToSymbol(c_refill_below_nearest, &refill_nearest, sizeof(int));
       refill_set = true;
     }
     // any-hit keeps no tnear column: half the stack, and the rest of the SM's 256 KB stays L1 for the BVH
