@@ -411,6 +411,10 @@ int run_batch(rt_ctx* c, RenderArgs& a, int s0, int nsamp) {
   const int persistent = c->num_sms * trace_ctas_per_sm(a.stack_depth);
   int grid = (int)std::min<long long>((paths + kBlock - 1) / kBlock, (long long)persistent);
   if (grid < 1) grid = 1;
+  // the any-hit kernel keeps no entry-distance column: its own (higher) occupancy sizes its persistent grid
+  int grid_any = (int)std::min<long long>((paths * std::max(a.nl, 1) + kBlock - 1) / kBlock,
+                                          (long long)c->num_sms * trace_any_ctas_per_sm(a.stack_depth));
+  if (grid_any < 1) grid_any = 1;
   const int grid_shade = (int)std::min<long long>((paths + kBlock - 1) / kBlock, (long long)c->num_sms * 8);
   CU(cudaMemsetAsync(c->d_qcount.p, 0, kQNum * sizeof(unsigned), c->stream));
   int rc;
@@ -428,7 +432,7 @@ int run_batch(rt_ctx* c, RenderArgs& a, int s0, int nsamp) {
       SPAN(kKSort, 3, launch_sort_hits(a, seg, c->stream));
     if (a.photon && a.knn_out) SPAN(kKGather, 1, launch_knn_gather(a, seg, c->stream));
     SPAN(kKShade, 1, launch_shade(a, seg, std::max(grid_shade, 1), c->stream));
-    if (!a.photon && a.nl > 0) SPAN(kKTraceAny, 1, launch_trace_any(a, seg, grid, c->stream));
+    if (!a.photon && a.nl > 0) SPAN(kKTraceAny, 1, launch_trace_any(a, seg, grid_any, c->stream));
     if (!a.photon) SPAN(kKCombine, 1, launch_combine(a, seg, std::max(grid_shade, 1), c->stream));
   }
 #undef SPAN

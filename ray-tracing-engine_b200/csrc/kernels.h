@@ -111,7 +111,8 @@ void launch_trace_nearest(const RenderArgs& a, int seg, int grid_ctas, cudaStrea
 void launch_shade(const RenderArgs& a, int seg, int grid_ctas, cudaStream_t st);
 void launch_trace_any(const RenderArgs& a, int seg, int grid_ctas, cudaStream_t st);
 void launch_combine(const RenderArgs& a, int seg, int grid_ctas, cudaStream_t st);
-int trace_ctas_per_sm(int stack_depth);
+int trace_ctas_per_sm(int stack_depth);      // resident CTAs per SM: nearest-hit kernel
+int trace_any_ctas_per_sm(int stack_depth);  // ... any-hit kernel (smaller stack)
 size_t trace_smem_bytes(int stack_depth);
 
 void launch_resolve(const float4* col0, const float4* col1, const float4* col2, int mode, int npix, int nsamp,
