@@ -1246,6 +1246,19 @@ void launch_shade(const RenderArgs& a, int seg, int grid, cudaStream_t st) {
     return;
   }
   const bool three = a.scene.num_lights == 3;
+  {  // grid-stride kernel: launch exactly what is resident (RT_SHADE_MINB CTAs per SM unless the registers say otherwise)
+    static int occ[2][2] = {{0, 0}, {0, 0}};
+    int& o = occ[a.mode == 1][three];
+    if (o == 0) {
+      if (a.mode == 0 && three) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_shade<0, false, 3, false>, kBlock, 0);
+      if (a.mode == 0 && !three) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_shade<0, false, 0, false>, kBlock, 0);
+      if (a.mode == 1 && three) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_shade<1, false, 3, false>, kBlock, 0);
+      if (a.mode == 1 && !three) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_shade<1, false, 0, false>, kBlock, 0);
+      if (o < 1) o = 1;
+    }
+    const long long blocks = ((long long)a.npix * a.nsamp + kBlock - 1) / kBlock;
+    grid = (int)std::max<long long>(1, std::min<long long>(blocks, (long long)(a.num_sms > 0 ? a.num_sms : 148) * o));
+  }
   if (a.mode == 0) {
     if (three) k_shade<0, false, 3, false><<<grid, kBlock, 0, st>>>(a, seg);
     else k_shade<0, false, 0, false><<<grid, kBlock, 0, st>>>(a, seg);
